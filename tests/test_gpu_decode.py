@@ -1,0 +1,191 @@
+"""Parity of the CUDA decode path (through the C ABI) against the CPU oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import open_oracle_graph, random_graph
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_csr(g, first=0, last=None):
+    off, succ = g.decode_range(first, last)
+    return off.cpu().numpy().astype(np.uint64), succ.cpu().numpy().view(np.uint32)
+
+
+def test_native_library_is_the_one_running(W, gpu):
+    assert W.cuda_available()
+    before = W.kernel_launches()
+    import torch
+    assert torch.cuda.get_device_capability(0)[0] >= 10, "sm_100a code needs a Blackwell GPU"
+    return before
+
+
+def test_golden_head_full_decode(W, O, gpu, head):
+    g = W.ANSBvGraphSeq.load(head["base"])
+    k0 = W.kernel_launches()
+    off, succ = gpu_csr(g)
+    assert W.kernel_launches() > k0
+    assert (off == head["offsets"]).all()
+    assert (succ == head["succ"]).all()
+    # end to end through the host-buffer entry point
+    off2, succ2 = g.decode_range_host()
+    assert (off2 == head["offsets"]).all() and (succ2 == head["succ"]).all()
+
+
+def test_packed_tables_equal_reference_decoder_tables(W, O, gpu, head):
+    """K3 parity: per slot (freq, cumul_freq, quasi_folded) == ANSModel4Decoder::new (model4decoder.rs:18-68)."""
+    g = W.ANSBvGraph.load(head["base"])
+    og = O.OracleGraph.load(head["base"])
+    for c in range(9):
+        ours = g.debug_expand_table(c)
+        ref = og.decoder_table(c)
+        assert ours.size == ref.size
+        for f in ("freq", "cumul_freq", "quasi_folded"):
+            assert (ours[f] == ref[f]).all(), (c, f)
+
+
+@pytest.mark.parametrize("case", ["dummy", "folding", "zipf", "interleaved"])
+def test_symbol_decoder_matches_oracle(W, O, gpu, case):
+    """ANSDecoder::decode on the device, one symbol at a time (tests/compressor_tests.rs)."""
+    rng = np.random.default_rng(0)
+    if case == "dummy":
+        comps, syms = [0] * 10, [1, 1, 1, 2, 2, 2, 3, 3, 4, 5]
+    elif case == "folding":
+        comps, syms = [0] * 3, [1000, 1000, 2000]
+    elif case == "zipf":
+        syms = np.minimum(rng.zipf(1.2, 100_000), 1 << 30)
+        comps = np.zeros(syms.size, np.uint8)
+    else:
+        syms = np.concatenate([np.minimum(rng.zipf(1.3, 30_000), 1 << 30), rng.integers(0, 6, 30_000),
+                               np.minimum(rng.zipf(1.1, 30_000), (1 << 47))])
+        comps = np.concatenate([np.full(30_000, c, np.uint8) for c in (0, 2, 8)])
+        p = rng.permutation(syms.size)
+        syms, comps = syms[p], comps[p]
+    comps = np.asarray(comps, np.uint8)
+    syms = np.asarray(syms, np.uint64)
+    og = O.OracleGraph()
+    og.build_model(comps, syms)
+    og.encode_symbols(comps, syms)
+    inf = og.info()
+    # a graph handle needs phases: give it a single dummy node
+    g = W.open_mem(og.tables(), og.stream(), inf["state"], 1, 0, 0, 0, [inf["state"]], [inf["stream_len"]])
+    out, ptr, state = g.debug_decode_symbols(comps[::-1])
+    ref, rptr, rstate = og.decode_symbols(comps[::-1])
+    assert (out == ref).all() and (out[::-1] == syms).all()
+    assert (ptr, state) == (rptr, rstate) == (0, 65536)
+
+
+GRAPH_CASES = [
+    # n, mean_deg, (window, max_ref, min_interval), seed
+    (6, 0, (7, 3, 2), 0),          # the 6-node dummy graph of tests/test_bvgraph.rs:23
+    (1, 3, (7, 3, 4), 1),
+    (2000, 8, (7, 3, 4), 2),       # CLI defaults
+    (2000, 8, (7, 3, 2), 3),       # what the reference's tests use
+    (3000, 12, (16, 1 << 30, 4), 4),  # "-hc": wide window, unbounded reference chains
+    (2000, 8, (0, 3, 4), 5),       # no references
+    (2000, 8, (7, 3, 0), 6),       # no intervals
+    (2000, 8, (1, 1, 2), 7),
+    (40000, 10, (7, 3, 4), 8),
+]
+
+
+def make_case(n, deg, seed):
+    if n == 6:
+        lists = [[2, 3], [5], [], [0, 1, 2], [1, 2, 3, 4, 5], [0]]
+        off = np.cumsum([0] + [len(x) for x in lists]).astype(np.uint64)
+        return off, np.array([x for l in lists for x in l], np.uint32)
+    return random_graph(np.random.default_rng(seed), n, deg)
+
+
+@pytest.mark.parametrize("n,deg,params,seed", GRAPH_CASES)
+def test_graph_decode_matches_oracle(W, O, gpu, n, deg, params, seed):
+    """tests/test_bvgraph.rs: successors(ANS graph) == successors(original), for every node."""
+    off, succ = make_case(n, deg, seed)
+    og = O.OracleGraph.store_csr(off, succ, *params)
+    o_off, o_succ, end = og.decode_seq()
+    assert (o_off == off).all() and (o_succ == succ).all()
+    g = open_oracle_graph(W, og)
+    d_off, d_succ = gpu_csr(g)
+    assert (d_off == off).all()
+    assert (d_succ == succ).all()
+
+
+def test_empty_and_all_dangling_graphs(W, O, gpu):
+    for n in (0, 1, 50):
+        off = np.zeros(n + 1, np.uint64)
+        og = O.OracleGraph.store_csr(off, np.zeros(0, np.uint32), 7, 3, 4)
+        g = open_oracle_graph(W, og)
+        d_off, d_succ = gpu_csr(g)
+        assert (d_off == off).all() and d_succ.size == 0
+
+
+def test_sub_ranges_with_halo(W, O, gpu):
+    """Node-range decode (what one rank of a sharded decode does): references leaving the range on the
+    left are resolved by re-decoding the predecessor halo."""
+    off, succ = make_case(30000, 10, 21)
+    for params in ((7, 3, 4), (16, 1 << 30, 4)):
+        og = O.OracleGraph.store_csr(off, succ, *params)
+        g = open_oracle_graph(W, og)
+        rng = np.random.default_rng(2)
+        cuts = sorted(set([0, 30000] + list(rng.integers(1, 30000, 9))))
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            d_off, d_succ = gpu_csr(g, int(a), int(b))
+            assert (d_off == off[a:b + 1] - off[a]).all(), (a, b)
+            assert (d_succ == succ[off[a]:off[b]]).all(), (a, b)
+        d_off, d_succ = gpu_csr(g, 12345, 12346)
+        assert (d_succ == succ[off[12345]:off[12346]]).all()
+
+
+def test_shard_open_decodes_only_its_range(W, O, gpu, head):
+    """wga_open_shard: only the stream span / phases of the shard are uploaded."""
+    n = 30000
+    for a, b in ((0, 7000), (7000, 19000), (19000, n)):
+        # widen the resident range to the left so the halo is available
+        g = W.ANSBvGraph.load(head["base"], shard=(max(0, a - 64), b))
+        d_off, d_succ = gpu_csr(g, a, b)
+        assert (d_off == head["offsets"][a:b + 1] - head["offsets"][a]).all()
+        assert (d_succ == head["succ"][head["offsets"][a]:head["offsets"][b]]).all()
+        assert g.compressed_bytes() < W.ANSBvGraph.load(head["base"], host_only=True).compressed_bytes()
+
+
+def test_iter_and_successor_api(W, O, gpu, head):
+    g = W.ANSBvGraph.load(head["base"])
+    assert g.num_nodes() == 30000 and g.num_arcs_hint() == head["succ"].size
+    g.ITER_CHUNK_NODES = 7000
+    for v, s in g.iter(0, 15000):
+        assert (s == head["succ"][head["offsets"][v]:head["offsets"][v + 1]]).all()
+
+
+@pytest.mark.parametrize("kind,n,deg", [("web", 300_000, 34.3), ("social", 200_000, 35.3)])
+def test_synthetic_shapes_roundtrip(W, O, gpu, kind, n, deg):
+    """Bench-shaped graphs at a size the oracle finishes in seconds: GPU decode == oracle decode == source."""
+    off, succ = W.synth_graph(kind, n, deg, seed=0x5EED0000)
+    og = O.OracleGraph.store_csr(off, succ, 7, 3, 4)
+    g = open_oracle_graph(W, og)
+    d_off, d_succ = gpu_csr(g)
+    assert (d_off == off).all() and (d_succ == succ).all()
+    o_off, o_succ, end = og.decode_seq()
+    assert (o_succ == d_succ).all() and end == (0, 65536)
+
+
+def test_corrupt_stream_is_reported_not_faulted(W, O, gpu):
+    """The reference panics on corrupt input (slice index); the kernels set an error flag instead."""
+    import torch
+    off, succ = make_case(3000, 8, 33)
+    og = O.OracleGraph.store_csr(off, succ, 7, 3, 4)
+    inf = og.info()
+    st, pt = og.phases()
+    stream = og.stream().copy()
+    rng = np.random.default_rng(0)
+    stream[rng.integers(0, stream.size, stream.size // 3)] ^= 0xFFFF
+    g = W.open_mem(og.tables(), stream, inf["state"], inf["n"], 7, 4, inf["arcs"], st, pt)
+    d_off = torch.zeros(3001, dtype=torch.int64, device="cuda")
+    d_succ = torch.zeros(succ.size + 1024, dtype=torch.int32, device="cuda")
+    ws = torch.zeros(g.workspace_size(0, 3000), dtype=torch.uint8, device="cuda")
+    with pytest.raises(W.WgaError) as e:
+        g.decode_range_into(0, 3000, d_off, d_succ, ws, want_arcs=True)
+    assert e.value.code in (-5, -6, -7)
+    # the device is still healthy afterwards
+    g2 = open_oracle_graph(W, og)
+    o2, s2 = gpu_csr(g2)
+    assert (s2 == succ).all()

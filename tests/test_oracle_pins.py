@@ -1,0 +1,140 @@
+"""Pins the CPU oracle: the reference's own tests (round-trip properties), the golden cnr-2000 files
+and the SURVEY.md 8a regression anchors.  CPU only."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, REF_CNR
+
+needs_ref = pytest.mark.skipif(not os.path.exists(REF_CNR + ".graph"), reason="/root/reference not mounted")
+
+
+def roundtrip(O, comps, syms):
+    g = O.OracleGraph()
+    g.build_model(comps, syms)
+    g.encode_symbols(comps, syms)
+    out, ptr, state = g.decode_symbols(np.asarray(comps)[::-1])
+    return g, out[::-1], ptr, state
+
+
+def test_decodes_correctly_single_dummy_sequence(O):  # tests/compressor_tests.rs:14-43
+    src = [1, 1, 1, 2, 2, 2, 3, 3, 4, 5]
+    g, dec, ptr, state = roundtrip(O, [0] * 10, src)
+    assert list(dec) == src
+    assert (ptr, state) == (0, 65536)
+    t = g.table(0)  # SURVEY 8a anchor
+    assert (t["frame_size"], t["fidelity"], t["radix"]) == (7, 1, 3)
+    assert list(t["entries"]["freq"]) == [0, 38, 38, 26, 13, 13]
+    assert list(t["entries"]["cumul_freq"]) == [0, 0, 38, 76, 102, 115]
+    assert g.info()["state"] == 3431671 and list(g.stream()) == [21212]
+
+
+def test_decodes_correctly_dummy_sequence_with_folding(O):  # tests/compressor_tests.rs:45-76
+    src = [1000, 1000, 2000]
+    g, dec, ptr, state = roundtrip(O, [0] * 3, src)
+    assert list(dec) == src
+    t = g.table(0)
+    assert (t["frame_size"], t["fidelity"], t["radix"]) == (16, 10, 1)
+    assert t["entries"]["freq"][1000] == 43691
+    assert (t["entries"]["freq"][1512], t["entries"]["cumul_freq"][1512]) == (21845, 43691)
+    assert g.info()["state"] == 699053 and g.stream().size == 0
+
+
+def zipf_symbols(seed, a, n=200_000, maximum=1 << 30):
+    rng = np.random.default_rng(seed)
+    x = rng.zipf(a, n)
+    return np.minimum(x, maximum).astype(np.uint64)
+
+
+def test_decoder_decodes_correctly_real_sequence(O):  # tests/compressor_tests.rs:78-109 (Zipf 1.2, up to 2^30)
+    src = zipf_symbols(0, 1.2)
+    g, dec, ptr, state = roundtrip(O, np.zeros(src.size, np.uint8), src)
+    assert (dec == src).all() and (ptr, state) == (0, 65536)
+
+
+def test_decodes_correctly_dummy_sequences(O):  # tests/compressor_tests.rs:111-152
+    a = [1, 1, 1, 2, 2, 2, 3, 3, 4, 5]
+    b = [1, 3, 3, 3, 2, 2, 3, 3, 4, 5]
+    comps = [0, 2] * 10
+    syms = [x for p in zip(a, b) for x in p]
+    g, dec, ptr, state = roundtrip(O, comps, syms)
+    assert list(dec) == syms
+    assert g.info()["state"] == 41903996 and list(g.stream()) == [37316, 54892]  # SURVEY 8a anchor
+
+
+def test_decodes_correctly_real_interleaved_sequences_with_different_frame_sizes(O):  # :154-213
+    rng = np.random.default_rng(7)
+    parts = [(0, zipf_symbols(1, 1.3, 60_000)), (2, zipf_symbols(2, 1.2, 60_000)), (4, np.random.default_rng(3).integers(0, 6, 60_000).astype(np.uint64))]
+    comps = np.concatenate([np.full(s.size, c, np.uint8) for c, s in parts])
+    syms = np.concatenate([s for _, s in parts])
+    perm = rng.permutation(syms.size)
+    comps, syms = comps[perm], syms[perm]
+    g, dec, ptr, state = roundtrip(O, comps, syms)
+    assert (dec == syms).all() and (ptr, state) == (0, 65536)
+    assert len({g.table(c)["frame_size"] for c in (0, 2, 4)}) > 1
+
+
+def test_decodes_correctly_dummy_graph(O):  # tests/test_bvgraph.rs:23-101 : BvComp::new(_, 7, 3, 2, 0)
+    lists = [[2, 3], [5], [], [0, 1, 2], [1, 2, 3, 4, 5], [0]]
+    off = np.cumsum([0] + [len(x) for x in lists]).astype(np.uint64)
+    succ = np.array([x for l in lists for x in l], np.uint32)
+    g = O.OracleGraph.store_csr(off, succ, 7, 3, 2)
+    for v, l in enumerate(lists):
+        assert list(g.successors(v)) == l
+    o2, s2, end = g.decode_seq()
+    assert (o2 == off).all() and (s2 == succ).all() and end == (0, 65536)
+
+
+def test_golden_head_fixture(O, head):
+    """The committed .ans/.pointers/.states decode back to the committed CSR, sequentially and by node."""
+    g = O.OracleGraph.load(head["base"])
+    off, succ, end = g.decode_seq()
+    assert (off == head["offsets"]).all() and (succ == head["succ"]).all() and end == (0, 65536)
+    rng = np.random.default_rng(0)
+    for v in rng.integers(0, g.info()["n"], 300):
+        assert (g.successors(int(v)) == head["succ"][head["offsets"][v]:head["offsets"][v + 1]]).all()
+    # decoding node v from its phase ends exactly at the phase of v+1 (SURVEY 8c invariant)
+    states, pointers = g.phases()
+    n = g.info()["n"]
+    assert (np.diff(pointers.astype(np.int64)) >= 0).all() and pointers[-1] == g.info()["stream_len"]
+    comps, syms = head["comps"], head["syms"]
+    starts = np.flatnonzero(comps == 0)
+    for v in (0, 1, 17, n - 2):
+        a, b = starts[v], starts[v + 1]
+        out, ptr, st = g.decode_symbols(comps[a:b], int(pointers[n - 1 - v]), int(states[n - 1 - v]))
+        assert (out == syms[a:b]).all()
+        assert (ptr, st) == (int(pointers[n - 2 - v]), int(states[n - 2 - v]))
+
+
+@needs_ref
+def test_cnr2000_golden_graph_and_ef(O):
+    """BV reader vs the reference's golden files: arcs/nodes from .properties, bit offsets from .ef."""
+    off, succ, bits = O.read_bvgraph(REF_CNR)
+    assert len(off) - 1 == 325557 and len(succ) == 3216152
+    ef = O.ef_read(REF_CNR + ".ef")
+    assert (ef == bits).all()
+    anchors = json.load(open(os.path.join(GOLDEN, "cnr2000_full.json")))
+    assert hashlib.sha256(off.tobytes() + succ.tobytes()).hexdigest() == anchors["graph"]["csr_sha256"]
+
+
+@needs_ref
+@pytest.mark.parametrize("params", [(7, 3, 4), (7, 3, 2)])
+def test_decodes_correctly_sequential_and_random_access_graph(O, params):
+    """tests/test_bvgraph.rs:105-154 on cnr-2000 (the reference uses 7/3/2), plus the SURVEY anchors."""
+    off, succ, _ = O.read_bvgraph(REF_CNR)
+    g = O.OracleGraph.store_csr(off, succ, *params)
+    o2, s2, end = g.decode_seq()
+    assert (o2 == off).all() and (s2 == succ).all() and end == (0, 65536)
+    rng = np.random.default_rng(1)
+    for v in rng.integers(0, len(off) - 1, 2000):
+        assert (g.successors(int(v)) == succ[off[v]:off[v + 1]]).all()
+    anchors = json.load(open(os.path.join(GOLDEN, "cnr2000_full.json")))["w%d_r%d_l%d" % params]
+    assert g.info()["stream_len"] * 2 == anchors["stream_bytes"] == {(7, 3, 4): 1040240, (7, 3, 2): 1044012}[params]
+    assert hashlib.sha256(g.stream().tobytes()).hexdigest() == anchors["stream_sha256"]
+    assert [[t["frame_size"], t["fidelity"], t["radix"], len(t["entries"])] for t in g.tables()] == anchors["models"]
+    if params == (7, 3, 4):  # SURVEY 8a "chosen models"
+        assert [m[:3] for m in anchors["models"]] == [[16, 5, 2], [6, 1, 3], [12, 3, 1], [13, 1, 6], [11, 1, 3],
+                                                      [16, 10, 1], [11, 1, 6], [16, 10, 1], [16, 10, 1]]

@@ -1,0 +1,474 @@
+// extern "C" surface of libwgans (include/wga.h).
+#include <cstdlib>
+#include <thread>
+
+#include "bvcomp.hpp"
+#include "formats.hpp"
+#include "graph.hpp"
+#include "model.hpp"
+
+namespace wga {
+const char* last_error_cstr();
+uint64_t decode_workspace_size(const wga_graph* g, uint64_t first, uint64_t last);
+void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets, uint32_t* d_succ,
+                  uint64_t succ_capacity, void* ws, uint64_t ws_bytes, uint64_t* h_arcs, cudaStream_t st);
+void outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets, void* ws, uint64_t ws_bytes,
+                cudaStream_t st);
+void debug_expand_table(wga_graph* g, int c, void* h_out, uint64_t n_slots);
+void debug_decode_symbols(wga_graph* g, const uint8_t* h_comps, uint64_t n, uint64_t ptr, uint32_t state,
+                          uint64_t* h_out, uint64_t* h_end_ptr, uint32_t* h_end_state);
+uint64_t successors_workspace_size(const wga_graph* g, uint64_t n_queries, uint64_t max_total_arcs);
+void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t n_queries, uint64_t* d_offsets,
+                      uint32_t* d_succ, uint64_t succ_capacity, void* ws, uint64_t ws_bytes, uint64_t* h_arcs,
+                      cudaStream_t st);
+uint64_t synth_graph(int kind, uint64_t N, double mean_degree, uint64_t seed, uint64_t first, uint64_t last,
+                     int threads, uint64_t* h_offsets, uint32_t* h_succ);
+
+static void view_to_models(const wga_component_model* in, ComponentModel* out) {
+  for (int c = 0; c < WGA_COMPONENTS; ++c) {
+    out[c].table.assign(in[c].table, in[c].table + in[c].table_len);
+    out[c].frame_size = in[c].frame_size;
+    out[c].radix = in[c].radix;
+    out[c].fidelity = in[c].fidelity;
+    out[c].folding_threshold = in[c].folding_threshold;
+    out[c].folding_offset = in[c].folding_offset;
+  }
+}
+
+static wga_graph* finish_open(std::unique_ptr<wga_graph> g, uint64_t first, uint64_t last, int flags) {
+  g->res_first = first;
+  g->res_last = last;
+  if (!(flags & WGA_OPEN_HOST_ONLY)) g->upload();
+  else g->packed = pack_tables(g->prelude.tables);
+  return g.release();
+}
+
+static std::string with_ext(const char* basename, const char* ext) { return std::string(basename) + "." + ext; }
+
+// ANSBvGraph::store on a node source (random_access.rs:91-222): pass 1 Log2Estimator -> model1,
+// pass 2 EntropyEstimator(model1) -> model2, pass 3 encodes the pass-2 symbols (same estimator, :166-168)
+static void store_from_source(const NodeSource& src, uint64_t n_nodes, const char* new_basename,
+                              const BvCompParams& p, uint64_t chunk_nodes, int threads) {
+  if (!new_basename) throw Error(WGA_E_ARG, "null basename");
+  Prelude pre;
+  {
+    SymbolStream s1;
+    bvcomp_graph(src, n_nodes, p, Estimator(), chunk_nodes, threads, s1);
+    ModelBuilder mb;
+    mb.accumulate_host(s1.comps.data(), s1.vals.data(), s1.size());
+    mb.build(pre.tables, nullptr, nullptr);
+  }
+  SymbolStream s2;
+  uint64_t arcs = 0;
+  {
+    Estimator entropy(pre.tables);
+    arcs = bvcomp_graph(src, n_nodes, p, entropy, chunk_nodes, threads, s2);
+    ModelBuilder mb;
+    mb.accumulate_host(s2.comps.data(), s2.vals.data(), s2.size());
+    mb.build(pre.tables, nullptr, nullptr);
+  }
+  EncodeResult enc;
+  ans_encode(pre.tables, s2.comps.data(), s2.vals.data(), s2.size(), enc);
+  pre.stream.swap(enc.stream);
+  pre.state = enc.state;
+  pre.number_of_nodes = n_nodes;
+  pre.compression_window = p.window;
+  pre.min_interval_length = p.min_interval_length;
+  pre.number_of_arcs = arcs;
+  if (enc.phases.states.size() != n_nodes) throw Error(WGA_E_ARG, "internal: phases != nodes");
+  store_states(with_ext(new_basename, "states"), enc.phases.states);  // random_access.rs:202-204
+  uint64_t upper = enc.phases.pointers.empty() ? 0 : enc.phases.pointers.back();
+  EliasFano ef = EliasFano::build(enc.phases.pointers.data(), n_nodes, upper + 1);  // :225-236
+  write_whole_file(with_ext(new_basename, "pointers"), ef.serialize());
+  store_prelude(with_ext(new_basename, "ans"), pre);  // :217-220
+}
+
+}  // namespace wga
+
+using namespace wga;
+
+struct wga_symbols {
+  SymbolStream s;
+};
+
+extern "C" {
+
+const char* wga_last_error(void) { return last_error_cstr(); }
+
+int wga_cuda_available(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n > 0;
+}
+
+uint64_t wga_kernel_launches(void) { return g_kernel_launches.load(); }
+
+// ------------------------------------------------------------------------------------------ load
+int wga_open(const char* basename, int flags, wga_graph** out) {
+  return guarded([&] {
+    if (!basename || !out) throw Error(WGA_E_ARG, "null argument");
+    std::unique_ptr<wga_graph> g(new wga_graph());
+    load_prelude(with_ext(basename, "ans"), g->prelude);  // random_access.rs:58-59
+    EliasFano ef = EliasFano::deserialize(read_whole_file(with_ext(basename, "pointers")));  // :62-63
+    ef.expand(g->phases.pointers);
+    g->pointers_payload_bytes = ef.payload_bytes();
+    load_states(with_ext(basename, "states"), g->phases.states);  // :66-67
+    uint64_t n = g->prelude.number_of_nodes;
+    *out = finish_open(std::move(g), 0, n, flags);
+  });
+}
+
+int wga_open_shard(const char* basename, uint64_t first, uint64_t last, int flags, wga_graph** out) {
+  return guarded([&] {
+    if (!basename || !out) throw Error(WGA_E_ARG, "null argument");
+    std::unique_ptr<wga_graph> g(new wga_graph());
+    load_prelude(with_ext(basename, "ans"), g->prelude);
+    EliasFano ef = EliasFano::deserialize(read_whole_file(with_ext(basename, "pointers")));
+    ef.expand(g->phases.pointers);
+    g->pointers_payload_bytes = ef.payload_bytes();
+    load_states(with_ext(basename, "states"), g->phases.states);
+    if (first > last || last > g->prelude.number_of_nodes) throw Error(WGA_E_ARG, "bad shard range");
+    *out = finish_open(std::move(g), first, last, flags);
+  });
+}
+
+int wga_open_mem(const wga_prelude_view* v, int flags, wga_graph** out) {
+  return guarded([&] {
+    if (!v || !out) throw Error(WGA_E_ARG, "null argument");
+    std::unique_ptr<wga_graph> g(new wga_graph());
+    view_to_models(v->tables, g->prelude.tables);
+    g->prelude.stream.assign(v->stream, v->stream + v->stream_len);
+    g->prelude.state = v->state;
+    g->prelude.number_of_nodes = v->number_of_nodes;
+    g->prelude.compression_window = v->compression_window;
+    g->prelude.min_interval_length = v->min_interval_length;
+    g->prelude.number_of_arcs = v->number_of_arcs;
+    if (v->states && v->pointers) {
+      g->phases.states.assign(v->states, v->states + v->number_of_nodes);
+      g->phases.pointers.assign(v->pointers, v->pointers + v->number_of_nodes);
+      // size the .pointers payload as the Elias-Fano the reference would store (random_access.rs:225-236)
+      uint64_t n = v->number_of_nodes, u = n ? g->phases.pointers.back() + 1 : 1;
+      uint64_t l = (n && u >= n) ? (uint64_t)(63 - __builtin_clzll(u / n)) : 0;
+      g->pointers_payload_bytes = (n * l + 7) / 8 + (n + (u >> l) + 1 + 7) / 8;
+    }
+    uint64_t n = g->prelude.number_of_nodes;
+    *out = finish_open(std::move(g), 0, n, flags);
+  });
+}
+
+void wga_close(wga_graph* g) { delete g; }
+
+uint64_t wga_num_nodes(const wga_graph* g) { return g->prelude.number_of_nodes; }
+uint64_t wga_num_arcs(const wga_graph* g) { return g->prelude.number_of_arcs; }
+uint64_t wga_window(const wga_graph* g) { return g->prelude.compression_window; }
+uint64_t wga_min_interval_length(const wga_graph* g) { return g->prelude.min_interval_length; }
+uint64_t wga_stream_len(const wga_graph* g) { return g->prelude.stream.size(); }
+uint64_t wga_compressed_bytes(const wga_graph* g) {
+  uint64_t n = g->res_last - g->res_first;
+  uint64_t N = g->prelude.number_of_nodes;
+  uint64_t ptr_bytes = N ? g->pointers_payload_bytes * n / N : 0;
+  uint64_t words = g->on_device ? g->stream_words : g->prelude.stream.size();
+  return 2 * words + 4 * n + ptr_bytes;
+}
+
+int wga_prelude(const wga_graph* g, wga_prelude_view* o) {
+  return guarded([&] {
+    if (!g || !o) throw Error(WGA_E_ARG, "null argument");
+    for (int c = 0; c < WGA_COMPONENTS; ++c) {
+      const ComponentModel& t = g->prelude.tables[c];
+      o->tables[c] = {t.table.data(), t.table.size(), t.frame_size, t.radix, t.fidelity, t.folding_threshold,
+                      t.folding_offset};
+    }
+    o->stream = g->prelude.stream.data();
+    o->stream_len = g->prelude.stream.size();
+    o->state = g->prelude.state;
+    o->number_of_nodes = g->prelude.number_of_nodes;
+    o->compression_window = g->prelude.compression_window;
+    o->min_interval_length = g->prelude.min_interval_length;
+    o->number_of_arcs = g->prelude.number_of_arcs;
+    o->states = g->phases.states.data();
+    o->pointers = g->phases.pointers.data();
+  });
+}
+
+// ---------------------------------------------------------------------------------------- decode
+uint64_t wga_decode_workspace_size(const wga_graph* g, uint64_t first, uint64_t last) {
+  if (!g || first > last) return 0;
+  return decode_workspace_size(g, first, last);
+}
+
+int wga_decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets, uint32_t* d_succ,
+                     uint64_t succ_capacity, void* d_workspace, uint64_t workspace_bytes, uint64_t* h_arcs,
+                     void* stream) {
+  return guarded([&] {
+    if (!g || !d_offsets || !d_workspace) throw Error(WGA_E_ARG, "null argument");
+    decode_range(g, first, last, d_offsets, d_succ, succ_capacity, d_workspace, workspace_bytes, h_arcs,
+                 (cudaStream_t)stream);
+  });
+}
+
+int wga_outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets, void* d_workspace,
+                   uint64_t workspace_bytes, void* stream) {
+  return guarded([&] {
+    if (!g || !d_offsets || !d_workspace) throw Error(WGA_E_ARG, "null argument");
+    outdegrees(g, first, last, d_offsets, d_workspace, workspace_bytes, (cudaStream_t)stream);
+  });
+}
+
+int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t* h_offsets, uint32_t* h_succ,
+                          uint64_t succ_capacity, uint64_t* h_arcs) {
+  return guarded([&] {
+    if (!g || !h_offsets) throw Error(WGA_E_ARG, "null argument");
+    uint64_t ws_bytes = decode_workspace_size(g, first, last);
+    void* ws = nullptr;
+    uint64_t* d_off = nullptr;
+    uint32_t* d_succ = nullptr;
+    struct Free {
+      void** p;
+      ~Free() { if (*p) cudaFree(*p); }
+    };
+    WGA_CUDA(cudaMalloc(&ws, ws_bytes));
+    Free f1{&ws};
+    WGA_CUDA(cudaMalloc((void**)&d_off, (last - first + 1) * 8));
+    Free f2{(void**)&d_off};
+    WGA_CUDA(cudaMalloc((void**)&d_succ, (succ_capacity ? succ_capacity : 1) * 4));
+    Free f3{(void**)&d_succ};
+    uint64_t arcs = 0;
+    decode_range(g, first, last, d_off, d_succ, succ_capacity, ws, ws_bytes, &arcs, 0);
+    WGA_CUDA(cudaMemcpy(h_offsets, d_off, (last - first + 1) * 8, cudaMemcpyDeviceToHost));
+    if (arcs && h_succ) WGA_CUDA(cudaMemcpy(h_succ, d_succ, arcs * 4, cudaMemcpyDeviceToHost));
+    if (h_arcs) *h_arcs = arcs;
+  });
+}
+
+// --------------------------------------------------------------------------------- random access
+uint64_t wga_successors_workspace_size(const wga_graph* g, uint64_t n_queries, uint64_t max_total_arcs) {
+  if (!g) return 0;
+  return successors_workspace_size(g, n_queries, max_total_arcs);
+}
+
+int wga_successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t n_queries, uint64_t* d_offsets,
+                         uint32_t* d_succ, uint64_t succ_capacity, void* d_workspace, uint64_t workspace_bytes,
+                         uint64_t* h_arcs, void* stream) {
+  return guarded([&] {
+    if (!g || !d_nodes || !d_offsets || !d_workspace) throw Error(WGA_E_ARG, "null argument");
+    successors_batch(g, d_nodes, n_queries, d_offsets, d_succ, succ_capacity, d_workspace, workspace_bytes, h_arcs,
+                     (cudaStream_t)stream);
+  });
+}
+
+// ----------------------------------------------------------------------------------------- debug
+int wga_debug_expand_table(wga_graph* g, int component, void* h_out, uint64_t n_slots) {
+  return guarded([&] {
+    if (!g || !h_out) throw Error(WGA_E_ARG, "null argument");
+    debug_expand_table(g, component, h_out, n_slots);
+  });
+}
+
+int wga_debug_decode_symbols(wga_graph* g, const uint8_t* h_components, uint64_t n, uint64_t ptr, uint32_t state,
+                             uint64_t* h_out, uint64_t* h_end_ptr, uint32_t* h_end_state) {
+  return guarded([&] {
+    if (!g || (!h_components && n) || (!h_out && n)) throw Error(WGA_E_ARG, "null argument");
+    debug_decode_symbols(g, h_components, n, ptr, state, h_out, h_end_ptr, h_end_state);
+  });
+}
+
+// ----------------------------------------------------------------------------------------- model
+int wga_model_create(wga_model** out) {
+  return guarded([&] {
+    if (!out) throw Error(WGA_E_ARG, "null argument");
+    *out = reinterpret_cast<wga_model*>(new ModelBuilder());
+  });
+}
+void wga_model_destroy(wga_model* m) { delete reinterpret_cast<ModelBuilder*>(m); }
+uint64_t* wga_model_bins(wga_model* m) { return reinterpret_cast<ModelBuilder*>(m)->device_bins(); }
+int wga_model_accumulate(wga_model* m, const uint8_t* d_components, const uint64_t* d_symbols, uint64_t n,
+                         void* stream) {
+  return guarded([&] { reinterpret_cast<ModelBuilder*>(m)->accumulate_device(d_components, d_symbols, n, (cudaStream_t)stream); });
+}
+int wga_model_accumulate_host(wga_model* m, const uint8_t* h_components, const uint64_t* h_symbols, uint64_t n) {
+  return guarded([&] { reinterpret_cast<ModelBuilder*>(m)->accumulate_host(h_components, h_symbols, n); });
+}
+uint64_t wga_model_sparse_count(wga_model* m) {
+  uint64_t n = 0;
+  guarded([&] { n = reinterpret_cast<ModelBuilder*>(m)->sparse_count(); });
+  return n;
+}
+int wga_model_sparse_export(wga_model* m, uint8_t* h_components, uint64_t* h_symbols, uint64_t* h_counts) {
+  return guarded([&] { reinterpret_cast<ModelBuilder*>(m)->sparse_export(h_components, h_symbols, h_counts); });
+}
+int wga_model_sparse_merge(wga_model* m, const uint8_t* h_components, const uint64_t* h_symbols,
+                           const uint64_t* h_counts, uint64_t n) {
+  return guarded([&] { reinterpret_cast<ModelBuilder*>(m)->sparse_merge(h_components, h_symbols, h_counts, n); });
+}
+int wga_model_build(wga_model* m, wga_component_model out_tables[WGA_COMPONENTS], double* h_original_cost9,
+                    double* h_final_cost9) {
+  return guarded([&] {
+    ModelBuilder* mb = reinterpret_cast<ModelBuilder*>(m);
+    mb->build(mb->result, h_original_cost9, h_final_cost9);
+    for (int c = 0; c < WGA_COMPONENTS; ++c) {
+      const ComponentModel& t = mb->result[c];
+      out_tables[c] = {t.table.data(), t.table.size(), t.frame_size, t.radix, t.fidelity, t.folding_threshold,
+                       t.folding_offset};
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------- bvcomp
+int wga_bvcomp_symbols(const uint64_t* h_offsets, const uint32_t* h_succ, uint64_t n_nodes,
+                       uint64_t compression_window, uint64_t max_ref_count, uint64_t min_interval_length,
+                       const wga_component_model* estimator_tables, uint64_t chunk_nodes, int threads,
+                       wga_symbols** out) {
+  return guarded([&] {
+    if (!h_offsets || !out) throw Error(WGA_E_ARG, "null argument");
+    BvCompParams p{compression_window, max_ref_count, min_interval_length};
+    std::unique_ptr<wga_symbols> s(new wga_symbols());
+    NodeSource src = [&](uint64_t v, std::vector<uint64_t>& o) {
+      o.assign(h_succ + h_offsets[v], h_succ + h_offsets[v + 1]);
+    };
+    if (estimator_tables) {
+      ComponentModel m[WGA_COMPONENTS];
+      view_to_models(estimator_tables, m);
+      Estimator est(m);
+      bvcomp_graph(src, n_nodes, p, est, chunk_nodes, threads, s->s);
+    } else {
+      bvcomp_graph(src, n_nodes, p, Estimator(), chunk_nodes, threads, s->s);
+    }
+    *out = s.release();
+  });
+}
+uint64_t wga_symbols_len(const wga_symbols* s) { return s->s.size(); }
+const uint8_t* wga_symbols_components(const wga_symbols* s) { return s->s.comps.data(); }
+const uint64_t* wga_symbols_values(const wga_symbols* s) { return s->s.vals.data(); }
+void wga_symbols_free(wga_symbols* s) { delete s; }
+
+int wga_ans_encode(const wga_component_model tables[WGA_COMPONENTS], const uint8_t* h_components,
+                   const uint64_t* h_symbols, uint64_t n, uint16_t** out_stream, uint64_t* out_stream_len,
+                   uint32_t* out_state, uint32_t** out_states, uint64_t** out_pointers, uint64_t* out_n_phases) {
+  return guarded([&] {
+    if (!tables || !out_stream || !out_stream_len || !out_state) throw Error(WGA_E_ARG, "null argument");
+    ComponentModel m[WGA_COMPONENTS];
+    view_to_models(tables, m);
+    EncodeResult r;
+    ans_encode(m, h_components, h_symbols, n, r);
+    *out_stream = (uint16_t*)std::malloc(r.stream.size() * 2 + 2);
+    std::memcpy(*out_stream, r.stream.data(), r.stream.size() * 2);
+    *out_stream_len = r.stream.size();
+    *out_state = r.state;
+    if (out_states && out_pointers && out_n_phases) {
+      size_t np = r.phases.states.size();
+      *out_states = (uint32_t*)std::malloc(np * 4 + 4);
+      *out_pointers = (uint64_t*)std::malloc(np * 8 + 8);
+      std::memcpy(*out_states, r.phases.states.data(), np * 4);
+      std::memcpy(*out_pointers, r.phases.pointers.data(), np * 8);
+      *out_n_phases = np;
+    }
+  });
+}
+void wga_free(void* p) { std::free(p); }
+
+int wga_write_files(const char* basename, const wga_prelude_view* v) {
+  return guarded([&] {
+    if (!basename || !v) throw Error(WGA_E_ARG, "null argument");
+    Prelude p;
+    view_to_models(v->tables, p.tables);
+    p.stream.assign(v->stream, v->stream + v->stream_len);
+    p.state = v->state;
+    p.number_of_nodes = v->number_of_nodes;
+    p.compression_window = v->compression_window;
+    p.min_interval_length = v->min_interval_length;
+    p.number_of_arcs = v->number_of_arcs;
+    if (v->states && v->pointers) {
+      std::vector<uint32_t> st(v->states, v->states + v->number_of_nodes);
+      store_states(with_ext(basename, "states"), st);
+      uint64_t upper = v->number_of_nodes ? v->pointers[v->number_of_nodes - 1] : 0;
+      EliasFano ef = EliasFano::build(v->pointers, v->number_of_nodes, upper + 1);
+      write_whole_file(with_ext(basename, "pointers"), ef.serialize());
+    }
+    store_prelude(with_ext(basename, "ans"), p);
+  });
+}
+
+int wga_store(const char* basename, const char* new_basename, uint64_t compression_window,
+              uint64_t max_ref_count, uint64_t min_interval_length) {
+  return guarded([&] {
+    if (!basename) throw Error(WGA_E_ARG, "null basename");
+    // BvGraphSeq::with_basename(..).load() (random_access.rs:101-103); the CSR is kept in host memory
+    std::vector<uint64_t> offs(1, 0);
+    std::vector<uint32_t> succ;
+    read_bvgraph(basename, [&](uint64_t, const std::vector<uint64_t>& s) {
+      for (uint64_t x : s) succ.push_back((uint32_t)x);
+      offs.push_back(succ.size());
+    });
+    NodeSource src = [&](uint64_t v, std::vector<uint64_t>& o) {
+      o.assign(succ.begin() + offs[v], succ.begin() + offs[v + 1]);
+    };
+    store_from_source(src, offs.size() - 1, new_basename,
+                      BvCompParams{compression_window, max_ref_count, min_interval_length}, 0, 1);
+  });
+}
+
+int wga_store_csr(const uint64_t* h_offsets, const uint32_t* h_succ, uint64_t n_nodes, const char* new_basename,
+                  uint64_t compression_window, uint64_t max_ref_count, uint64_t min_interval_length,
+                  uint64_t chunk_nodes, int threads) {
+  return guarded([&] {
+    if (!h_offsets) throw Error(WGA_E_ARG, "null argument");
+    NodeSource src = [&](uint64_t v, std::vector<uint64_t>& o) {
+      o.assign(h_succ + h_offsets[v], h_succ + h_offsets[v + 1]);
+    };
+    store_from_source(src, n_nodes, new_basename,
+                      BvCompParams{compression_window, max_ref_count, min_interval_length}, chunk_nodes, threads);
+  });
+}
+
+int wga_bvgraph_read(const char* basename, uint64_t* n_nodes, uint64_t* n_arcs, uint64_t* h_offsets,
+                     uint32_t* h_succ) {
+  return guarded([&] {
+    if (!basename) throw Error(WGA_E_ARG, "null basename");
+    uint64_t nodes = 0, arcs = 0;
+    if (h_offsets) h_offsets[0] = 0;
+    read_bvgraph(basename, [&](uint64_t v, const std::vector<uint64_t>& s) {
+      if (h_succ)
+        for (size_t i = 0; i < s.size(); ++i) h_succ[arcs + i] = (uint32_t)s[i];
+      arcs += s.size();
+      nodes = v + 1;
+      if (h_offsets) h_offsets[v + 1] = arcs;
+    });
+    if (n_nodes) *n_nodes = nodes;
+    if (n_arcs) *n_arcs = arcs;
+  });
+}
+
+int wga_ef_write(const char* path, const uint64_t* values, uint64_t n, uint64_t u) {
+  return guarded([&] {
+    if (!path || (!values && n)) throw Error(WGA_E_ARG, "null argument");
+    write_whole_file(path, EliasFano::build(values, n, u).serialize());
+  });
+}
+
+int wga_ef_read(const char* path, uint64_t* n, uint64_t* h_values) {
+  return guarded([&] {
+    if (!path) throw Error(WGA_E_ARG, "null path");
+    EliasFano ef = EliasFano::deserialize(read_whole_file(path));
+    if (n) *n = ef.n;
+    if (h_values) {
+      std::vector<uint64_t> v;
+      ef.expand(v);
+      std::memcpy(h_values, v.data(), v.size() * 8);
+      // exercise the inventory path on a sample (IndexedSeq::get)
+      for (uint64_t i = 0; i < ef.n; i += 997)
+        if (ef.get(i) != v[i]) throw Error(WGA_E_FORMAT, "Elias-Fano: inventory select disagrees with the scan");
+    }
+  });
+}
+
+int wga_synth_graph(int kind, uint64_t n_nodes, double mean_degree, uint64_t seed, uint64_t first, uint64_t last,
+                    int threads, uint64_t* h_offsets, uint32_t* h_succ, uint64_t* n_arcs) {
+  return guarded([&] {
+    uint64_t a = synth_graph(kind, n_nodes, mean_degree, seed, first, last, threads, h_offsets, h_succ);
+    if (n_arcs) *n_arcs = a;
+  });
+}
+
+}  // extern "C"

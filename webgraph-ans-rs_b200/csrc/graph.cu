@@ -1,0 +1,144 @@
+// Graph handle: packed decoder tables (host build) and upload of the decode inputs to HBM.
+#include "graph.hpp"
+
+namespace wga {
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& m) { t_last_error = m; }
+const char* last_error_cstr() { return t_last_error.c_str(); }
+
+// Builds the packed tables from the encoder tables of the Prelude.  Same content as the reference's
+// ANSModel4Decoder::new (src/ans/models/model4decoder.rs:18-54) + quasi_fold (:56-68), different layout:
+// see common.hpp.  `base` = symbol - folding_offset*folds, so the decoder's
+// quasi_folded = (base << folds*radix) | folds << 48.
+PackedTablesData pack_tables(const ComponentModel tables[WGA_COMPONENTS]) {
+  PackedTablesData p;
+  for (int c = 0; c < WGA_COMPONENTS; ++c) {
+    const ComponentModel& t = tables[c];
+    if (t.frame_size > 16) throw Error(WGA_E_FORMAT, "frame size > 2^16");
+    if (t.radix == 0 || t.radix > 16 || t.fidelity == 0) throw Error(WGA_E_FORMAT, "bad radix/fidelity");
+    const uint32_t L = (uint32_t)t.frame_size;
+    const uint32_t lut_bits = L < (uint32_t)LUT_BITS ? L : (uint32_t)LUT_BITS;
+    const uint32_t shift = L - lut_bits;
+    p.L[c] = (uint8_t)L;
+    p.R[c] = (uint8_t)t.radix;
+    p.shift[c] = (uint8_t)shift;
+    p.lut_off[c] = (uint32_t)p.lut.size();
+    p.ent_off[c] = (uint32_t)p.ent.size();
+    const uint32_t frame = 1u << L;
+    // non-zero symbols in index order; running sum gives the slot ranges (model4decoder.rs:24-43)
+    uint32_t nnz = 0;
+    uint32_t last_slot = 0;
+    std::vector<uint32_t> starts;  // first slot of every nz symbol
+    for (size_t sym = 0; sym < t.table.size(); ++sym) {
+      const wga_encoder_entry& e = t.table[sym];
+      if (e.freq == 0) continue;
+      if (last_slot + e.freq > frame) throw Error(WGA_E_FORMAT, "frequencies exceed the frame");
+      uint32_t folds = 0, base = (uint32_t)sym;
+      if ((uint16_t)sym >= (uint16_t)t.folding_threshold) {  // quasi_fold, :57
+        folds = (uint32_t)(((uint64_t)sym - t.folding_threshold) / t.folding_offset + 1);
+        base = (uint32_t)((uint64_t)sym - t.folding_offset * folds);
+      }
+      if (folds >= 0xFFFF || base > 0xFFFF || folds * t.radix > 48) throw Error(WGA_E_FORMAT, "bad folding parameters");
+      Ent en;
+      // NOTE the decode formula uses cumul_freq as stored (decoder.rs:65), the slot range uses the running sum
+      en.cf = (uint32_t)e.cumul_freq | ((uint32_t)e.freq << 16);
+      en.bf = base | (folds << 16);
+      if (e.cumul_freq != (uint16_t)last_slot) throw Error(WGA_E_FORMAT, "cumulative frequency does not match the running sum");
+      p.ent.push_back(en);
+      starts.push_back(last_slot);
+      last_slot += e.freq;
+      ++nnz;
+    }
+    // sentinel: owns every slot >= sum of frequencies (unused slots; the reference leaves default entries)
+    Ent s;
+    s.cf = (last_slot & 0xFFFFu) | (0xFFFFu << 16);
+    s.bf = 0xFFFFu << 16;
+    p.ent.push_back(s);
+    starts.push_back(last_slot);
+    p.nnz[c] = nnz;
+    // lut: owner of the first slot of every bucket
+    uint32_t j = 0;
+    for (uint32_t b = 0; b < (1u << lut_bits); ++b) {
+      uint32_t slot = b << shift;
+      while (j < nnz && starts[j + 1] <= slot) ++j;
+      p.lut.push_back((uint16_t)j);
+    }
+  }
+  return p;
+}
+
+}  // namespace wga
+
+using namespace wga;
+
+wga_graph::~wga_graph() {
+  if (on_device) {
+    cudaFree(d_stream);
+    cudaFree(d_states);
+    cudaFree(d_ptrs);
+    cudaFree(d_lut);
+    cudaFree(d_ent);
+    cudaFree(d_err);
+  }
+}
+
+// Uploads the decode inputs of nodes [res_first,res_last) to the current device.
+void wga_graph::upload() {
+  const uint64_t N = prelude.number_of_nodes;
+  if (phases.states.size() != N || phases.pointers.size() != N)
+    throw Error(WGA_E_FORMAT, "the GPU decode needs .states and .pointers with one phase per node");
+  if (prelude.compression_window > 0xFFFF) throw Error(WGA_E_UNSUPPORTED, "compression window > 65535");
+  if (N >= (1ull << 32)) throw Error(WGA_E_UNSUPPORTED, "graphs with >= 2^32 nodes need 64-bit successors");
+  int dev = 0;
+  WGA_CUDA(cudaGetDevice(&dev));
+  device = dev;
+  const uint64_t n_res = res_last - res_first;
+  // stream span needed by [res_first,res_last): words [ptr(res_last), ptr(res_first)) ; ptr(N) := 0
+  // (node v's record starts at pointer(N-1-v) and reads downwards, src/ans/decoder.rs:89-93)
+  uint64_t hi = n_res ? phases.pointers[N - 1 - res_first] : 0;
+  uint64_t lo = res_last < N ? phases.pointers[N - 1 - res_last] : 0;
+  if (hi > prelude.stream.size() || lo > hi) throw Error(WGA_E_FORMAT, "stream pointers are not monotone");
+  stream_base = lo;
+  stream_words = hi - lo;
+  WGA_CUDA(cudaMalloc(&d_stream, (stream_words + 8) * 2));
+  WGA_CUDA(cudaMemset(d_stream, 0, (stream_words + 8) * 2));
+  if (stream_words)
+    WGA_CUDA(cudaMemcpy(d_stream, prelude.stream.data() + lo, stream_words * 2, cudaMemcpyHostToDevice));
+  WGA_CUDA(cudaMalloc(&d_states, (n_res + 1) * 4));
+  WGA_CUDA(cudaMalloc(&d_ptrs, (n_res + 1) * 8));
+  if (n_res) {
+    // file order: entry i = node N-1-i ; resident nodes are entries [N-res_last, N-res_first)
+    WGA_CUDA(cudaMemcpy(d_states, phases.states.data() + (N - res_last), n_res * 4, cudaMemcpyHostToDevice));
+    WGA_CUDA(cudaMemcpy(d_ptrs, phases.pointers.data() + (N - res_last), n_res * 8, cudaMemcpyHostToDevice));
+  }
+  packed = pack_tables(prelude.tables);
+  WGA_CUDA(cudaMalloc(&d_lut, packed.lut.size() * 2 + 16));
+  WGA_CUDA(cudaMalloc(&d_ent, packed.ent.size() * 8 + 16));
+  WGA_CUDA(cudaMemcpy(d_lut, packed.lut.data(), packed.lut.size() * 2, cudaMemcpyHostToDevice));
+  WGA_CUDA(cudaMemcpy(d_ent, packed.ent.data(), packed.ent.size() * 8, cudaMemcpyHostToDevice));
+  WGA_CUDA(cudaMalloc(&d_err, 4));
+  WGA_CUDA(cudaMemset(d_err, 0, 4));
+  on_device = true;
+
+  this->dev.tb.lut = d_lut;
+  this->dev.tb.ent = d_ent;
+  for (int c = 0; c < WGA_COMPONENTS; ++c) {
+    this->dev.tb.lut_off[c] = packed.lut_off[c];
+    this->dev.tb.ent_off[c] = packed.ent_off[c];
+    this->dev.tb.L[c] = packed.L[c];
+    this->dev.tb.R[c] = packed.R[c];
+    this->dev.tb.shift[c] = packed.shift[c];
+  }
+  this->dev.tb.lut_total = (uint32_t)packed.lut.size();
+  this->dev.tb.ent_total = (uint32_t)packed.ent.size();
+  this->dev.stream = d_stream;
+  this->dev.stream_base = stream_base;
+  this->dev.stream_words = stream_words;
+  this->dev.states = d_states;
+  this->dev.ptrs = d_ptrs;
+  this->dev.top = res_last ? res_last - 1 : 0;
+  this->dev.N = N;
+  this->dev.window = (uint32_t)prelude.compression_window;
+  this->dev.min_interval = (uint32_t)prelude.min_interval_length;
+}

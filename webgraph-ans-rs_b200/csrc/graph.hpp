@@ -1,0 +1,45 @@
+// The graph handle behind wga_graph*: host copy of the files + device-resident decode inputs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "common.hpp"
+#include "device.cuh"
+
+namespace wga {
+
+#define WGA_CUDA(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (call);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      throw ::wga::Error(WGA_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));            \
+  } while (0)
+
+extern std::atomic<uint64_t> g_kernel_launches;
+inline void count_launch(int n = 1) { g_kernel_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+}  // namespace wga
+
+struct wga_graph {
+  wga::Prelude prelude;
+  wga::Phases phases;       // full (or shard-local) phases, file order
+  wga::PackedTablesData packed;
+  // nodes whose inputs are resident: [res_first, res_last); whole graph unless opened as a shard
+  uint64_t res_first = 0, res_last = 0;
+  bool on_device = false;
+  int device = -1;
+  // device buffers
+  uint16_t* d_stream = nullptr;
+  uint64_t stream_base = 0, stream_words = 0;
+  uint32_t* d_states = nullptr;  // res_last-res_first entries; entry k = node res_last-1-k
+  uint64_t* d_ptrs = nullptr;
+  uint16_t* d_lut = nullptr;
+  uint2* d_ent = nullptr;
+  uint32_t* d_err = nullptr;  // device error word
+  wga::DevGraph dev{};         // view passed to kernels
+  uint64_t pointers_payload_bytes = 0;
+
+  ~wga_graph();
+  void upload();
+};
