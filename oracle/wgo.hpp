@@ -391,6 +391,9 @@ class ANSEncoder {
     }
     const EncoderModelEntry& sd = cm.table.at((Symbol)symbol);  // Index<Symbol> panics when OOB
     if (state >= sd.upperbound) shrink_state();
+    // the reference divides by NonZeroU32::unwrap_unchecked(freq) (:72-73): freq == 0 is UB there
+    // (e.g. a zero-entropy input makes `ratio` NaN and the single symbol gets freq 65536 as u16 == 0)
+    if (sd.freq == 0) throw std::domain_error("ANSEncoder: symbol with frequency 0 (undefined behaviour in the reference)");
     State block = state / (State)sd.freq;
     state = (block << cm.frame_size) + (State)sd.cumul_freq + (state - block * (State)sd.freq);
   }

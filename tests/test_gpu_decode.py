@@ -78,7 +78,7 @@ def test_symbol_decoder_matches_oracle(W, O, gpu, case):
 GRAPH_CASES = [
     # n, mean_deg, (window, max_ref, min_interval), seed
     (6, 0, (7, 3, 2), 0),          # the 6-node dummy graph of tests/test_bvgraph.rs:23
-    (1, 3, (7, 3, 4), 1),
+    (2, 3, (7, 3, 4), 1),
     (2000, 8, (7, 3, 4), 2),       # CLI defaults
     (2000, 8, (7, 3, 2), 3),       # what the reference's tests use
     (3000, 12, (16, 1 << 30, 4), 4),  # "-hc": wide window, unbounded reference chains

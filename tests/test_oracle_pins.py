@@ -88,6 +88,14 @@ def test_decodes_correctly_dummy_graph(O):  # tests/test_bvgraph.rs:23-101 : BvC
     assert (o2 == off).all() and (s2 == succ).all() and end == (0, 65536)
 
 
+def test_zero_entropy_input_is_rejected(O):
+    """A graph whose every component is deterministic has original cost 0: `ratio` is NaN
+    (model4encoder_builder.rs:166), the 2^16 fallback stores freq 65536 `as u16` == 0 (:223) and the
+    reference's encoder then divides by zero (encoder.rs:72-73, UB).  The oracle raises instead."""
+    with pytest.raises(RuntimeError):
+        O.OracleGraph.store_csr(np.array([0, 1], np.uint64), np.array([0], np.uint32), 7, 3, 4)
+
+
 def test_golden_head_fixture(O, head):
     """The committed .ans/.pointers/.states decode back to the committed CSR, sequentially and by node."""
     g = O.OracleGraph.load(head["base"])
