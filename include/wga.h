@@ -133,6 +133,15 @@ int wga_outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offs
 int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t* h_offsets, uint32_t* h_succ,
                           uint64_t succ_capacity, uint64_t* h_arcs);
 
+/* Re-copies the decode inputs of the resident range (stream words, states, pointers) from the handle's
+ * pinned host copy to the device: the host->device leg of an end-to-end step. */
+int wga_upload(wga_graph* g, void* stream);
+uint64_t wga_upload_bytes(const wga_graph* g);
+/* Per-stage device times of the last wga_decode_range (CUDA events on the caller's stream):
+ * [outdegrees+scan, entropy decode, reference levels, copy resolution].  Returns the number of events. */
+int wga_set_profiling(wga_graph* g, int on);
+int wga_last_profile(const wga_graph* g, float* h_stage_ms8);
+
 /* ---------------------------------------------------------------- random access (successors(v)) - */
 uint64_t wga_successors_workspace_size(const wga_graph* g, uint64_t n_queries, uint64_t max_total_arcs);
 int wga_successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t n_queries, uint64_t* d_offsets,

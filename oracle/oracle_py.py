@@ -228,6 +228,12 @@ class OracleGraph:
                                        C.byref(arcs), C.byref(secs)))
         return arcs.value, secs.value
 
+    def decode_parallel_into(self, first, last, nthreads, offsets, succ_out):
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        assert succ_out.dtype == np.uint32 and succ_out.flags.c_contiguous
+        _chk(lib().wgo_decode_parallel_into(self.h, C.c_uint64(first), C.c_uint64(last), C.c_int(nthreads),
+                                            _p(offsets), _p(succ_out)))
+
     def random_access_bench(self, nodes):
         nodes = np.ascontiguousarray(nodes, np.uint64)
         arcs = C.c_uint64(0)

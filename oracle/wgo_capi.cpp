@@ -295,6 +295,35 @@ int wgo_decode_parallel(void* h, uint64_t first, uint64_t last, int nthreads, ui
     if (secs) *secs = std::chrono::duration<double>(t1 - t0).count();
   });
 }
+// Node-range-parallel decode INTO caller arrays, for whole-graph verification of a device result:
+// `offsets` (last-first+1 entries, relative to first) are given; every node's decoded outdegree must match
+// them, and its successors are written to succ[offsets[v-first]..].  Returns 0, or -1 with a message.
+int wgo_decode_parallel_into(void* h, uint64_t first, uint64_t last, int nthreads, const uint64_t* offsets,
+                             uint32_t* succ) {
+  return guard([&] {
+    Graph* G = (Graph*)h;
+    G->model();
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::string> errs(nthreads);
+    std::vector<std::thread> th;
+    uint64_t span = last - first;
+    for (int t = 0; t < nthreads; ++t) {
+      th.emplace_back([&, t] {
+        try {
+          uint64_t a = first + span * t / nthreads, b = first + span * (t + 1) / nthreads;
+          decode_range(*G, a, b, [&](size_t v, const std::vector<uint64_t>& s) {
+            uint64_t o = offsets[v - first];
+            if (offsets[v - first + 1] - o != s.size())
+              throw std::runtime_error("outdegree mismatch at node " + std::to_string(v));
+            for (size_t i = 0; i < s.size(); ++i) succ[o + i] = (uint32_t)s[i];
+          });
+        } catch (const std::exception& e) { errs[t] = e.what(); }
+      });
+    }
+    for (auto& x : th) x.join();
+    for (auto& e : errs) if (!e.empty()) throw std::runtime_error(e);
+  });
+}
 // Random-access benchmark (examples/bench_random_access.rs:28-41): sum of outdegrees over `n` nodes.
 int wgo_random_access_bench(void* h, const uint64_t* nodes, uint64_t n, uint64_t* arcs, double* secs) {
   return guard([&] {

@@ -57,7 +57,7 @@ def lib():
         L.wga_last_error.restype = C.c_char_p
         for name in ("wga_num_nodes", "wga_num_arcs", "wga_window", "wga_min_interval_length", "wga_stream_len",
                      "wga_compressed_bytes", "wga_decode_workspace_size", "wga_successors_workspace_size",
-                     "wga_kernel_launches", "wga_symbols_len", "wga_model_sparse_count"):
+                     "wga_kernel_launches", "wga_symbols_len", "wga_model_sparse_count", "wga_upload_bytes"):
             getattr(L, name).restype = C.c_uint64
         L.wga_model_bins.restype = C.c_void_p
         L.wga_symbols_components.restype = C.c_void_p

@@ -220,26 +220,60 @@ int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t*
                           uint64_t succ_capacity, uint64_t* h_arcs) {
   return guarded([&] {
     if (!g || !h_offsets) throw Error(WGA_E_ARG, "null argument");
+    if (!g->on_device) throw Error(WGA_E_CUDA, "graph was opened host-only");
+    // grow-only device buffers owned by the handle: no allocation on the steady-state path
     uint64_t ws_bytes = decode_workspace_size(g, first, last);
-    void* ws = nullptr;
-    uint64_t* d_off = nullptr;
-    uint32_t* d_succ = nullptr;
-    struct Free {
-      void** p;
-      ~Free() { if (*p) cudaFree(*p); }
-    };
-    WGA_CUDA(cudaMalloc(&ws, ws_bytes));
-    Free f1{&ws};
-    WGA_CUDA(cudaMalloc((void**)&d_off, (last - first + 1) * 8));
-    Free f2{(void**)&d_off};
-    WGA_CUDA(cudaMalloc((void**)&d_succ, (succ_capacity ? succ_capacity : 1) * 4));
-    Free f3{(void**)&d_succ};
+    if (g->e2e_ws_bytes < ws_bytes) {
+      if (g->e2e_ws) cudaFree(g->e2e_ws);
+      g->e2e_ws = nullptr; g->e2e_ws_bytes = 0;
+      WGA_CUDA(cudaMalloc(&g->e2e_ws, ws_bytes));
+      g->e2e_ws_bytes = ws_bytes;
+    }
+    uint64_t n_off = last - first + 1;
+    if (g->e2e_off_n < n_off) {
+      if (g->e2e_off) cudaFree(g->e2e_off);
+      g->e2e_off = nullptr; g->e2e_off_n = 0;
+      WGA_CUDA(cudaMalloc((void**)&g->e2e_off, n_off * 8));
+      g->e2e_off_n = n_off;
+    }
+    uint64_t cap = succ_capacity ? succ_capacity : 1;
+    if (g->e2e_succ_n < cap) {
+      if (g->e2e_succ) cudaFree(g->e2e_succ);
+      g->e2e_succ = nullptr; g->e2e_succ_n = 0;
+      WGA_CUDA(cudaMalloc((void**)&g->e2e_succ, cap * 4));
+      g->e2e_succ_n = cap;
+    }
     uint64_t arcs = 0;
-    decode_range(g, first, last, d_off, d_succ, succ_capacity, ws, ws_bytes, &arcs, 0);
-    WGA_CUDA(cudaMemcpy(h_offsets, d_off, (last - first + 1) * 8, cudaMemcpyDeviceToHost));
-    if (arcs && h_succ) WGA_CUDA(cudaMemcpy(h_succ, d_succ, arcs * 4, cudaMemcpyDeviceToHost));
+    decode_range(g, first, last, g->e2e_off, g->e2e_succ, succ_capacity, g->e2e_ws, g->e2e_ws_bytes, &arcs, 0);
+    WGA_CUDA(cudaMemcpyAsync(h_offsets, g->e2e_off, n_off * 8, cudaMemcpyDeviceToHost, 0));
+    if (arcs && h_succ) WGA_CUDA(cudaMemcpyAsync(h_succ, g->e2e_succ, arcs * 4, cudaMemcpyDeviceToHost, 0));
+    WGA_CUDA(cudaStreamSynchronize(0));
     if (h_arcs) *h_arcs = arcs;
   });
+}
+
+int wga_upload(wga_graph* g, void* stream) {
+  return guarded([&] {
+    if (!g) throw Error(WGA_E_ARG, "null argument");
+    g->reupload((cudaStream_t)stream);
+  });
+}
+
+uint64_t wga_upload_bytes(const wga_graph* g) {
+  uint64_t n = g->res_last - g->res_first;
+  return 2 * g->stream_words + 4 * n + 8 * n;
+}
+
+int wga_set_profiling(wga_graph* g, int on) {
+  if (!g) return WGA_E_ARG;
+  g->profiling = on != 0;
+  return WGA_OK;
+}
+
+int wga_last_profile(const wga_graph* g, float* h_stage_ms8) {
+  if (!g || !h_stage_ms8) return WGA_E_ARG;
+  for (int i = 0; i < 8; ++i) h_stage_ms8[i] = g->stage_ms[i];
+  return g->n_ev;
 }
 
 // --------------------------------------------------------------------------------- random access

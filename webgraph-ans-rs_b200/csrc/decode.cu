@@ -388,6 +388,12 @@ void outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets
 
 void launch_offsets_rebase(const uint64_t* src, uint64_t base, uint64_t* dst, uint64_t n, cudaStream_t st);
 
+static void mark(wga_graph* g, cudaStream_t st) {
+  if (!g->profiling || g->n_ev >= 8) return;
+  if (!g->ev[g->n_ev]) cudaEventCreate(&g->ev[g->n_ev]);
+  cudaEventRecord(g->ev[g->n_ev++], st);
+}
+
 void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets, uint32_t* d_succ,
                   uint64_t succ_capacity, void* ws, uint64_t ws_bytes, uint64_t* h_arcs, cudaStream_t st) {
   if (!g->on_device) throw Error(WGA_E_CUDA, "graph was opened host-only");
@@ -401,6 +407,8 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   uint8_t* w = (uint8_t*)ws;
   if (ws_bytes < 256) throw Error(WGA_E_WORKSPACE, "workspace too small");
   WGA_CUDA(cudaMemsetAsync(w, 0, 256, st));
+  g->n_ev = 0;
+  mark(g, st);  // 0: start
   uint64_t* d_lo = (uint64_t*)(w + 16);
   // ---- halo
   uint64_t lo = first;
@@ -438,6 +446,7 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_cub, cb, it, rv.offs, (int64_t)(n + 1), st));
     count_launch(2);
   }
+  mark(g, st);  // 1: outdegrees + scan done
   // capacity check needs the totals: read back (halo arcs, range arcs)
   uint64_t tot[2] = {0, 0};
   WGA_CUDA(cudaMemcpyAsync(&tot[0], rv.offs + rv.h, 8, cudaMemcpyDeviceToHost, st));
@@ -449,10 +458,12 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   // ---- K1
   k_decode_nodes<<<grid, TPB, 0, st>>>(g->dev, rv);
   count_launch();
+  mark(g, st);  // 2: entropy decode done
   // ---- K2
   if (g->prelude.compression_window != 0) {
     k_levels<<<grid, TPB, 0, st>>>(rv);
     count_launch();
+    mark(g, st);  // 3: levels done
     uint32_t maxlevel = 0;
     WGA_CUDA(cudaMemcpyAsync(&maxlevel, rv.maxlevel, 4, cudaMemcpyDeviceToHost, st));
     WGA_CUDA(cudaStreamSynchronize(st));
@@ -463,8 +474,13 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   }
   if (rv.h)  // hand the caller offsets relative to `first`
     launch_offsets_rebase(rv.offs + rv.h, tot[0], d_offsets, last - first + 1, st);
+  mark(g, st);  // last: resolve done
   WGA_CUDA(cudaGetLastError());
   check_device_error(g, st);
+  if (g->profiling) {
+    for (int i = 0; i < 8; ++i) g->stage_ms[i] = 0.f;
+    for (int i = 1; i < g->n_ev; ++i) cudaEventElapsedTime(&g->stage_ms[i - 1], g->ev[i - 1], g->ev[i]);
+  }
   if (h_arcs) *h_arcs = tot[1] - tot[0];
 }
 

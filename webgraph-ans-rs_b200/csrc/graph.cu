@@ -80,6 +80,35 @@ wga_graph::~wga_graph() {
     cudaFree(d_lut);
     cudaFree(d_ent);
     cudaFree(d_err);
+    if (e2e_ws) cudaFree(e2e_ws);
+    if (e2e_off) cudaFree(e2e_off);
+    if (e2e_succ) cudaFree(e2e_succ);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (pinned) {
+      if (!prelude.stream.empty()) cudaHostUnregister(prelude.stream.data());
+      if (!phases.states.empty()) cudaHostUnregister(phases.states.data());
+      if (!phases.pointers.empty()) cudaHostUnregister(phases.pointers.data());
+    }
+  }
+}
+
+void wga_graph::reupload(cudaStream_t st) {
+  if (!on_device) throw Error(WGA_E_CUDA, "graph was opened host-only");
+  const uint64_t N = prelude.number_of_nodes;
+  const uint64_t n_res = res_last - res_first;
+  if (!pinned) {  // pin the host copies once so the copies below run at full PCIe speed
+    bool ok = true;
+    if (!prelude.stream.empty()) ok &= cudaHostRegister(prelude.stream.data(), prelude.stream.size() * 2, cudaHostRegisterDefault) == cudaSuccess;
+    if (!phases.states.empty()) ok &= cudaHostRegister(phases.states.data(), phases.states.size() * 4, cudaHostRegisterDefault) == cudaSuccess;
+    if (!phases.pointers.empty()) ok &= cudaHostRegister(phases.pointers.data(), phases.pointers.size() * 8, cudaHostRegisterDefault) == cudaSuccess;
+    cudaGetLastError();
+    pinned = ok;
+  }
+  if (stream_words)
+    WGA_CUDA(cudaMemcpyAsync(d_stream, prelude.stream.data() + stream_base, stream_words * 2, cudaMemcpyHostToDevice, st));
+  if (n_res) {
+    WGA_CUDA(cudaMemcpyAsync(d_states, phases.states.data() + (N - res_last), n_res * 4, cudaMemcpyHostToDevice, st));
+    WGA_CUDA(cudaMemcpyAsync(d_ptrs, phases.pointers.data() + (N - res_last), n_res * 8, cudaMemcpyHostToDevice, st));
   }
 }
 

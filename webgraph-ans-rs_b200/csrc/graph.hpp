@@ -39,7 +39,18 @@ struct wga_graph {
   uint32_t* d_err = nullptr;  // device error word
   wga::DevGraph dev{};         // view passed to kernels
   uint64_t pointers_payload_bytes = 0;
+  bool pinned = false;          // host copies registered with cudaHostRegister (fast re-upload)
+  // optional per-stage timing of the last decode_range (bench.py's kernel breakdown)
+  bool profiling = false;
+  cudaEvent_t ev[8] = {};
+  int n_ev = 0;                 // events recorded by the last decode
+  float stage_ms[8] = {};
+  // grow-only device buffers of the host-buffer entry points
+  void* e2e_ws = nullptr; uint64_t e2e_ws_bytes = 0;
+  uint64_t* e2e_off = nullptr; uint64_t e2e_off_n = 0;
+  uint32_t* e2e_succ = nullptr; uint64_t e2e_succ_n = 0;
 
   ~wga_graph();
   void upload();
+  void reupload(cudaStream_t st);  // H2D of stream words, states and pointers only
 };

@@ -75,10 +75,17 @@ void web_list(uint64_t seed, uint64_t v, uint64_t N, double mean_degree, std::ve
   out.clear();
   Rng r(seed, v, 2);
   if (r.unit() < 0.08) return;  // dangling pages
+  mean_degree *= 1.34;  // calibration: dangling pages, dropped segments and duplicates
   web_template(seed, v / HOST, N, mean_degree, T);
+  std::sort(T.begin(), T.end());
   const bool faithful = r.unit() < 0.35;  // navigation pages copy the whole template
-  for (uint64_t x : T)
-    if (faithful || r.unit() < 0.78) out.push_back(x);
+  // the others drop whole segments of the (sorted) template, as pages of one site share link blocks
+  for (size_t i = 0; i < T.size();) {
+    size_t seg = 1 + (size_t)r.geometric(7.0);
+    bool keep = faithful || r.unit() < 0.8;
+    for (size_t k = 0; k < seg && i < T.size(); ++k, ++i)
+      if (keep) out.push_back(T[i]);
+  }
   uint64_t own = r.geometric(mean_degree * 0.08);
   for (uint64_t i = 0; i < own; ++i) {
     int64_t t = (int64_t)v + r.powerlaw_gap((double)N * 0.25);
