@@ -138,7 +138,8 @@ int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t*
 int wga_upload(wga_graph* g, void* stream);
 uint64_t wga_upload_bytes(const wga_graph* g);
 /* Per-stage device times of the last wga_decode_range (CUDA events on the caller's stream):
- * [outdegrees+scan, entropy decode, reference levels, copy resolution].  Returns the number of events. */
+ * [outdegrees+scan, entropy decode (K1), streamed merge (K2), pass 2 for span-crossing references].
+ * Returns the number of events. */
 int wga_set_profiling(wga_graph* g, int on);
 int wga_last_profile(const wga_graph* g, float* h_stage_ms8);
 
@@ -157,6 +158,11 @@ int wga_debug_expand_table(wga_graph* g, int component, void* h_out, uint64_t n_
  * start (stream_len, prelude.state)] with ONE device thread -- ANSDecoder::decode, src/ans/decoder.rs:58-87. */
 int wga_debug_decode_symbols(wga_graph* g, const uint8_t* h_components, uint64_t n, uint64_t ptr, uint32_t state,
                              uint64_t* h_out, uint64_t* h_end_ptr, uint32_t* h_end_state);
+
+/* Kernel tuning knobs of the decode path (process-wide; the parity tests shrink them so that small graphs
+ * cross span boundaries, wrap the shared-memory ring and take the overflow paths).  Keys: "k1_span",
+ * "k1_tpb", "k2_span", "k2_tpb", "ring_log2", "force_ovf", "reset". */
+int wga_debug_set_tuning(const char* key, uint64_t value);
 
 /* ---------------------------------------------------------------- model build -------------------- */
 /* ANSModel4EncoderBuilder (src/ans/model4encoder_builder.rs:39-56) with device-resident histograms. */

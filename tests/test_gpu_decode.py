@@ -110,6 +110,35 @@ def test_graph_decode_matches_oracle(W, O, gpu, n, deg, params, seed):
     assert (d_succ == succ).all()
 
 
+STRESS_TUNINGS = [
+    dict(k1_span=37, k1_tpb=32, k2_span=53, k2_tpb=64, ring_log2=8),    # many span crossings, tiny ring (wraps)
+    dict(k1_span=5, k2_span=3, ring_log2=6),                            # nearly every reference leaves its span
+    dict(force_ovf=1, k2_span=301, ring_log2=10),                        # every header in the overflow arena
+    dict(k2_span=32768, ring_log2=15, k2_tpb=128),
+]
+
+
+@pytest.mark.parametrize("tuning", range(len(STRESS_TUNINGS)))
+@pytest.mark.parametrize("n,deg,params,seed", [GRAPH_CASES[2], GRAPH_CASES[4], GRAPH_CASES[6], GRAPH_CASES[8]])
+def test_graph_decode_under_stress_tunings(W, O, gpu, n, deg, params, seed, tuning):
+    """Same parity check with the kernel knobs shrunk so that small graphs exercise span boundaries
+    (pass 2), ring wrap-around, nodes that do not fit the ring and the overflow-arena headers."""
+    off, succ = make_case(n, deg, seed)
+    og = O.OracleGraph.store_csr(off, succ, *params)
+    g = open_oracle_graph(W, og)
+    try:
+        W.set_tuning(**STRESS_TUNINGS[tuning])
+        d_off, d_succ = gpu_csr(g)
+        a, b = n // 3, n // 3 + n // 2
+        s_off, s_succ = gpu_csr(g, a, b)
+    finally:
+        W.set_tuning(reset=1)
+    assert (d_off == off).all()
+    assert (d_succ == succ).all()
+    assert (s_off == off[a:b + 1] - off[a]).all()
+    assert (s_succ == succ[off[a]:off[b]]).all()
+
+
 def test_empty_and_mostly_dangling_graphs(W, O, gpu):
     """Empty graph, and graphs where almost every record is the single Outdegree symbol 0.  (A graph
     with ONLY dangling nodes has zero entropy, which the reference cannot encode: see

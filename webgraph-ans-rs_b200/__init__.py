@@ -79,6 +79,12 @@ def cuda_available():
     return bool(lib().wga_cuda_available())
 
 
+def set_tuning(**kw):
+    """Decode-kernel tuning knobs (wga_debug_set_tuning); set_tuning(reset=1) restores the defaults."""
+    for k, v in kw.items():
+        _chk(lib().wga_debug_set_tuning(k.encode(), C.c_uint64(int(v))))
+
+
 def kernel_launches():
     return int(lib().wga_kernel_launches())
 

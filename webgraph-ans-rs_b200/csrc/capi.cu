@@ -17,6 +17,7 @@ void outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets
 void debug_expand_table(wga_graph* g, int c, void* h_out, uint64_t n_slots);
 void debug_decode_symbols(wga_graph* g, const uint8_t* h_comps, uint64_t n, uint64_t ptr, uint32_t state,
                           uint64_t* h_out, uint64_t* h_end_ptr, uint32_t* h_end_state);
+int set_tuning(const char* key, uint64_t value);
 uint64_t successors_workspace_size(const wga_graph* g, uint64_t n_queries, uint64_t max_total_arcs);
 void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t n_queries, uint64_t* d_offsets,
                       uint32_t* d_succ, uint64_t succ_capacity, void* ws, uint64_t ws_bytes, uint64_t* h_arcs,
@@ -306,6 +307,12 @@ int wga_debug_decode_symbols(wga_graph* g, const uint8_t* h_components, uint64_t
     if (!g || (!h_components && n) || (!h_out && n)) throw Error(WGA_E_ARG, "null argument");
     debug_decode_symbols(g, h_components, n, ptr, state, h_out, h_end_ptr, h_end_state);
   });
+}
+
+int wga_debug_set_tuning(const char* key, uint64_t value) {
+  int rc = set_tuning(key, value);
+  if (rc != WGA_OK) set_last_error("unknown tuning key");
+  return rc;
 }
 
 // ----------------------------------------------------------------------------------------- model

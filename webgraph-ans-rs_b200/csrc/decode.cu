@@ -7,15 +7,23 @@
 //      -> ANSBVGraphDecoderFactory::new_decoder(v)   src/bvgraph/factories/bvgraph_decoder_factory.rs:46-58
 //      -> ANSDecoder::decode(component)              src/ans/decoder.rs:58-100
 //  Pipeline (all launches on the caller's stream):
-//    K0  k_outdegree      first symbol of every record from (states[N-1-v], pointers[N-1-v]) -> outdegree
-//        cub scan         -> CSR offsets
-//    K1  k_decode_nodes   entropy-decodes every component of every node (one node per lane).
-//                         Residual gaps are prefix-summed and merged with the expanded intervals on the
-//                         fly and written straight into the TAIL of the node's final CSR slot; copy-block
-//                         lengths go to a small staging arena.  Nodes without a reference are final.
-//    K2a k_levels         reference-chain depth of every node (depth[v] = depth[v-r]+1)
-//    K2b k_resolve        per depth level: copies the masked blocks of the (finished) referenced list and
-//                         merges them with the node's extras, in place.
+//    K0  k_outdegree   first symbol of every record from (states[N-1-v], pointers[N-1-v]) -> outdegree
+//        cub scan      -> CSR offsets
+//    K1  k_entropy     phase one: entropy decode of every component of every node.  One node per LANE,
+//                      lanes pull nodes from a per-block counter and run a uniform per-symbol state
+//                      machine (which component next / how many left), so the instruction stream stays
+//                      convergent although records differ.  Decoded values are PARKED inside the node's
+//                      own final CSR slot: residuals (already prefix-summed) at the tail, copy-block
+//                      lengths (u16) and interval (start,len) pairs at the head.  Nodes that are pure
+//                      residual lists are final after K1.
+//    K2  k_merge       phase two: copy-block resolution + interval expansion + 3-way merge, streamed
+//                      through a shared-memory ring that is a sliding window over the output array.
+//                      Merge lanes take nodes in order and emit one successor per step; a lane that
+//                      copies from a referenced list follows the producer's per-node progress counter
+//                      (element-level wavefront), so reference chains do not serialise.  One writer
+//                      warp per block retires finished nodes in order with coalesced stores.
+//    K2p k_pend_*      the few nodes whose reference leaves the block's span (or that do not fit the
+//                      ring) are resolved afterwards, level by level of the remaining chain depth.
 // =============================================================================
 #include <cub/cub.cuh>
 
@@ -25,9 +33,35 @@ namespace wga {
 
 std::atomic<uint64_t> g_kernel_launches{0};
 
+// run-time tuning (tests shrink these to exercise span boundaries, ring wrap and the overflow paths)
+struct Tuning {
+  uint32_t k1_span = 2048;    // nodes per K1 block
+  uint32_t k1_tpb = 64;       // threads per K1 block
+  uint32_t k2_span = 4096;    // nodes per K2 block
+  uint32_t k2_tpb = 256;      // threads per K2 block (warp 0 = writer)
+  uint32_t ring_log2 = 13;    // K2 ring entries (u32) = 1 << ring_log2
+  uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
+};
+static Tuning g_tuning;
+
+int set_tuning(const char* key, uint64_t value) {
+  std::string k(key ? key : "");
+  if (k == "k1_span") g_tuning.k1_span = (uint32_t)value;
+  else if (k == "k1_tpb") g_tuning.k1_tpb = (uint32_t)value;
+  else if (k == "k2_span") g_tuning.k2_span = (uint32_t)value;
+  else if (k == "k2_tpb") g_tuning.k2_tpb = (uint32_t)value;
+  else if (k == "ring_log2") g_tuning.ring_log2 = (uint32_t)value;
+  else if (k == "force_ovf") g_tuning.force_ovf = (uint32_t)value;
+  else if (k == "reset") g_tuning = Tuning();
+  else return WGA_E_ARG;
+  return WGA_OK;
+}
+
 namespace {
 
 constexpr int TPB = 128;
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr uint32_t INF = 0xffffffffu;  // "stream exhausted"; successor ids are <= 0xfffffffe
 
 struct RangeView {
   uint64_t lo;        // first decoded node (halo start)
@@ -36,11 +70,14 @@ struct RangeView {
   uint32_t h;         // halo nodes: first - lo
   uint32_t* outdeg;   // n+1
   uint64_t* offs;     // n+1, relative to lo
-  uint64_t* meta;     // n : r (16 bit) | stage offset << 16
-  uint32_t* level;    // n
-  uint32_t* stage;    // staging arena for copy blocks: [b, len_0, ..., len_{b-1}] per referencing node
-  uint64_t stage_cap;
+  uint64_t* meta;     // n : per-node record of K1 (see M_*)
+  uint32_t* arena;    // overflow headers (K1) and pass-2 temporaries
+  uint64_t arena_cap;
   unsigned long long* cursor;
+  uint32_t* pend;     // nodes left to pass 2 (index relative to lo)
+  uint32_t pend_cap;
+  uint32_t* pend_count;
+  uint32_t* pend_lev;
   uint32_t* maxlevel;
   uint32_t* halo_succ;  // successors of halo nodes
   uint64_t halo_cap;
@@ -49,10 +86,39 @@ struct RangeView {
   uint32_t* err;
 };
 
+// meta word written by K1:
+//   bits 0-15 reference offset r | bit 16 header in the overflow arena | bit 17 node is final after K1
+//   bit 18 left to pass 2 (set by K2)
+//   in-slot header: bits 19-33 block count b | 34-47 interval count | 48-63 residual count
+//   overflow header: bits 19-63 arena offset of {b, ni, nres, pairs offset, blocks...}
+constexpr uint64_t M_OVF = 1ull << 16, M_DIRECT = 1ull << 17, M_PEND = 1ull << 18;
+constexpr uint32_t MAX_B = 1u << 15, MAX_NI = 1u << 14, MAX_NRES = 1u << 16;
+
 __device__ __forceinline__ uint32_t* node_slot(const RangeView& rv, uint32_t t) {
   uint64_t o = rv.offs[t];
   if (t < rv.h) return rv.halo_succ + o;
   return rv.succ + (o - rv.offs[rv.h]);
+}
+
+// Block -> node span [A,B) (indices relative to rv.lo).  Spans never straddle the halo boundary rv.h, so
+// that a span's successors are one contiguous piece of either halo_succ or succ.
+__host__ __device__ inline uint32_t span_count(uint32_t n, uint32_t h, uint32_t span) {
+  return (h + span - 1) / span + (n - h + span - 1) / span;
+}
+__device__ __forceinline__ void span_range(const RangeView& rv, uint32_t span, uint32_t blk, uint32_t& A, uint32_t& B) {
+  const uint32_t nbh = (rv.h + span - 1) / span;
+  if (blk < nbh) {
+    A = blk * span;
+    B = min(A + span, rv.h);
+  } else {
+    A = rv.h + (blk - nbh) * span;
+    B = (rv.n - A > span) ? A + span : rv.n;
+  }
+}
+// true (and error set) when the span's successors would not fit the destination
+__device__ __forceinline__ bool span_overflows(const RangeView& rv, uint32_t A, uint32_t B) {
+  if (A < rv.h) return rv.offs[B] > rv.halo_cap;
+  return rv.offs[B] - rv.offs[rv.h] > rv.succ_cap;
 }
 
 // (state, pointer) of node v: ANSBVGraphDecoderFactory::new_decoder (bvgraph_decoder_factory.rs:46-58)
@@ -128,158 +194,521 @@ __global__ void k_halo(DevGraph g, uint64_t first, uint64_t last, uint64_t* lo_o
 }
 
 // -------------------------------------------------------------------------------------------- K1
-__global__ void __launch_bounds__(TPB) k_decode_nodes(DevGraph g, RangeView rv) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= rv.n) return;
-  const uint64_t v = rv.lo + t;
-  uint32_t state, err = 0;
-  int64_t ptr;
-  load_phase(g, v, state, ptr, err);
+// Pseudo components of the per-lane state machine (0..8 are the BVGraphComponent values, mod.rs:46-61).
+enum : uint32_t { C_AFTER_BLOCKS = 9, C_FINISH = 10, C_FETCH = 11 };
+
+// Moves the header of a node (kb block lengths, kp interval pairs already parked in the slot) to a
+// record in the overflow arena.  Returns false when the arena is full.
+__device__ __noinline__ bool header_to_arena_impl(uint32_t* arena, uint64_t arena_cap, unsigned long long* cursor,
+                                                  const uint32_t* slot, uint32_t b, uint32_t kb, uint32_t ni,
+                                                  uint32_t kp, uint32_t* ao_out) {
+  const unsigned long long need = 4ull + b + 2ull * ni;
+  const unsigned long long o = atomicAdd(cursor, need);
+  if (o + need > arena_cap || o + need >= 0xFFFFFFFFull) return false;
+  const uint32_t ao = (uint32_t)o;
+  const uint32_t apo = ao + 4 + b;
+  *ao_out = ao;
+  uint32_t* rec = arena + ao;
+  rec[0] = b;
+  rec[1] = ni;
+  rec[2] = 0;
+  rec[3] = apo;
+  const uint16_t* s16 = reinterpret_cast<const uint16_t*>(slot);
+  for (uint32_t i = 0; i < kb; ++i) rec[4 + i] = s16[i];
+  const uint32_t hb = (b + 1) >> 1;
+  for (uint32_t i = 0; i < 2 * kp; ++i) arena[apo + i] = slot[hb + i];
+  return true;
+}
+__device__ __forceinline__ bool header_to_arena(const RangeView& rv, const uint32_t* slot, uint32_t b, uint32_t kb,
+                                                uint32_t ni, uint32_t kp, uint32_t& ao, uint32_t& apo) {
+  uint32_t a = 0;
+  const bool ok = header_to_arena_impl(rv.arena, rv.arena_cap, rv.cursor, slot, b, kb, ni, kp, &a);
+  ao = a;
+  apo = a + 4 + b;
+  return ok;
+}
+
+__global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint32_t span, uint32_t force_ovf) {
+  __shared__ uint32_t s_next;
+  __shared__ uint2 s_cp[WGA_COMPONENTS];
+  uint32_t A, Bn;
+  span_range(rv, span, blockIdx.x, A, Bn);
+  if (span_overflows(rv, A, Bn)) {
+    if (threadIdx.x == 0) atomicOr(rv.err, ERR_WORKSPACE);
+    return;
+  }
+  if (threadIdx.x == 0) s_next = A;
+  if (threadIdx.x < WGA_COMPONENTS) s_cp[threadIdx.x] = comp_params(g.tb, threadIdx.x);
+  __syncthreads();
   const uint16_t* lut = g.tb.lut;
   const uint2* ent = g.tb.ent;
-#define DEC(c) ans_decode(g.tb, lut, ent, (c), state, ptr, g.stream, err)
-  const uint32_t d = (uint32_t)DEC(Outdegree);
-  uint64_t meta = 0;
-  if (d != 0) {
-    uint32_t r = g.window ? (uint32_t)DEC(ReferenceOffset) : 0u;
-    uint32_t copied = 0;
-    if (r != 0) {
-      if (r > t) {
-        err |= ERR_RANGE;
-        r = 0;
-      } else {
-        const uint32_t dref = rv.outdeg[t - r];
-        const uint64_t b64 = DEC(BlockCount);
-        const uint32_t b = (uint32_t)b64;
-        if (b64 > (uint64_t)dref + 1) err |= ERR_CORRUPT;
-        unsigned long long so = atomicAdd(rv.cursor, (unsigned long long)b + 1ull);
-        bool fits = so + b + 1 <= rv.stage_cap;
-        if (!fits) err |= ERR_WORKSPACE;
-        if (fits) rv.stage[so] = b;
-        uint64_t pos = 0;
-        for (uint32_t k = 0; k < b && !(err & ERR_CORRUPT); ++k) {
-          uint64_t x = DEC(Blocks);
-          uint64_t len = k == 0 ? x : x + 1;
-          if (fits) rv.stage[so + 1 + k] = (uint32_t)len;
+  const uint32_t c_extras = g.min_interval ? (uint32_t)IntervalCount : (uint32_t)FirstResidual;
+  const uint32_t minint = g.min_interval;
+
+  uint32_t c = C_FETCH, t = 0, state = 0, d = 0, r = 0, dref = 0, b = 0, k = 0, copied = 0, pos = 0, extras = 0,
+           ni = 0, hb = 0, nres = 0, ao = 0, apo = 0;
+  int64_t ptr = 0, v = 0, prev = 0, istart = 0;
+  uint32_t* slot = nullptr;
+  uint32_t* wp = nullptr;
+  bool ovf = false, direct = false;
+
+  for (;;) {
+    uint32_t err = 0;
+    if (c == C_FETCH) {
+      t = atomicAdd(&s_next, 1u);
+      if (t >= Bn) break;
+      v = (int64_t)(rv.lo + t);
+      load_phase(g, (uint64_t)v, state, ptr, err);
+      c = Outdegree;
+      r = b = ni = copied = hb = nres = 0;
+      ovf = direct = false;
+    }
+    const uint64_t x = ans_decode_cp(s_cp[c], lut, ent, state, ptr, g.stream, err);
+    if (!err) {
+      switch (c) {
+        case Outdegree:
+          if (x > 0xFFFFFFFFull) { err = ERR_SYMBOL_WIDTH; break; }
+          d = (uint32_t)x;
+          if (d == 0) { direct = true; c = C_FINISH; break; }
+          slot = node_slot(rv, t);
+          extras = d;
+          c = g.window ? (uint32_t)ReferenceOffset : c_extras;
+          break;
+        case ReferenceOffset:
+          if (x > g.window) { err = ERR_CORRUPT; break; }
+          if (x > t) { err = ERR_RANGE; break; }
+          r = (uint32_t)x;
+          if (r == 0) c = c_extras;
+          else { dref = rv.outdeg[t - r]; c = BlockCount; }
+          break;
+        case BlockCount:
+          if (x > (uint64_t)dref + 1) { err = ERR_CORRUPT; break; }
+          b = (uint32_t)x;
+          hb = (b + 1) >> 1;
+          pos = 0;
+          k = 0;
+          if (b == 0) { copied = dref; c = C_AFTER_BLOCKS; break; }
+          if (hb > d || b >= MAX_B || dref > 0xFFFFu || force_ovf) {
+            if (!header_to_arena(rv, slot, b, 0, 0, 0, ao, apo)) { err = ERR_WORKSPACE; break; }
+            ovf = true;
+          }
+          c = Blocks;
+          break;
+        case Blocks: {
+          const uint64_t len = k == 0 ? x : x + 1;
+          if (len > (uint64_t)(dref - pos)) { err = ERR_CORRUPT; break; }
+          if (ovf) rv.arena[ao + 4 + k] = (uint32_t)len;
+          else reinterpret_cast<uint16_t*>(slot)[k] = (uint16_t)len;
           if ((k & 1) == 0) copied += (uint32_t)len;
-          pos += len;
-          if (pos > dref) err |= ERR_CORRUPT;
+          pos += (uint32_t)len;
+          if (++k == b) {
+            if ((b & 1) == 0) copied += dref - pos;
+            c = C_AFTER_BLOCKS;
+          }
+          break;
         }
-        if ((b & 1) == 0 && pos <= dref) copied += dref - (uint32_t)pos;
-        meta = (uint64_t)r | ((uint64_t)so << 16);
+        case IntervalCount:
+          if (x > extras) { err = ERR_CORRUPT; break; }
+          ni = (uint32_t)x;
+          if (ni == 0) { c = FirstResidual; break; }
+          if (ovf) {  // header already in the arena: the pairs get their own piece
+            const unsigned long long o = atomicAdd(rv.cursor, 2ull * ni);
+            if (o + 2ull * ni > rv.arena_cap || o + 2ull * ni >= 0xFFFFFFFFull) { err = ERR_WORKSPACE; break; }
+            apo = (uint32_t)o;
+            rv.arena[ao + 3] = apo;
+          } else if (ni >= MAX_NI || hb + 2ull * ni > d || force_ovf) {
+            if (!header_to_arena(rv, slot, b, b, ni, 0, ao, apo)) { err = ERR_WORKSPACE; break; }
+            ovf = true;
+          }
+          k = 0;
+          c = IntervalStart;
+          break;
+        case IntervalStart:
+          istart = k == 0 ? v + nat2int(x) : prev + 1 + (int64_t)x;
+          if (x > 0x1FFFFFFFFull || istart < 0 || istart > 0xFFFFFFFEll) { err = ERR_SYMBOL_WIDTH; break; }
+          if (ovf) rv.arena[apo + 2 * k] = (uint32_t)istart;
+          else slot[hb + 2 * k] = (uint32_t)istart;
+          c = IntervalLen;
+          break;
+        case IntervalLen: {
+          const uint64_t len = x + minint;
+          if (len > extras || len == 0) { err = ERR_CORRUPT; break; }
+          prev = istart + (int64_t)len;
+          if (prev > 0xFFFFFFFFll) { err = ERR_SYMBOL_WIDTH; break; }
+          if (ovf) rv.arena[apo + 2 * k + 1] = (uint32_t)len;
+          else slot[hb + 2 * k + 1] = (uint32_t)len;
+          extras -= (uint32_t)len;
+          if (++k == ni) c = extras ? (uint32_t)FirstResidual : (uint32_t)C_FINISH;
+          else c = IntervalStart;
+          break;
+        }
+        case FirstResidual: {
+          nres = extras;
+          direct = (r == 0 && ni == 0);
+          if (!direct && !ovf && (nres >= MAX_NRES || hb + 2ull * ni > (uint64_t)(d - nres))) {
+            if (!header_to_arena(rv, slot, b, b, ni, ni, ao, apo)) { err = ERR_WORKSPACE; break; }
+            ovf = true;
+          }
+          prev = v + nat2int(x);
+          if (x > 0x1FFFFFFFFull || prev < 0 || prev > 0xFFFFFFFEll) { err = ERR_SYMBOL_WIDTH; break; }
+          wp = slot + (d - nres);
+          *wp++ = (uint32_t)prev;
+          c = --extras ? (uint32_t)Residual : (uint32_t)C_FINISH;
+          break;
+        }
+        case Residual:
+          if (x > 0xFFFFFFFFull) { err = ERR_SYMBOL_WIDTH; break; }
+          prev = prev + 1 + (int64_t)x;
+          if (prev > 0xFFFFFFFEll) { err = ERR_SYMBOL_WIDTH; break; }
+          *wp++ = (uint32_t)prev;
+          if (--extras == 0) c = C_FINISH;
+          break;
+        default:
+          err = ERR_CORRUPT;
       }
     }
-    if (copied > d) { err |= ERR_CORRUPT; copied = d; }
-    const uint32_t extras = d - copied;
-    if (extras != 0 && !(err & (ERR_CORRUPT | ERR_WORKSPACE))) {
-      uint32_t* out = node_slot(rv, t) + copied;
-      uint32_t ni = 0;
-      if (g.min_interval != 0) {
-        uint64_t x = DEC(IntervalCount);
-        if (2 * x > extras) { err |= ERR_CORRUPT; x = 0; }
-        ni = (uint32_t)x;
+    if (c == C_AFTER_BLOCKS && !err) {
+      if (copied > d) err = ERR_CORRUPT;
+      else {
+        extras = d - copied;
+        c = extras ? c_extras : (uint32_t)C_FINISH;
       }
-      // intervals: (start,len) pairs are parked at the end of the extras region until merged
-      uint32_t* park = out + (extras - 2 * ni);
-      uint32_t nres = extras;
-      int64_t prev_end = 0;
-      for (uint32_t k = 0; k < ni; ++k) {
-        uint64_t x = DEC(IntervalStart);
-        int64_t start = k == 0 ? (int64_t)v + nat2int(x) : prev_end + 1 + (int64_t)x;
-        uint64_t len = DEC(IntervalLen) + g.min_interval;
-        if (len > nres || len < 2 || start < 0) { err |= ERR_CORRUPT; len = 0; ni = k; break; }
-        park[2 * k] = (uint32_t)start;
-        park[2 * k + 1] = (uint32_t)len;
-        prev_end = start + (int64_t)len;
-        nres -= (uint32_t)len;
+    }
+    if (err) {  // the record is inconsistent: leave the node out of phase two and report
+      atomicOr(rv.err, err);
+      rv.meta[t] = M_DIRECT;
+      c = C_FETCH;
+      continue;
+    }
+    if (c == C_FINISH) {
+      uint64_t m;
+      if (direct) m = M_DIRECT;
+      else if (ovf) {
+        rv.arena[ao + 1] = ni;
+        rv.arena[ao + 2] = nres;
+        m = (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
+      } else {
+        m = (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
       }
-      uint32_t q = 0, cur = 0;
-      uint32_t is = 0xFFFFFFFFu, il = 0;
-      if (ni) { is = park[0]; il = park[1]; }
-      int64_t prev = 0;
-      for (uint32_t k = 0; k < nres; ++k) {
-        uint64_t x = k == 0 ? DEC(FirstResidual) : DEC(Residual);
-        int64_t val = k == 0 ? (int64_t)v + nat2int(x) : prev + 1 + (int64_t)x;
-        prev = val;
-        if (val < 0 || val > 0xFFFFFFFFll) { err |= ERR_SYMBOL_WIDTH; break; }
-        while (cur < ni && is < (uint32_t)val) {
-          for (uint32_t e = 0; e < il; ++e) out[q++] = is + e;
-          ++cur;
-          if (cur < ni) { is = park[2 * cur]; il = park[2 * cur + 1]; }
-        }
-        out[q++] = (uint32_t)val;
-      }
-      while (cur < ni && !(err & ERR_SYMBOL_WIDTH)) {
-        for (uint32_t e = 0; e < il; ++e) out[q++] = is + e;
-        ++cur;
-        if (cur < ni) { is = park[2 * cur]; il = park[2 * cur + 1]; }
-      }
+      rv.meta[t] = m;
+      c = C_FETCH;
     }
   }
-#undef DEC
-  // a record that failed validation must not be resolved against its reference (K2 trusts the staging)
-  rv.meta[t] = err ? 0ull : meta;
-  if (err) atomicOr(rv.err, err);
 }
 
-// -------------------------------------------------------------------------------------------- K2a
-__global__ void __launch_bounds__(TPB) k_levels(RangeView rv) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= rv.n) return;
-  uint32_t lev = 0, u = t;
-  uint32_t r = (uint32_t)(rv.meta[u] & 0xFFFFu);
-  while (r) {
-    u -= r;
-    ++lev;
-    r = (uint32_t)(rv.meta[u] & 0xFFFFu);
+// -------------------------------------------------------------------------------------------- K2
+// The three sorted streams a successor list is the union of (webgraph BvGraph decode, SURVEY.md 8a
+// "BV record order"): copied elements of the referenced list selected by the copy blocks, expanded
+// intervals, residuals.  `RefSrc` supplies element i of the referenced list.
+struct NodeStreams {
+  // header
+  const uint16_t* blk16;
+  const uint32_t* blk32;
+  const uint32_t* pp;  // interval pairs
+  const uint32_t* rp;  // residuals
+  uint32_t b, ni, nres, dref;
+  // copy stream
+  uint32_t ci, cend, bk;
+  bool cact;
+  // interval stream
+  uint32_t ik, ival, iend;
+  // residual stream
+  uint32_t rj, rval;
+
+  __device__ __forceinline__ uint32_t blk(uint32_t k) const { return blk32 ? blk32[k] : (uint32_t)blk16[k]; }
+
+  // gs = the node's CSR slot (d entries) holding the parked header / residuals
+  __device__ __forceinline__ void setup(const RangeView& rv, uint64_t m, const uint32_t* gs, uint32_t d, uint32_t dref_) {
+    if (m & M_OVF) {
+      const uint32_t* rec = rv.arena + (uint32_t)(m >> 19);
+      b = rec[0]; ni = rec[1]; nres = rec[2];
+      blk32 = rec + 4; blk16 = nullptr;
+      pp = rv.arena + rec[3];
+    } else {
+      b = (uint32_t)(m >> 19) & (MAX_B - 1);
+      ni = (uint32_t)(m >> 34) & (MAX_NI - 1);
+      nres = (uint32_t)(m >> 48);
+      blk16 = reinterpret_cast<const uint16_t*>(gs); blk32 = nullptr;
+      pp = gs + ((b + 1) >> 1);
+    }
+    rp = gs + (d - nres);
+    rj = 0;
+    rval = nres ? rp[0] : INF;
+    ik = 0;
+    if (ni) { ival = pp[0]; iend = ival + pp[1]; } else { ival = INF; iend = INF; }
+    dref = dref_;
+    cact = false;
+    ci = cend = bk = 0;
+    if ((uint32_t)(m & 0xFFFFu)) {
+      if (b == 0) cend = dref;
+      else { cend = blk(0); bk = 1; }
+      cact = true;
+      if (ci >= cend) next_copy_block();
+    }
   }
-  rv.level[t] = lev;
-  // one atomic per warp
-  uint32_t m = lev;
-  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(rv.maxlevel, m);
+  // current copy block exhausted: skip block, then the next copy block (explicit, or the implicit tail
+  // when the block count is even)
+  __device__ __forceinline__ void next_copy_block() {
+    if (bk >= b) { cact = false; return; }
+    ci += blk(bk); ++bk;
+    if (bk < b) { cend = ci + blk(bk); ++bk; } else cend = dref;
+    if (ci >= cend) cact = false;
+  }
+  __device__ __forceinline__ void take_copy() { if (++ci == cend) next_copy_block(); }
+  __device__ __forceinline__ void take_interval() {
+    if (++ival == iend) {
+      if (++ik < ni) { ival = pp[2 * ik]; iend = ival + pp[2 * ik + 1]; } else ival = INF;
+    }
+  }
+  __device__ __forceinline__ void take_residual() { rval = (++rj < nres) ? rp[rj] : INF; }
+};
+
+constexpr uint32_t FLN = 1024;  // per-block ring of node flags (power of two)
+constexpr uint32_t ST_RING = 0, ST_DIRECT = 1, ST_POISON = 2;
+// flag word of node k (relative to the span): tag (k+1) in bits 16-31 | status in bits 14-15 | progress
+// (elements of the list already in the ring) in bits 0-13.  A tag mismatch means "not announced yet".
+constexpr uint32_t SPIN_LIMIT = 1u << 25;
+constexpr uint32_t ERR_INTERNAL = 16u;
+
+__device__ __forceinline__ void pend_push(const RangeView& rv, uint32_t t, uint64_t m) {
+  const uint32_t i = atomicAdd(rv.pend_count, 1u);
+  if (i < rv.pend_cap) rv.pend[i] = t;
+  else atomicOr(rv.err, ERR_WORKSPACE);
+  rv.meta[t] = m | M_PEND;
 }
 
-// -------------------------------------------------------------------------------------------- K2b
-__global__ void __launch_bounds__(TPB) k_resolve(RangeView rv, uint32_t lev) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= rv.n) return;
-  if (rv.level[t] != lev) return;
-  const uint64_t meta = rv.meta[t];
-  const uint32_t r = (uint32_t)(meta & 0xFFFFu);
-  const uint64_t so = meta >> 16;
-  const uint32_t u = t - r;
-  const uint32_t* ref = node_slot(rv, u);
-  const uint32_t dref = rv.outdeg[u];
-  const uint32_t d = rv.outdeg[t];
-  uint32_t* dst = node_slot(rv, t);
-  const uint32_t b = rv.stage[so];
-  const uint32_t* bl = rv.stage + so + 1;
-  uint32_t copied = 0, pos = 0;
-  for (uint32_t k = 0; k < b; ++k) {
-    uint32_t len = bl[k];
-    if ((k & 1) == 0) copied += len;
-    pos += len;
+__global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_t span, uint32_t ring_mask,
+                                                uint32_t dbig) {
+  extern __shared__ uint32_t sm[];
+  uint32_t* ring = sm;
+  volatile uint32_t* flag = sm + ring_mask + 1;
+  __shared__ uint32_t s_next;
+  __shared__ volatile uint32_t s_flushed;
+  __shared__ volatile unsigned long long s_free_pos;
+  uint32_t A, Bn;
+  span_range(rv, span, blockIdx.x, A, Bn);
+  if (span_overflows(rv, A, Bn)) {
+    if (threadIdx.x == 0) atomicOr(rv.err, ERR_WORKSPACE);
+    return;
   }
-  if ((b & 1) == 0) copied += dref - pos;
-  const uint32_t ne = d - copied;
-  const uint32_t* ext = dst + copied;
-  uint32_t p = 0, e = 0;
-  pos = 0;
-  for (uint32_t k = 0; k <= b; ++k) {
-    uint32_t len;
-    if (k < b) len = bl[k];
-    else len = dref - pos;  // implicit tail block
-    if ((k & 1) == 0) {
-      for (uint32_t i = 0; i < len; ++i) {
-        uint32_t c = ref[pos + i];
-        while (e < ne && ext[e] < c) dst[p++] = ext[e++];
-        dst[p++] = c;
+  const uint32_t nspan = Bn - A;
+  for (uint32_t i = threadIdx.x; i < FLN; i += blockDim.x) flag[i] = 0;
+  if (threadIdx.x == 0) { s_next = 0; s_flushed = 0; s_free_pos = 0; }
+  __syncthreads();
+  const uint64_t obase = rv.offs[A];
+  uint32_t* const gbase = node_slot(rv, A);  // global address of ring position 0
+  const uint32_t W = g.window;
+  const uint32_t C = ring_mask + 1;
+  const uint32_t lane = threadIdx.x & 31;
+
+  if (threadIdx.x < 32) {
+    // ---------------------------------------------------------------- writer warp: in-order retirement
+    uint32_t kw = 0;
+    while (kw < nspan) {
+      const uint32_t k = kw + lane;
+      const bool valid = k < nspan;
+      uint64_t p0 = 0, p1 = 0;
+      if (valid) { p0 = rv.offs[A + k] - obase; p1 = rv.offs[A + k + 1] - obase; }
+      const uint32_t dk = (uint32_t)(p1 - p0);
+      const uint32_t tag = (k + 1) & 0xFFFFu;
+      uint32_t w = 0, run = 0, spins = 0;
+      for (;;) {
+        bool ok = !valid;
+        if (valid) {
+          w = flag[k & (FLN - 1)];
+          ok = (w >> 16) == tag && (((w >> 14) & 3u) != ST_RING || (w & 0x3FFFu) == dk);
+        }
+        const uint32_t m = __ballot_sync(FULL, ok);
+        run = (m == FULL) ? 32u : (uint32_t)__ffs(~m) - 1u;
+        if (run) break;
+        __nanosleep(64);
+        if (++spins > SPIN_LIMIT) {
+          if (lane == 0) atomicOr(rv.err, ERR_INTERNAL);
+          return;
+        }
+      }
+      uint32_t rm = __ballot_sync(FULL, valid && (w >> 16) == tag && ((w >> 14) & 3u) == ST_RING);
+      if (run < 32) rm &= (1u << run) - 1u;
+      while (rm) {  // maximal runs of ring-resident nodes -> flat coalesced copies
+        const int s = __ffs(rm) - 1;
+        const uint32_t y = ~(rm >> s);
+        const int len = y ? __ffs(y) - 1 : 32 - s;
+        const uint64_t qs = __shfl_sync(FULL, p0, s);
+        const uint64_t qe = __shfl_sync(FULL, p1, s + len - 1);
+        for (uint64_t q = qs + lane; q < qe; q += 32) gbase[q] = ring[(uint32_t)q & ring_mask];
+        rm &= (s + len >= 32) ? 0u : ~((1u << (s + len)) - 1u);
+      }
+      kw += run;
+      __syncwarp();
+      if (lane == 0) {
+        const uint64_t fp = kw > W ? rv.offs[A + kw - W] - obase : 0ull;
+        __threadfence_block();
+        s_free_pos = fp;
+        s_flushed = kw;
       }
     }
-    pos += len;
+    return;
   }
-  // remaining extras are already in place (p == copied + e)
+
+  // ------------------------------------------------------------------ merge lanes
+  enum { S_FETCH, S_DISPATCH, S_WAIT, S_MERGE };
+  int st = S_FETCH;
+  uint32_t k = 0, t = 0, d = 0, r = 0, p = 0, kslot = 0, ktag = 0, jslot = 0, jtag = 0, rb = 0, cval = 0, idle = 0;
+  uint64_t o0 = 0, o1 = 0, m = 0;
+  const uint32_t* refg = nullptr;
+  bool havec = false;
+  NodeStreams ns;
+  for (;;) {
+    if (st == S_FETCH) {
+      k = atomicAdd(&s_next, 1u);
+      if (k >= nspan) break;
+      st = S_DISPATCH;
+      idle = 0;
+    }
+    if (st == S_DISPATCH) {
+      if (k - s_flushed + W + 2 >= FLN) {  // the flag ring would wrap onto a node still needed
+        if (++idle > SPIN_LIMIT) { atomicOr(rv.err, ERR_INTERNAL); break; }
+        continue;
+      }
+      t = A + k;
+      m = rv.meta[t];
+      o0 = rv.offs[t] - obase;
+      o1 = rv.offs[t + 1] - obase;
+      d = (uint32_t)(o1 - o0);
+      kslot = k & (FLN - 1);
+      ktag = ((k + 1) & 0xFFFFu) << 16;
+      r = (uint32_t)(m & 0xFFFFu);
+      if ((m & M_DIRECT) || d == 0) {
+        flag[kslot] = ktag | (ST_DIRECT << 14);
+        st = S_FETCH;
+        continue;
+      }
+      if (d > dbig || r > k) {  // does not fit the ring / reference before the span: pass 2
+        pend_push(rv, t, m);
+        flag[kslot] = ktag | (ST_POISON << 14);
+        st = S_FETCH;
+        continue;
+      }
+      jslot = (k - r) & (FLN - 1);
+      jtag = (k - r + 1) & 0xFFFFu;
+      st = S_WAIT;
+    }
+    if (st == S_WAIT) {
+      bool ready = o1 - s_free_pos <= (uint64_t)C;
+      uint32_t js = ST_DIRECT;
+      if (ready && r) {
+        const uint32_t w = flag[jslot];
+        ready = (w >> 16) == jtag;
+        js = (w >> 14) & 3u;
+      }
+      if (!ready) {
+        if (++idle > SPIN_LIMIT) { atomicOr(rv.err, ERR_INTERNAL); break; }
+        continue;
+      }
+      if (r && js == ST_POISON) {
+        pend_push(rv, t, m);
+        flag[kslot] = ktag | (ST_POISON << 14);
+        st = S_FETCH;
+        continue;
+      }
+      uint32_t dref = 0;
+      refg = nullptr;
+      if (r) {
+        const uint64_t ro = rv.offs[t - r] - obase;
+        dref = (uint32_t)(rv.offs[t - r + 1] - obase - ro);
+        if (js == ST_DIRECT) refg = gbase + ro;
+        else rb = (uint32_t)ro;
+      }
+      ns.setup(rv, m, gbase + o0, d, dref);
+      p = 0;
+      havec = false;
+      flag[kslot] = ktag;  // announce: ring-resident, nothing written yet
+      st = S_MERGE;
+      idle = 0;
+    }
+    // S_MERGE: one successor per step
+    if (ns.cact && !havec) {
+      uint32_t avail = ns.dref;
+      if (!refg) avail = flag[jslot] & 0x3FFFu;
+      if (ns.ci < avail) {
+        cval = refg ? refg[ns.ci] : ring[(rb + ns.ci) & ring_mask];
+        havec = true;
+      }
+    }
+    if (!ns.cact || havec) {
+      const uint32_t cv = ns.cact ? cval : INF;
+      const uint32_t mn = min(cv, min(ns.ival, ns.rval));
+      ring[((uint32_t)o0 + p) & ring_mask] = mn;
+      ++p;
+      if (mn == INF) {  // cannot happen on records K1 accepted
+        atomicOr(rv.err, ERR_CORRUPT);
+        p = d;
+      } else if (mn == cv) { havec = false; ns.take_copy(); }
+      else if (mn == ns.ival) ns.take_interval();
+      else ns.take_residual();
+      __threadfence_block();
+      flag[kslot] = ktag | p;
+      if (p == d) st = S_FETCH;
+      idle = 0;
+    } else if (++idle > SPIN_LIMIT) {
+      atomicOr(rv.err, ERR_INTERNAL);
+      break;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------- K2p
+// Chain depth of every pending node inside the pending set (1 = its reference is final).
+__global__ void __launch_bounds__(TPB) k_pend_levels(RangeView rv, uint32_t np) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t lev = 0;
+  if (i < np) {
+    uint32_t u = rv.pend[i];
+    lev = 1;
+    for (;;) {
+      const uint32_t r = (uint32_t)(rv.meta[u] & 0xFFFFu);
+      if (!r) break;
+      u -= r;
+      if (!(rv.meta[u] & M_PEND)) break;
+      ++lev;
+    }
+    rv.pend_lev[i] = lev;
+  }
+  for (int o = 16; o; o >>= 1) lev = max(lev, __shfl_xor_sync(FULL, lev, o));
+  if ((threadIdx.x & 31) == 0 && lev) atomicMax(rv.maxlevel, lev);
+}
+
+// One pending node per lane: merge from global memory into an arena temporary, then copy over the slot
+// (the slot still holds the parked header / residuals while they are being read).
+__global__ void __launch_bounds__(TPB) k_pend_resolve(DevGraph g, RangeView rv, uint32_t np, uint32_t lev) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np || rv.pend_lev[i] != lev) return;
+  const uint32_t t = rv.pend[i];
+  const uint64_t m = rv.meta[t];
+  const uint32_t r = (uint32_t)(m & 0xFFFFu);
+  uint32_t* const gs = node_slot(rv, t);
+  const uint32_t d = (uint32_t)(rv.offs[t + 1] - rv.offs[t]);
+  const uint32_t* ref = nullptr;
+  uint32_t dref = 0;
+  if (r) {
+    ref = node_slot(rv, t - r);
+    dref = (uint32_t)(rv.offs[t - r + 1] - rv.offs[t - r]);
+  }
+  const unsigned long long o = atomicAdd(rv.cursor, (unsigned long long)d);
+  if (o + d > rv.arena_cap) { atomicOr(rv.err, ERR_WORKSPACE); return; }
+  uint32_t* tmp = rv.arena + o;
+  NodeStreams ns;
+  ns.setup(rv, m, gs, d, dref);
+  for (uint32_t p = 0; p < d; ++p) {
+    const uint32_t cv = ns.cact ? ref[ns.ci] : INF;
+    const uint32_t mn = min(cv, min(ns.ival, ns.rval));
+    tmp[p] = mn;
+    if (mn == INF) { atomicOr(rv.err, ERR_CORRUPT); break; }
+    if (mn == cv) ns.take_copy();
+    else if (mn == ns.ival) ns.take_interval();
+    else ns.take_residual();
+  }
+  for (uint32_t p = 0; p < d; ++p) gs[p] = tmp[p];
 }
 
 // -------------------------------------------------------------------------------------------- debug kernels
@@ -317,21 +746,37 @@ __global__ void k_decode_symbols(DevGraph g, const uint8_t* comps, uint64_t n, i
   end[2] = err;
 }
 
+__global__ void k_offsets_rebase(const uint64_t* src, uint64_t base, uint64_t* dst, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] - base;
+}
+
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
+// Scalars at the head of the workspace (one 256-byte line, cleared per call).
+struct Scalars {
+  unsigned long long cursor;  // arena bump pointer
+  uint64_t lo;                // k_halo result
+  uint32_t maxlevel;
+  uint32_t pend_count;
+};
+
 struct WorkspacePlan {
-  uint64_t off_outdeg, off_offs, off_meta, off_level, off_scalars, off_cub, off_halo, off_stage;
-  uint64_t cub_bytes, halo_cap, fixed_bytes;
+  uint64_t off_outdeg, off_offs, off_meta, off_pend, off_pend_lev, off_cub, off_halo, off_arena;
+  uint64_t cub_bytes, halo_cap, pend_cap, fixed_bytes;
 };
 
 WorkspacePlan plan_workspace(uint64_t n) {
   WorkspacePlan p{};
   uint64_t o = 0;
-  p.off_scalars = o; o += 256;
+  o += 256;  // Scalars
   p.off_outdeg = o; o = align_up(o + 4 * (n + 1), 256);
   p.off_offs = o; o = align_up(o + 8 * (n + 1), 256);
   p.off_meta = o; o = align_up(o + 8 * n, 256);
-  p.off_level = o; o = align_up(o + 4 * n, 256);
+  p.pend_cap = n / 8 + 65536;
+  if (p.pend_cap > n) p.pend_cap = n + 1;
+  p.off_pend = o; o = align_up(o + 4 * p.pend_cap, 256);
+  p.off_pend_lev = o; o = align_up(o + 4 * p.pend_cap, 256);
   size_t cub_bytes = 0;
   cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(nullptr, U32ToU64());
   cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, it, (uint64_t*)nullptr, (int64_t)(n + 1));
@@ -339,7 +784,7 @@ WorkspacePlan plan_workspace(uint64_t n) {
   p.off_cub = o; o = align_up(o + cub_bytes, 256);
   p.halo_cap = 1u << 20;  // successors of halo nodes (u32 each)
   p.off_halo = o; o = align_up(o + 4 * p.halo_cap, 256);
-  p.off_stage = o;
+  p.off_arena = o;
   p.fixed_bytes = o;
   return p;
 }
@@ -350,22 +795,28 @@ uint64_t decode_workspace_size(const wga_graph* g, uint64_t first, uint64_t last
   uint64_t n = last - first + 4096;  // room for a halo
   WorkspacePlan p = plan_workspace(n);
   double frac = g->prelude.number_of_nodes ? (double)(last - first) / (double)g->prelude.number_of_nodes : 1.0;
-  uint64_t arcs_est = (uint64_t)((double)g->prelude.number_of_arcs * frac * 1.25) + (1u << 20);
-  uint64_t stage_cap = n + arcs_est / 2;
-  return p.fixed_bytes + 4 * stage_cap;
+  uint64_t arcs_est = (uint64_t)((double)g->prelude.number_of_arcs * frac) + (1u << 20);
+  // arena: overflow headers (rare) + pass-2 temporaries (successors of the nodes left to pass 2)
+  uint64_t arena_cap = n + arcs_est / 8 + (1u << 20);
+  return p.fixed_bytes + 4 * arena_cap;
 }
 
-static void check_device_error(wga_graph* g, cudaStream_t st) {
-  uint32_t herr = 0;
-  WGA_CUDA(cudaMemcpyAsync(&herr, g->d_err, 4, cudaMemcpyDeviceToHost, st));
-  WGA_CUDA(cudaStreamSynchronize(st));
+static void check_device_error(wga_graph* g, uint32_t herr, cudaStream_t st) {
   if (herr) {
     WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
-    if (herr & ERR_WORKSPACE) throw Error(WGA_E_WORKSPACE, "decode: block staging arena too small; pass a larger workspace");
+    if (herr & ERR_INTERNAL) throw Error(WGA_E_CUDA, "decode: internal scheduling error (spin limit reached)");
+    if (herr & ERR_WORKSPACE) throw Error(WGA_E_WORKSPACE, "decode: workspace or output buffer too small; pass larger buffers");
     if (herr & ERR_RANGE) throw Error(WGA_E_CORRUPT, "decode: a reference leaves the decoded range");
     if (herr & ERR_SYMBOL_WIDTH) throw Error(WGA_E_UNSUPPORTED, "decode: a decoded value does not fit 32 bits");
     throw Error(WGA_E_CORRUPT, "decode: inconsistent stream or tables");
   }
+}
+
+static uint32_t read_device_error(wga_graph* g, cudaStream_t st) {
+  uint32_t herr = 0;
+  WGA_CUDA(cudaMemcpyAsync(&herr, g->d_err, 4, cudaMemcpyDeviceToHost, st));
+  WGA_CUDA(cudaStreamSynchronize(st));
+  return herr;
 }
 
 void outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets, void* ws, uint64_t ws_bytes,
@@ -386,8 +837,6 @@ void outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets
   WGA_CUDA(cudaGetLastError());
 }
 
-void launch_offsets_rebase(const uint64_t* src, uint64_t base, uint64_t* dst, uint64_t n, cudaStream_t st);
-
 static void mark(wga_graph* g, cudaStream_t st) {
   if (!g->profiling || g->n_ev >= 8) return;
   if (!g->ev[g->n_ev]) cudaEventCreate(&g->ev[g->n_ev]);
@@ -404,18 +853,19 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     if (h_arcs) *h_arcs = 0;
     return;
   }
+  const Tuning tn = g_tuning;
   uint8_t* w = (uint8_t*)ws;
   if (ws_bytes < 256) throw Error(WGA_E_WORKSPACE, "workspace too small");
   WGA_CUDA(cudaMemsetAsync(w, 0, 256, st));
+  Scalars* sc = (Scalars*)w;
   g->n_ev = 0;
   mark(g, st);  // 0: start
-  uint64_t* d_lo = (uint64_t*)(w + 16);
   // ---- halo
   uint64_t lo = first;
   if (first > g->res_first && g->prelude.compression_window != 0) {
-    k_halo<<<1, 32, 0, st>>>(g->dev, first, last, d_lo, g->d_err);
+    k_halo<<<1, 32, 0, st>>>(g->dev, first, last, &sc->lo, g->d_err);
     count_launch();
-    WGA_CUDA(cudaMemcpyAsync(&lo, d_lo, 8, cudaMemcpyDeviceToHost, st));
+    WGA_CUDA(cudaMemcpyAsync(&lo, &sc->lo, 8, cudaMemcpyDeviceToHost, st));
     WGA_CUDA(cudaStreamSynchronize(st));
     if (lo < g->res_first) throw Error(WGA_E_ARG, "reference chain leaves the resident shard");
   }
@@ -427,16 +877,18 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   rv.outdeg = (uint32_t*)(w + p.off_outdeg);
   rv.offs = rv.h ? (uint64_t*)(w + p.off_offs) : d_offsets;
   rv.meta = (uint64_t*)(w + p.off_meta);
-  rv.level = (uint32_t*)(w + p.off_level);
-  rv.stage = (uint32_t*)(w + p.off_stage);
-  rv.stage_cap = (ws_bytes - p.off_stage) / 4;
-  rv.cursor = (unsigned long long*)(w + 0);
-  rv.maxlevel = (uint32_t*)(w + 8);
+  rv.arena = (uint32_t*)(w + p.off_arena);
+  rv.arena_cap = (ws_bytes - p.off_arena) / 4;
+  rv.cursor = &sc->cursor;
+  rv.pend = (uint32_t*)(w + p.off_pend);
+  rv.pend_cap = (uint32_t)p.pend_cap;
+  rv.pend_count = &sc->pend_count;
+  rv.pend_lev = (uint32_t*)(w + p.off_pend_lev);
+  rv.maxlevel = &sc->maxlevel;
   rv.halo_succ = (uint32_t*)(w + p.off_halo);
   rv.halo_cap = p.halo_cap;
   rv.succ = d_succ; rv.succ_cap = succ_capacity;
   rv.err = g->d_err;
-  const unsigned grid = (unsigned)((n + TPB - 1) / TPB);
   // ---- K0 + scan
   k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, lo, (uint32_t)n, rv.outdeg, g->d_err);
   count_launch();
@@ -447,50 +899,78 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     count_launch(2);
   }
   mark(g, st);  // 1: outdegrees + scan done
-  // capacity check needs the totals: read back (halo arcs, range arcs)
+  // ---- K1: entropy decode (spans that would overflow the output are skipped and reported)
+  {
+    uint32_t tpb = tn.k1_tpb < 32 ? 32 : (tn.k1_tpb > 128 ? 128 : tn.k1_tpb / 32 * 32);
+    uint32_t span = tn.k1_span ? tn.k1_span : 1;
+    k_entropy<<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
+    count_launch();
+  }
+  mark(g, st);  // 2: entropy decode done
+  // ---- K2: streamed merge
+  {
+    uint32_t ring_log2 = tn.ring_log2 < 6 ? 6 : (tn.ring_log2 > 15 ? 15 : tn.ring_log2);
+    uint32_t C = 1u << ring_log2;
+    uint32_t W = (uint32_t)g->prelude.compression_window;
+    uint32_t dbig = C / (W + 1);
+    if (dbig > 0x3FFFu) dbig = 0x3FFFu;
+    if (W + 2 >= FLN / 2) dbig = 0;  // window too wide for the flag ring: everything goes to pass 2
+    uint32_t span = tn.k2_span ? tn.k2_span : 1;
+    if (span > 32768) span = 32768;  // node tags are 16 bits
+    uint32_t tpb = tn.k2_tpb < 64 ? 64 : (tn.k2_tpb > 256 ? 256 : tn.k2_tpb / 32 * 32);
+    size_t smem = (size_t)(C + FLN) * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+      WGA_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (FLN + (1 << 15)) * 4));
+      attr_set = true;
+    }
+    k_merge<<<span_count(rv.n, rv.h, span), tpb, smem, st>>>(g->dev, rv, span, C - 1, dbig);
+    count_launch();
+  }
+  mark(g, st);  // 3: merge done
+  // ---- results of the fast path: totals, pending count, error word
   uint64_t tot[2] = {0, 0};
+  uint32_t np = 0, herr = 0;
   WGA_CUDA(cudaMemcpyAsync(&tot[0], rv.offs + rv.h, 8, cudaMemcpyDeviceToHost, st));
   WGA_CUDA(cudaMemcpyAsync(&tot[1], rv.offs + n, 8, cudaMemcpyDeviceToHost, st));
+  WGA_CUDA(cudaMemcpyAsync(&np, &sc->pend_count, 4, cudaMemcpyDeviceToHost, st));
+  WGA_CUDA(cudaMemcpyAsync(&herr, g->d_err, 4, cudaMemcpyDeviceToHost, st));
   WGA_CUDA(cudaStreamSynchronize(st));
-  if (tot[0] > rv.halo_cap) throw Error(WGA_E_WORKSPACE, "halo successors exceed the workspace");
-  if (tot[1] - tot[0] > succ_capacity)
+  WGA_CUDA(cudaGetLastError());
+  if (tot[0] > rv.halo_cap) { check_device_error(g, herr & ~ERR_WORKSPACE, st); if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st)); throw Error(WGA_E_WORKSPACE, "halo successors exceed the workspace"); }
+  if (tot[1] - tot[0] > succ_capacity) {
+    if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
     throw Error(WGA_E_WORKSPACE, "d_succ too small: need " + std::to_string(tot[1] - tot[0]) + " elements");
-  // ---- K1
-  k_decode_nodes<<<grid, TPB, 0, st>>>(g->dev, rv);
-  count_launch();
-  mark(g, st);  // 2: entropy decode done
-  // ---- K2
-  if (g->prelude.compression_window != 0) {
-    k_levels<<<grid, TPB, 0, st>>>(rv);
+  }
+  check_device_error(g, herr, st);
+  // ---- K2p: nodes whose reference left their span, level by level
+  if (np) {
+    if (np > rv.pend_cap) throw Error(WGA_E_WORKSPACE, "pending list exceeds the workspace");
+    const unsigned pgrid = (np + TPB - 1) / TPB;
+    k_pend_levels<<<pgrid, TPB, 0, st>>>(rv, np);
     count_launch();
-    mark(g, st);  // 3: levels done
     uint32_t maxlevel = 0;
-    WGA_CUDA(cudaMemcpyAsync(&maxlevel, rv.maxlevel, 4, cudaMemcpyDeviceToHost, st));
+    WGA_CUDA(cudaMemcpyAsync(&maxlevel, &sc->maxlevel, 4, cudaMemcpyDeviceToHost, st));
     WGA_CUDA(cudaStreamSynchronize(st));
     for (uint32_t lev = 1; lev <= maxlevel; ++lev) {
-      k_resolve<<<grid, TPB, 0, st>>>(rv, lev);
+      k_pend_resolve<<<pgrid, TPB, 0, st>>>(g->dev, rv, np, lev);
       count_launch();
     }
+    check_device_error(g, read_device_error(g, st), st);
   }
-  if (rv.h)  // hand the caller offsets relative to `first`
-    launch_offsets_rebase(rv.offs + rv.h, tot[0], d_offsets, last - first + 1, st);
-  mark(g, st);  // last: resolve done
+  if (rv.h) {  // hand the caller offsets relative to `first`
+    const uint64_t cnt = last - first + 1;
+    k_offsets_rebase<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(rv.offs + rv.h, tot[0], d_offsets, cnt);
+    count_launch();
+  }
+  mark(g, st);  // 4: pass 2 done
   WGA_CUDA(cudaGetLastError());
-  check_device_error(g, st);
   if (g->profiling) {
+    WGA_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < 8; ++i) g->stage_ms[i] = 0.f;
     for (int i = 1; i < g->n_ev; ++i) cudaEventElapsedTime(&g->stage_ms[i - 1], g->ev[i - 1], g->ev[i]);
   }
   if (h_arcs) *h_arcs = tot[1] - tot[0];
-}
-
-__global__ void k_offsets_rebase(const uint64_t* src, uint64_t base, uint64_t* dst, uint64_t n) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[i] - base;
-}
-void launch_offsets_rebase(const uint64_t* src, uint64_t base, uint64_t* dst, uint64_t n, cudaStream_t st) {
-  k_offsets_rebase<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, base, dst, n);
-  count_launch();
 }
 
 void debug_expand_table(wga_graph* g, int c, void* h_out, uint64_t n_slots) {

@@ -44,6 +44,13 @@ enum : uint32_t {
 
 #define WGA_LOWER_BOUND 65536u  // INTERVAL_LOWER_BOUND, src/ans/mod.rs:21
 
+// Per-component decode parameters packed for one 8-byte (shared-memory) load:
+//   x = lut_off | L << 16 | shift << 21 | R << 26      y = ent_off
+__host__ __device__ inline uint2 comp_params(const DevTables& tb, int c) {
+  return make_uint2(tb.lut_off[c] | ((uint32_t)tb.L[c] << 16) | ((uint32_t)tb.shift[c] << 21) | ((uint32_t)tb.R[c] << 26),
+                    tb.ent_off[c]);
+}
+
 // One ANS symbol.  Restates ANSDecoder::decode (src/ans/decoder.rs:58-87) on the packed tables:
 //   slot  = state & (2^L-1)                                   decoder.rs:59
 //   entry = owner(slot)                                       decoder.rs:60  (lut + forward walk)
@@ -51,15 +58,14 @@ enum : uint32_t {
 //   one conditional 16-bit extend                             decoder.rs:67-69, 89-93
 //   folds x { [extend]; fold=(fold<<R)|(state&(2^R-1)); state>>=R; [extend] }   decoder.rs:74-85
 //   result = (base << folds*R) | fold                         decoder.rs:86 with quasi_fold (model4decoder.rs:56-68)
-// LUT / ENT are pointers to the component-indexed packed tables (global or shared memory).
+// LUT / ENT are pointers to the component-indexed packed tables (global or shared memory); cp = comp_params(c).
 template <class LutPtr, class EntPtr>
-__device__ __forceinline__ uint64_t ans_decode(const DevTables& tb, LutPtr lut, EntPtr ent, int c,
-                                               uint32_t& state, int64_t& ptr,
-                                               const uint16_t* __restrict__ stream, uint32_t& err) {
-  const uint32_t L = tb.L[c];
+__device__ __forceinline__ uint64_t ans_decode_cp(const uint2 cp, LutPtr lut, EntPtr ent, uint32_t& state,
+                                                  int64_t& ptr, const uint16_t* __restrict__ stream, uint32_t& err) {
+  const uint32_t L = (cp.x >> 16) & 31u;
   const uint32_t slot = state & ((1u << L) - 1u);
-  uint32_t j = lut[tb.lut_off[c] + (slot >> tb.shift[c])];
-  const uint32_t eo = tb.ent_off[c];
+  uint32_t j = lut[(cp.x & 0xFFFFu) + (slot >> ((cp.x >> 21) & 31u))];
+  const uint32_t eo = cp.y;
   uint2 e = ent[eo + j];
   while (slot - (e.x & 0xFFFFu) >= (e.x >> 16)) {  // rare: several symbols share the bucket
     ++j;
@@ -78,7 +84,7 @@ __device__ __forceinline__ uint64_t ans_decode(const DevTables& tb, LutPtr lut, 
   }
   uint64_t sym = e.y & 0xFFFFu;
   if (folds) {
-    const uint32_t R = tb.R[c];
+    const uint32_t R = cp.x >> 26;
     const uint32_t rmask = (1u << R) - 1u;
     uint64_t fold = 0;
     for (uint32_t i = 0; i < folds; ++i) {
@@ -98,6 +104,13 @@ __device__ __forceinline__ uint64_t ans_decode(const DevTables& tb, LutPtr lut, 
     sym = (sym << (folds * R)) | fold;
   }
   return sym;
+}
+
+template <class LutPtr, class EntPtr>
+__device__ __forceinline__ uint64_t ans_decode(const DevTables& tb, LutPtr lut, EntPtr ent, int c,
+                                               uint32_t& state, int64_t& ptr,
+                                               const uint16_t* __restrict__ stream, uint32_t& err) {
+  return ans_decode_cp(comp_params(tb, c), lut, ent, state, ptr, stream, err);
 }
 
 __device__ __forceinline__ int64_t nat2int(uint64_t x) {
