@@ -463,11 +463,11 @@ struct NodeStreams {
   __device__ __forceinline__ void take_residual() { rval = (++rj < nres) ? rp[rj] : INF; }
 };
 
-constexpr uint32_t FLN = 1024;  // per-block ring of node flags (power of two)
+constexpr uint32_t FLN = 512;  // per-block window of in-flight nodes (power of two)
 constexpr uint32_t ST_RING = 0, ST_DIRECT = 1, ST_POISON = 2;
 // flag word of node k (relative to the span): tag (k+1) in bits 16-31 | status in bits 14-15 | progress
 // (elements of the list already in the ring) in bits 0-13.  A tag mismatch means "not announced yet".
-constexpr uint32_t SPIN_LIMIT = 1u << 25;
+constexpr uint32_t SPIN_LIMIT = 1u << 24;
 constexpr uint32_t ERR_INTERNAL = 16u;
 
 __device__ __forceinline__ void pend_push(const RangeView& rv, uint32_t t, uint64_t m) {
@@ -477,14 +477,28 @@ __device__ __forceinline__ void pend_push(const RangeView& rv, uint32_t t, uint6
   rv.meta[t] = m | M_PEND;
 }
 
+// Per-block shared state of k_merge.  All per-node arrays are indexed by (k & (FLN-1)), k relative to the span.
+struct MergeShared {
+  uint64_t meta[FLN];   // K1 record of the node (copied from HBM by the dispatcher, coalesced)
+  uint32_t flag[FLN];   // tag | status | progress (see above)
+  uint32_t rpos[FLN];   // ring position of the node's list: prefix sum of the degrees of ring-eligible nodes
+  uint32_t pos[FLN];    // output position of the node's list relative to the span start
+  uint32_t deg[FLN];    // outdegree
+  uint32_t next;        // next node to hand to a merge lane
+  uint32_t disp;        // nodes whose rpos/pos/deg/meta are valid
+  uint32_t flushed;     // nodes retired by the writer
+  uint32_t free_rpos;   // ring positions below this one may be overwritten
+};
+
 __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_t span, uint32_t ring_mask,
                                                 uint32_t dbig) {
-  extern __shared__ uint32_t sm[];
-  uint32_t* ring = sm;
-  volatile uint32_t* flag = sm + ring_mask + 1;
-  __shared__ uint32_t s_next;
-  __shared__ volatile uint32_t s_flushed;
-  __shared__ volatile unsigned long long s_free_pos;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  MergeShared& S = *reinterpret_cast<MergeShared*>(smraw);
+  uint32_t* ring = reinterpret_cast<uint32_t*>(smraw + sizeof(MergeShared));
+  volatile uint32_t* flag = S.flag;
+  volatile uint32_t* v_disp = &S.disp;
+  volatile uint32_t* v_flushed = &S.flushed;
+  volatile uint32_t* v_free = &S.free_rpos;
   uint32_t A, Bn;
   span_range(rv, span, blockIdx.x, A, Bn);
   if (span_overflows(rv, A, Bn)) {
@@ -492,59 +506,102 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
     return;
   }
   const uint32_t nspan = Bn - A;
-  for (uint32_t i = threadIdx.x; i < FLN; i += blockDim.x) flag[i] = 0;
-  if (threadIdx.x == 0) { s_next = 0; s_flushed = 0; s_free_pos = 0; }
+  for (uint32_t i = threadIdx.x; i < FLN; i += blockDim.x) S.flag[i] = 0;
+  if (threadIdx.x == 0) { S.next = 0; S.disp = 0; S.flushed = 0; S.free_rpos = 0; }
   __syncthreads();
   const uint64_t obase = rv.offs[A];
-  uint32_t* const gbase = node_slot(rv, A);  // global address of ring position 0
-  const uint32_t W = g.window;
+  uint32_t* const gbase = node_slot(rv, A);  // global address of output position 0 of the span
+  if (rv.offs[Bn] - obase >= 0xFFFFFFFFull) dbig = 0;  // positions are kept in 32 bits: leave everything to pass 2
+  const uint32_t W = dbig ? g.window : 0u;  // nothing is ring-resident when dbig == 0: no list has to be kept
   const uint32_t C = ring_mask + 1;
   const uint32_t lane = threadIdx.x & 31;
 
   if (threadIdx.x < 32) {
-    // ---------------------------------------------------------------- writer warp: in-order retirement
-    uint32_t kw = 0;
+    // ------------------------------------------------ warp 0: dispatcher (runs ahead) + writer (in-order retirement)
+    uint32_t kd = 0, kw = 0, rbase = 0, spins = 0;
+    // software-pipelined loads of the next dispatch batch
+    uint64_t nm = M_DIRECT, np0 = 0, np1 = 0;
+    auto prefetch = [&](uint32_t k0) {
+      const uint32_t k = k0 + lane;
+      nm = M_DIRECT; np0 = np1 = 0;
+      if (k < nspan) { nm = rv.meta[A + k]; np0 = rv.offs[A + k] - obase; np1 = rv.offs[A + k + 1] - obase; }
+    };
+    prefetch(0);
     while (kw < nspan) {
-      const uint32_t k = kw + lane;
-      const bool valid = k < nspan;
-      uint64_t p0 = 0, p1 = 0;
-      if (valid) { p0 = rv.offs[A + k] - obase; p1 = rv.offs[A + k + 1] - obase; }
-      const uint32_t dk = (uint32_t)(p1 - p0);
-      const uint32_t tag = (k + 1) & 0xFFFFu;
-      uint32_t w = 0, run = 0, spins = 0;
-      for (;;) {
-        bool ok = !valid;
-        if (valid) {
-          w = flag[k & (FLN - 1)];
-          ok = (w >> 16) == tag && (((w >> 14) & 3u) != ST_RING || (w & 0x3FFFu) == dk);
+      bool progressed = false;
+      // ---- dispatch one batch of 32 nodes when the window has room for it
+      if (kd < nspan && kd + 32 + W + 2 <= kw + FLN) {
+        const uint32_t k = kd + lane;
+        const bool valid = k < nspan;
+        const uint32_t d = (uint32_t)(np1 - np0);
+        const bool elig = valid && !(nm & M_DIRECT) && d != 0 && d <= dbig;
+        uint32_t sz = elig ? d : 0u, inc = sz;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(FULL, inc, o);
+          if ((int)lane >= o) inc += y;
         }
-        const uint32_t m = __ballot_sync(FULL, ok);
-        run = (m == FULL) ? 32u : (uint32_t)__ffs(~m) - 1u;
-        if (run) break;
-        __nanosleep(64);
+        if (valid) {
+          const uint32_t sl = k & (FLN - 1);
+          S.meta[sl] = nm;
+          S.rpos[sl] = rbase + inc - sz;
+          S.pos[sl] = (uint32_t)np0;
+          S.deg[sl] = d;
+        }
+        rbase += __shfl_sync(FULL, inc, 31);
+        kd = min(kd + 32, nspan);
+        prefetch(kd);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *v_disp = kd;
+        progressed = true;
+      }
+      // ---- retire the longest prefix of finished nodes
+      {
+        const uint32_t k = kw + lane;
+        const bool valid = k < kd;
+        const uint32_t sl = k & (FLN - 1);
+        uint32_t w = 0, dk = 0;
+        bool ok = false;
+        if (valid) {
+          w = flag[sl];
+          dk = S.deg[sl];
+          ok = (w >> 16) == ((k + 1) & 0xFFFFu) && (((w >> 14) & 3u) != ST_RING || (w & 0x3FFFu) == dk);
+        }
+        const uint32_t mk = __ballot_sync(FULL, ok);
+        const uint32_t run = (mk == FULL) ? 32u : (uint32_t)__ffs(~mk) - 1u;
+        if (run) {
+          uint32_t rm = __ballot_sync(FULL, ok && ((w >> 14) & 3u) == ST_RING);
+          if (run < 32) rm &= (1u << run) - 1u;
+          const uint32_t mypos = valid ? S.pos[sl] : 0u, myrpos = valid ? S.rpos[sl] : 0u;
+          while (rm) {  // maximal runs of ring-resident nodes -> flat coalesced copies
+            const int s0 = __ffs(rm) - 1;
+            const uint32_t y = ~(rm >> s0);
+            const int len = y ? __ffs(y) - 1 : 32 - s0;
+            const uint32_t ps = __shfl_sync(FULL, mypos, s0);
+            const uint32_t rs = __shfl_sync(FULL, myrpos, s0);
+            const uint32_t cnt = __shfl_sync(FULL, mypos + dk, s0 + len - 1) - ps;
+            for (uint32_t q = lane; q < cnt; q += 32) gbase[ps + q] = ring[(rs + q) & ring_mask];
+            rm &= (s0 + len >= 32) ? 0u : ~((1u << (s0 + len)) - 1u);
+          }
+          kw += run;
+          __syncwarp();
+          if (lane == 0) {
+            // lists of the last W retired nodes stay (they may still be referenced)
+            const uint32_t fr = kw > W ? S.rpos[(kw - W) & (FLN - 1)] : 0u;
+            __threadfence_block();
+            *v_free = fr;
+            *v_flushed = kw;
+          }
+          progressed = true;
+        }
+      }
+      if (progressed) spins = 0;
+      else {
+        __nanosleep(32);
         if (++spins > SPIN_LIMIT) {
           if (lane == 0) atomicOr(rv.err, ERR_INTERNAL);
           return;
         }
-      }
-      uint32_t rm = __ballot_sync(FULL, valid && (w >> 16) == tag && ((w >> 14) & 3u) == ST_RING);
-      if (run < 32) rm &= (1u << run) - 1u;
-      while (rm) {  // maximal runs of ring-resident nodes -> flat coalesced copies
-        const int s = __ffs(rm) - 1;
-        const uint32_t y = ~(rm >> s);
-        const int len = y ? __ffs(y) - 1 : 32 - s;
-        const uint64_t qs = __shfl_sync(FULL, p0, s);
-        const uint64_t qe = __shfl_sync(FULL, p1, s + len - 1);
-        for (uint64_t q = qs + lane; q < qe; q += 32) gbase[q] = ring[(uint32_t)q & ring_mask];
-        rm &= (s + len >= 32) ? 0u : ~((1u << (s + len)) - 1u);
-      }
-      kw += run;
-      __syncwarp();
-      if (lane == 0) {
-        const uint64_t fp = kw > W ? rv.offs[A + kw - W] - obase : 0ull;
-        __threadfence_block();
-        s_free_pos = fp;
-        s_flushed = kw;
       }
     }
     return;
@@ -553,29 +610,27 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
   // ------------------------------------------------------------------ merge lanes
   enum { S_FETCH, S_DISPATCH, S_WAIT, S_MERGE };
   int st = S_FETCH;
-  uint32_t k = 0, t = 0, d = 0, r = 0, p = 0, kslot = 0, ktag = 0, jslot = 0, jtag = 0, rb = 0, cval = 0, idle = 0;
-  uint64_t o0 = 0, o1 = 0, m = 0;
+  uint32_t k = 0, d = 0, r = 0, p = 0, kslot = 0, ktag = 0, jslot = 0, jtag = 0, rb = 0, wb = 0, cval = 0, idle = 0;
+  uint64_t m = 0;
   const uint32_t* refg = nullptr;
   bool havec = false;
   NodeStreams ns;
   for (;;) {
     if (st == S_FETCH) {
-      k = atomicAdd(&s_next, 1u);
+      k = atomicAdd(&S.next, 1u);
       if (k >= nspan) break;
       st = S_DISPATCH;
       idle = 0;
     }
     if (st == S_DISPATCH) {
-      if (k - s_flushed + W + 2 >= FLN) {  // the flag ring would wrap onto a node still needed
+      if (k >= *v_disp) {  // the dispatcher has not reached this node yet
         if (++idle > SPIN_LIMIT) { atomicOr(rv.err, ERR_INTERNAL); break; }
         continue;
       }
-      t = A + k;
-      m = rv.meta[t];
-      o0 = rv.offs[t] - obase;
-      o1 = rv.offs[t + 1] - obase;
-      d = (uint32_t)(o1 - o0);
       kslot = k & (FLN - 1);
+      m = S.meta[kslot];
+      d = S.deg[kslot];
+      wb = S.rpos[kslot];
       ktag = ((k + 1) & 0xFFFFu) << 16;
       r = (uint32_t)(m & 0xFFFFu);
       if ((m & M_DIRECT) || d == 0) {
@@ -584,7 +639,7 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
         continue;
       }
       if (d > dbig || r > k) {  // does not fit the ring / reference before the span: pass 2
-        pend_push(rv, t, m);
+        pend_push(rv, A + k, m);
         flag[kslot] = ktag | (ST_POISON << 14);
         st = S_FETCH;
         continue;
@@ -594,7 +649,7 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
       st = S_WAIT;
     }
     if (st == S_WAIT) {
-      bool ready = o1 - s_free_pos <= (uint64_t)C;
+      bool ready = (wb + d - *v_free) <= C;
       uint32_t js = ST_DIRECT;
       if (ready && r) {
         const uint32_t w = flag[jslot];
@@ -606,7 +661,7 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
         continue;
       }
       if (r && js == ST_POISON) {
-        pend_push(rv, t, m);
+        pend_push(rv, A + k, m);
         flag[kslot] = ktag | (ST_POISON << 14);
         st = S_FETCH;
         continue;
@@ -614,12 +669,11 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
       uint32_t dref = 0;
       refg = nullptr;
       if (r) {
-        const uint64_t ro = rv.offs[t - r] - obase;
-        dref = (uint32_t)(rv.offs[t - r + 1] - obase - ro);
-        if (js == ST_DIRECT) refg = gbase + ro;
-        else rb = (uint32_t)ro;
+        dref = S.deg[jslot];
+        if (js == ST_DIRECT) refg = gbase + S.pos[jslot];
+        else rb = S.rpos[jslot];
       }
-      ns.setup(rv, m, gbase + o0, d, dref);
+      ns.setup(rv, m, gbase + S.pos[kslot], d, dref);
       p = 0;
       havec = false;
       flag[kslot] = ktag;  // announce: ring-resident, nothing written yet
@@ -638,7 +692,7 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
     if (!ns.cact || havec) {
       const uint32_t cv = ns.cact ? cval : INF;
       const uint32_t mn = min(cv, min(ns.ival, ns.rval));
-      ring[((uint32_t)o0 + p) & ring_mask] = mn;
+      ring[(wb + p) & ring_mask] = mn;
       ++p;
       if (mn == INF) {  // cannot happen on records K1 accepted
         atomicOr(rv.err, ERR_CORRUPT);
@@ -903,6 +957,8 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   {
     uint32_t tpb = tn.k1_tpb < 32 ? 32 : (tn.k1_tpb > 128 ? 128 : tn.k1_tpb / 32 * 32);
     uint32_t span = tn.k1_span ? tn.k1_span : 1;
+    // small ranges: shrink the spans so that the grid still fills the machine (148 SMs x 32 blocks)
+    span = std::min<uint32_t>(span, std::max<uint32_t>(128u, (uint32_t)(n / (148 * 32))));
     k_entropy<<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
     count_launch();
   }
@@ -914,14 +970,15 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     uint32_t W = (uint32_t)g->prelude.compression_window;
     uint32_t dbig = C / (W + 1);
     if (dbig > 0x3FFFu) dbig = 0x3FFFu;
-    if (W + 2 >= FLN / 2) dbig = 0;  // window too wide for the flag ring: everything goes to pass 2
+    if (W + 2 + 64 >= FLN) dbig = 0;  // window too wide for the in-flight node window: everything goes to pass 2
     uint32_t span = tn.k2_span ? tn.k2_span : 1;
+    span = std::min<uint32_t>(span, std::max<uint32_t>(512u, (uint32_t)(n / (148 * 8))));
     if (span > 32768) span = 32768;  // node tags are 16 bits
     uint32_t tpb = tn.k2_tpb < 64 ? 64 : (tn.k2_tpb > 256 ? 256 : tn.k2_tpb / 32 * 32);
-    size_t smem = (size_t)(C + FLN) * 4;
+    size_t smem = sizeof(MergeShared) + (size_t)C * 4;
     static bool attr_set = false;
     if (!attr_set) {
-      WGA_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (FLN + (1 << 15)) * 4));
+      WGA_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MergeShared) + (4u << 15))));
       attr_set = true;
     }
     k_merge<<<span_count(rv.n, rv.h, span), tpb, smem, st>>>(g->dev, rv, span, C - 1, dbig);
