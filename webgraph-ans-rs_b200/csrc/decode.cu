@@ -195,7 +195,7 @@ __global__ void k_halo(DevGraph g, uint64_t first, uint64_t last, uint64_t* lo_o
 
 // -------------------------------------------------------------------------------------------- K1
 // Pseudo components of the per-lane state machine (0..8 are the BVGraphComponent values, mod.rs:46-61).
-enum : uint32_t { C_AFTER_BLOCKS = 9, C_FINISH = 10, C_FETCH = 11 };
+enum : uint32_t { C_AFTER_BLOCKS = 9, C_FINISH = 10, C_FETCH = 11, C_IDLE = 12 };
 
 // Moves the header of a node (kb block lengths, kp interval pairs already parked in the slot) to a
 // record in the overflow arena.  Returns false when the arena is full.
@@ -230,7 +230,7 @@ __device__ __forceinline__ bool header_to_arena(const RangeView& rv, const uint3
 
 __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint32_t span, uint32_t force_ovf) {
   __shared__ uint32_t s_next;
-  __shared__ uint2 s_cp[WGA_COMPONENTS];
+  __shared__ uint4 s_cp[WGA_COMPONENTS];
   uint32_t A, Bn;
   span_range(rv, span, blockIdx.x, A, Bn);
   if (span_overflows(rv, A, Bn)) {
@@ -244,154 +244,171 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
   const uint2* ent = g.tb.ent;
   const uint32_t c_extras = g.min_interval ? (uint32_t)IntervalCount : (uint32_t)FirstResidual;
   const uint32_t minint = g.min_interval;
+  const uint32_t window = g.window;
 
+  // per-lane record state
   uint32_t c = C_FETCH, t = 0, state = 0, d = 0, r = 0, dref = 0, b = 0, k = 0, copied = 0, pos = 0, extras = 0,
            ni = 0, hb = 0, nres = 0, ao = 0, apo = 0;
-  int64_t ptr = 0, v = 0, prev = 0, istart = 0;
+  int64_t ptr = 0, v = 0, prev = 0;
   uint32_t* slot = nullptr;
   uint32_t* wp = nullptr;
   bool ovf = false, direct = false;
 
+  // Every lane stays in the loop until the whole warp has run out of nodes: the vote at the top is the
+  // per-iteration reconvergence point, so that the symbol decode below runs with all busy lanes together.
+  // Each case computes a `bad` flag instead of leaving early, which keeps the cases short and single-exit.
   for (;;) {
     uint32_t err = 0;
     if (c == C_FETCH) {
       t = atomicAdd(&s_next, 1u);
-      if (t >= Bn) break;
-      v = (int64_t)(rv.lo + t);
-      load_phase(g, (uint64_t)v, state, ptr, err);
-      c = Outdegree;
-      r = b = ni = copied = hb = nres = 0;
-      ovf = direct = false;
+      if (t >= Bn) c = C_IDLE;
+      else {
+        v = (int64_t)(rv.lo + t);
+        load_phase(g, (uint64_t)v, state, ptr, err);
+        c = Outdegree;
+        r = b = ni = copied = hb = nres = 0;
+        ovf = direct = false;
+      }
     }
-    const uint64_t x = ans_decode_cp(s_cp[c], lut, ent, state, ptr, g.stream, err);
-    if (!err) {
-      switch (c) {
-        case Outdegree:
-          if (x > 0xFFFFFFFFull) { err = ERR_SYMBOL_WIDTH; break; }
-          d = (uint32_t)x;
-          if (d == 0) { direct = true; c = C_FINISH; break; }
-          slot = node_slot(rv, t);
-          extras = d;
-          c = g.window ? (uint32_t)ReferenceOffset : c_extras;
-          break;
-        case ReferenceOffset:
-          if (x > g.window) { err = ERR_CORRUPT; break; }
-          if (x > t) { err = ERR_RANGE; break; }
-          r = (uint32_t)x;
-          if (r == 0) c = c_extras;
-          else { dref = rv.outdeg[t - r]; c = BlockCount; }
-          break;
-        case BlockCount:
-          if (x > (uint64_t)dref + 1) { err = ERR_CORRUPT; break; }
-          b = (uint32_t)x;
-          hb = (b + 1) >> 1;
-          pos = 0;
-          k = 0;
-          if (b == 0) { copied = dref; c = C_AFTER_BLOCKS; break; }
-          if (hb > d || b >= MAX_B || dref > 0xFFFFu || force_ovf) {
-            if (!header_to_arena(rv, slot, b, 0, 0, 0, ao, apo)) { err = ERR_WORKSPACE; break; }
-            ovf = true;
+    if (__all_sync(FULL, c == C_IDLE)) break;
+    if (c <= Residual) {
+      const uint64_t x = ans_decode_cp(s_cp[c], lut, ent, state, ptr, g.stream, err);
+      const uint32_t xl = (uint32_t)x;
+      const bool wide = (x >> 32) != 0;  // no component value of a valid record needs more than 32 bits
+      if (wide && !err) err = ERR_SYMBOL_WIDTH;  // (nat2int arguments: ids < 2^32 give x < 2^33, checked below)
+      if (c >= FirstResidual) {
+        // ---- residuals: value = node + nat2int(x) | previous + 1 + x   (most frequent symbols)
+        if (c == FirstResidual) {
+          if (err == ERR_SYMBOL_WIDTH && x <= 0x1FFFFFFFFull) err = 0;
+          nres = extras;
+          direct = (r == 0 && ni == 0);
+          if (!direct && !ovf && (nres >= MAX_NRES || hb + 2ull * ni > (uint64_t)(d - nres))) {
+            if (header_to_arena(rv, slot, b, b, ni, ni, ao, apo)) ovf = true;
+            else err |= ERR_WORKSPACE;
           }
-          c = Blocks;
-          break;
-        case Blocks: {
-          const uint64_t len = k == 0 ? x : x + 1;
-          if (len > (uint64_t)(dref - pos)) { err = ERR_CORRUPT; break; }
-          if (ovf) rv.arena[ao + 4 + k] = (uint32_t)len;
+          wp = slot + (d - nres);
+          prev = v + nat2int(x);
+        } else {
+          prev = prev + 1 + (int64_t)xl;
+        }
+        if (prev < 0 || prev > 0xFFFFFFFEll) err |= ERR_SYMBOL_WIDTH;
+        if (!err) {
+          *wp++ = (uint32_t)prev;
+          c = --extras ? (uint32_t)Residual : (uint32_t)C_FINISH;
+        }
+      } else if (c == Blocks) {
+        const uint32_t len = xl + (k != 0);
+        if (len > dref - pos || len < xl) err |= ERR_CORRUPT;
+        if (!err) {
+          if (ovf) rv.arena[ao + 4 + k] = len;
           else reinterpret_cast<uint16_t*>(slot)[k] = (uint16_t)len;
-          if ((k & 1) == 0) copied += (uint32_t)len;
-          pos += (uint32_t)len;
+          if ((k & 1) == 0) copied += len;
+          pos += len;
           if (++k == b) {
             if ((b & 1) == 0) copied += dref - pos;
             c = C_AFTER_BLOCKS;
           }
-          break;
         }
-        case IntervalCount:
-          if (x > extras) { err = ERR_CORRUPT; break; }
-          ni = (uint32_t)x;
-          if (ni == 0) { c = FirstResidual; break; }
-          if (ovf) {  // header already in the arena: the pairs get their own piece
-            const unsigned long long o = atomicAdd(rv.cursor, 2ull * ni);
-            if (o + 2ull * ni > rv.arena_cap || o + 2ull * ni >= 0xFFFFFFFFull) { err = ERR_WORKSPACE; break; }
-            apo = (uint32_t)o;
-            rv.arena[ao + 3] = apo;
-          } else if (ni >= MAX_NI || hb + 2ull * ni > d || force_ovf) {
-            if (!header_to_arena(rv, slot, b, b, ni, 0, ao, apo)) { err = ERR_WORKSPACE; break; }
-            ovf = true;
+      } else if (c >= IntervalStart) {
+        if (c == IntervalStart) {
+          if (err == ERR_SYMBOL_WIDTH && x <= 0x1FFFFFFFFull) err = 0;
+          prev = k == 0 ? v + nat2int(x) : prev + 1 + (int64_t)x;  // prev: start of this interval
+          if (prev < 0 || prev > 0xFFFFFFFEll) err |= ERR_SYMBOL_WIDTH;
+          if (!err) {
+            if (ovf) rv.arena[apo + 2 * k] = (uint32_t)prev;
+            else slot[hb + 2 * k] = (uint32_t)prev;
+            c = IntervalLen;
           }
+        } else {
+          const uint64_t len = (uint64_t)xl + minint;
+          if (len > extras || len == 0) err |= ERR_CORRUPT;
+          prev += (int64_t)len;  // prev: one past the end of this interval
+          if (prev > 0xFFFFFFFFll) err |= ERR_SYMBOL_WIDTH;
+          if (!err) {
+            if (ovf) rv.arena[apo + 2 * k + 1] = (uint32_t)len;
+            else slot[hb + 2 * k + 1] = (uint32_t)len;
+            extras -= (uint32_t)len;
+            if (++k == ni) c = extras ? (uint32_t)FirstResidual : (uint32_t)C_FINISH;
+            else c = IntervalStart;
+          }
+        }
+      } else if (c == Outdegree) {
+        d = xl;
+        extras = d;
+        if (!err) {
+          if (d == 0) { direct = true; c = C_FINISH; }
+          else {
+            slot = node_slot(rv, t);
+            c = window ? (uint32_t)ReferenceOffset : c_extras;
+          }
+        }
+      } else if (c == ReferenceOffset) {
+        if (xl > window) err |= ERR_CORRUPT;
+        else if (xl > t) err |= ERR_RANGE;
+        if (!err) {
+          r = xl;
+          if (r == 0) c = c_extras;
+          else { dref = rv.outdeg[t - r]; c = BlockCount; }
+        }
+      } else if (c == BlockCount) {
+        if (x > (uint64_t)dref + 1) err |= ERR_CORRUPT;
+        if (!err) {
+          b = xl;
+          hb = (b + 1) >> 1;
+          pos = 0;
           k = 0;
-          c = IntervalStart;
-          break;
-        case IntervalStart:
-          istart = k == 0 ? v + nat2int(x) : prev + 1 + (int64_t)x;
-          if (x > 0x1FFFFFFFFull || istart < 0 || istart > 0xFFFFFFFEll) { err = ERR_SYMBOL_WIDTH; break; }
-          if (ovf) rv.arena[apo + 2 * k] = (uint32_t)istart;
-          else slot[hb + 2 * k] = (uint32_t)istart;
-          c = IntervalLen;
-          break;
-        case IntervalLen: {
-          const uint64_t len = x + minint;
-          if (len > extras || len == 0) { err = ERR_CORRUPT; break; }
-          prev = istart + (int64_t)len;
-          if (prev > 0xFFFFFFFFll) { err = ERR_SYMBOL_WIDTH; break; }
-          if (ovf) rv.arena[apo + 2 * k + 1] = (uint32_t)len;
-          else slot[hb + 2 * k + 1] = (uint32_t)len;
-          extras -= (uint32_t)len;
-          if (++k == ni) c = extras ? (uint32_t)FirstResidual : (uint32_t)C_FINISH;
-          else c = IntervalStart;
-          break;
-        }
-        case FirstResidual: {
-          nres = extras;
-          direct = (r == 0 && ni == 0);
-          if (!direct && !ovf && (nres >= MAX_NRES || hb + 2ull * ni > (uint64_t)(d - nres))) {
-            if (!header_to_arena(rv, slot, b, b, ni, ni, ao, apo)) { err = ERR_WORKSPACE; break; }
-            ovf = true;
+          if (b == 0) { copied = dref; c = C_AFTER_BLOCKS; }
+          else {
+            if (hb > d || b >= MAX_B || dref > 0xFFFFu || force_ovf) {
+              if (header_to_arena(rv, slot, b, 0, 0, 0, ao, apo)) ovf = true;
+              else err |= ERR_WORKSPACE;
+            }
+            c = Blocks;
           }
-          prev = v + nat2int(x);
-          if (x > 0x1FFFFFFFFull || prev < 0 || prev > 0xFFFFFFFEll) { err = ERR_SYMBOL_WIDTH; break; }
-          wp = slot + (d - nres);
-          *wp++ = (uint32_t)prev;
-          c = --extras ? (uint32_t)Residual : (uint32_t)C_FINISH;
-          break;
         }
-        case Residual:
-          if (x > 0xFFFFFFFFull) { err = ERR_SYMBOL_WIDTH; break; }
-          prev = prev + 1 + (int64_t)x;
-          if (prev > 0xFFFFFFFEll) { err = ERR_SYMBOL_WIDTH; break; }
-          *wp++ = (uint32_t)prev;
-          if (--extras == 0) c = C_FINISH;
-          break;
-        default:
-          err = ERR_CORRUPT;
+      } else {  // IntervalCount
+        if (xl > extras) err |= ERR_CORRUPT;
+        if (!err) {
+          ni = xl;
+          k = 0;
+          if (ni == 0) c = FirstResidual;
+          else {
+            if (ovf) {  // header already in the arena: the pairs get their own piece
+              const unsigned long long o = atomicAdd(rv.cursor, 2ull * ni);
+              if (o + 2ull * ni > rv.arena_cap || o + 2ull * ni >= 0xFFFFFFFFull) err |= ERR_WORKSPACE;
+              else { apo = (uint32_t)o; rv.arena[ao + 3] = apo; }
+            } else if (ni >= MAX_NI || hb + 2ull * ni > d || force_ovf) {
+              if (header_to_arena(rv, slot, b, b, ni, 0, ao, apo)) ovf = true;
+              else err |= ERR_WORKSPACE;
+            }
+            c = IntervalStart;
+          }
+        }
       }
-    }
-    if (c == C_AFTER_BLOCKS && !err) {
-      if (copied > d) err = ERR_CORRUPT;
-      else {
-        extras = d - copied;
-        c = extras ? c_extras : (uint32_t)C_FINISH;
+      if (c == C_AFTER_BLOCKS && !err) {
+        if (copied > d) err |= ERR_CORRUPT;
+        else {
+          extras = d - copied;
+          c = extras ? c_extras : (uint32_t)C_FINISH;
+        }
       }
-    }
-    if (err) {  // the record is inconsistent: leave the node out of phase two and report
-      atomicOr(rv.err, err);
-      rv.meta[t] = M_DIRECT;
-      c = C_FETCH;
-      continue;
-    }
-    if (c == C_FINISH) {
-      uint64_t m;
-      if (direct) m = M_DIRECT;
-      else if (ovf) {
-        rv.arena[ao + 1] = ni;
-        rv.arena[ao + 2] = nres;
-        m = (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
-      } else {
-        m = (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
+      if (err) {  // the record is inconsistent: leave the node out of phase two and report
+        atomicOr(rv.err, err);
+        rv.meta[t] = M_DIRECT;
+        c = C_FETCH;
+      } else if (c == C_FINISH) {
+        uint64_t m;
+        if (direct) m = M_DIRECT;
+        else if (ovf) {
+          rv.arena[ao + 1] = ni;
+          rv.arena[ao + 2] = nres;
+          m = (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
+        } else {
+          m = (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
+        }
+        rv.meta[t] = m;
+        c = C_FETCH;
       }
-      rv.meta[t] = m;
-      c = C_FETCH;
     }
   }
 }
@@ -608,105 +625,109 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
   }
 
   // ------------------------------------------------------------------ merge lanes
-  enum { S_FETCH, S_DISPATCH, S_WAIT, S_MERGE };
+  // Per-lane state machine.  Control steps (fetch a node, wait for the dispatcher / ring space / the
+  // referenced node, set the streams up) are batched: the warp runs them only when CTL_BATCH lanes need
+  // one (or periodically), so that the common iteration is the short merge step executed by all lanes.
+  enum { S_FETCH, S_DISPATCH, S_WAIT, S_MERGE, S_DONE };
+  constexpr uint32_t CTL_BATCH = 8;
   int st = S_FETCH;
-  uint32_t k = 0, d = 0, r = 0, p = 0, kslot = 0, ktag = 0, jslot = 0, jtag = 0, rb = 0, wb = 0, cval = 0, idle = 0;
+  uint32_t k = 0, d = 0, r = 0, p = 0, kslot = 0, ktag = 0, jslot = 0, jtag = 0, rb = 0, wb = 0, cval = 0, idle = 0,
+           it = 0;
   uint64_t m = 0;
   const uint32_t* refg = nullptr;
   bool havec = false;
   NodeStreams ns;
-  for (;;) {
-    if (st == S_FETCH) {
-      k = atomicAdd(&S.next, 1u);
-      if (k >= nspan) break;
-      st = S_DISPATCH;
-      idle = 0;
-    }
-    if (st == S_DISPATCH) {
-      if (k >= *v_disp) {  // the dispatcher has not reached this node yet
-        if (++idle > SPIN_LIMIT) { atomicOr(rv.err, ERR_INTERNAL); break; }
-        continue;
+  for (;; ++it) {
+    const uint32_t ctl = __ballot_sync(FULL, st != S_MERGE && st != S_DONE);
+    const uint32_t mrg = __ballot_sync(FULL, st == S_MERGE);
+    if ((ctl | mrg) == 0) break;  // every lane is done
+    if (__popc(ctl) >= CTL_BATCH || mrg == 0 || (ctl && (it & 7u) == 0)) {
+      if (st == S_FETCH) {
+        k = atomicAdd(&S.next, 1u);
+        st = k >= nspan ? S_DONE : S_DISPATCH;
+        idle = 0;
       }
-      kslot = k & (FLN - 1);
-      m = S.meta[kslot];
-      d = S.deg[kslot];
-      wb = S.rpos[kslot];
-      ktag = ((k + 1) & 0xFFFFu) << 16;
-      r = (uint32_t)(m & 0xFFFFu);
-      if ((m & M_DIRECT) || d == 0) {
-        flag[kslot] = ktag | (ST_DIRECT << 14);
-        st = S_FETCH;
-        continue;
+      if (st == S_DISPATCH) {
+        if (k < *v_disp) {
+          kslot = k & (FLN - 1);
+          m = S.meta[kslot];
+          d = S.deg[kslot];
+          wb = S.rpos[kslot];
+          ktag = ((k + 1) & 0xFFFFu) << 16;
+          r = (uint32_t)(m & 0xFFFFu);
+          if ((m & M_DIRECT) || d == 0) {
+            flag[kslot] = ktag | (ST_DIRECT << 14);
+            st = S_FETCH;
+          } else if (d > dbig || r > k) {  // does not fit the ring / reference before the span: pass 2
+            pend_push(rv, A + k, m);
+            flag[kslot] = ktag | (ST_POISON << 14);
+            st = S_FETCH;
+          } else {
+            jslot = (k - r) & (FLN - 1);
+            jtag = (k - r + 1) & 0xFFFFu;
+            st = S_WAIT;
+          }
+        } else ++idle;  // the dispatcher has not reached this node yet
       }
-      if (d > dbig || r > k) {  // does not fit the ring / reference before the span: pass 2
-        pend_push(rv, A + k, m);
-        flag[kslot] = ktag | (ST_POISON << 14);
-        st = S_FETCH;
-        continue;
-      }
-      jslot = (k - r) & (FLN - 1);
-      jtag = (k - r + 1) & 0xFFFFu;
-      st = S_WAIT;
-    }
-    if (st == S_WAIT) {
-      bool ready = (wb + d - *v_free) <= C;
-      uint32_t js = ST_DIRECT;
-      if (ready && r) {
-        const uint32_t w = flag[jslot];
-        ready = (w >> 16) == jtag;
-        js = (w >> 14) & 3u;
-      }
-      if (!ready) {
-        if (++idle > SPIN_LIMIT) { atomicOr(rv.err, ERR_INTERNAL); break; }
-        continue;
-      }
-      if (r && js == ST_POISON) {
-        pend_push(rv, A + k, m);
-        flag[kslot] = ktag | (ST_POISON << 14);
-        st = S_FETCH;
-        continue;
-      }
-      uint32_t dref = 0;
-      refg = nullptr;
-      if (r) {
-        dref = S.deg[jslot];
-        if (js == ST_DIRECT) refg = gbase + S.pos[jslot];
-        else rb = S.rpos[jslot];
-      }
-      ns.setup(rv, m, gbase + S.pos[kslot], d, dref);
-      p = 0;
-      havec = false;
-      flag[kslot] = ktag;  // announce: ring-resident, nothing written yet
-      st = S_MERGE;
-      idle = 0;
-    }
-    // S_MERGE: one successor per step
-    if (ns.cact && !havec) {
-      uint32_t avail = ns.dref;
-      if (!refg) avail = flag[jslot] & 0x3FFFu;
-      if (ns.ci < avail) {
-        cval = refg ? refg[ns.ci] : ring[(rb + ns.ci) & ring_mask];
-        havec = true;
+      if (st == S_WAIT) {
+        bool ready = (wb + d - *v_free) <= C;
+        uint32_t js = ST_DIRECT;
+        if (ready && r) {
+          const uint32_t w = flag[jslot];
+          ready = (w >> 16) == jtag;
+          js = (w >> 14) & 3u;
+        }
+        if (!ready) ++idle;
+        else if (r && js == ST_POISON) {
+          pend_push(rv, A + k, m);
+          flag[kslot] = ktag | (ST_POISON << 14);
+          st = S_FETCH;
+        } else {
+          uint32_t dref = 0;
+          refg = nullptr;
+          if (r) {
+            dref = S.deg[jslot];
+            if (js == ST_DIRECT) refg = gbase + S.pos[jslot];
+            else rb = S.rpos[jslot];
+          }
+          ns.setup(rv, m, gbase + S.pos[kslot], d, dref);
+          p = 0;
+          havec = false;
+          flag[kslot] = ktag;  // announce: ring-resident, nothing written yet
+          st = S_MERGE;
+          idle = 0;
+        }
       }
     }
-    if (!ns.cact || havec) {
-      const uint32_t cv = ns.cact ? cval : INF;
-      const uint32_t mn = min(cv, min(ns.ival, ns.rval));
-      ring[(wb + p) & ring_mask] = mn;
-      ++p;
-      if (mn == INF) {  // cannot happen on records K1 accepted
-        atomicOr(rv.err, ERR_CORRUPT);
-        p = d;
-      } else if (mn == cv) { havec = false; ns.take_copy(); }
-      else if (mn == ns.ival) ns.take_interval();
-      else ns.take_residual();
-      __threadfence_block();
-      flag[kslot] = ktag | p;
-      if (p == d) st = S_FETCH;
-      idle = 0;
-    } else if (++idle > SPIN_LIMIT) {
+    if (st == S_MERGE) {  // one successor per step
+      if (ns.cact && !havec) {
+        uint32_t avail = ns.dref;
+        if (!refg) avail = flag[jslot] & 0x3FFFu;
+        if (ns.ci < avail) {
+          cval = refg ? refg[ns.ci] : ring[(rb + ns.ci) & ring_mask];
+          havec = true;
+        }
+      }
+      if (!ns.cact || havec) {
+        const uint32_t cv = ns.cact ? cval : INF;
+        const uint32_t mn = min(cv, min(ns.ival, ns.rval));
+        ring[(wb + p) & ring_mask] = mn;
+        ++p;
+        if (mn == INF) {  // cannot happen on records K1 accepted
+          atomicOr(rv.err, ERR_CORRUPT);
+          p = d;
+        } else if (mn == cv) { havec = false; ns.take_copy(); }
+        else if (mn == ns.ival) ns.take_interval();
+        else ns.take_residual();
+        __threadfence_block();
+        flag[kslot] = ktag | p;
+        if (p == d) st = S_FETCH;
+        idle = 0;
+      } else ++idle;
+    }
+    if (idle > SPIN_LIMIT) {
       atomicOr(rv.err, ERR_INTERNAL);
-      break;
+      st = S_DONE;
     }
   }
 }

@@ -44,11 +44,20 @@ enum : uint32_t {
 
 #define WGA_LOWER_BOUND 65536u  // INTERVAL_LOWER_BOUND, src/ans/mod.rs:21
 
-// Per-component decode parameters packed for one 8-byte (shared-memory) load:
-//   x = lut_off | L << 16 | shift << 21 | R << 26      y = ent_off
-__host__ __device__ inline uint2 comp_params(const DevTables& tb, int c) {
-  return make_uint2(tb.lut_off[c] | ((uint32_t)tb.L[c] << 16) | ((uint32_t)tb.shift[c] << 21) | ((uint32_t)tb.R[c] << 26),
-                    tb.ent_off[c]);
+// Per-component decode parameters packed for one 16-byte (shared-memory) load:
+//   x = lut_off | L << 16 | shift << 21 | R << 26      y = ent_off     z = floor(65536/R)+1 (division by R)
+__host__ __device__ inline uint4 comp_params(const DevTables& tb, int c) {
+  const uint32_t R = tb.R[c] ? tb.R[c] : 1u;
+  return make_uint4(tb.lut_off[c] | ((uint32_t)tb.L[c] << 16) | ((uint32_t)tb.shift[c] << 21) | (R << 26),
+                    tb.ent_off[c], 65536u / R + 1u, 0u);
+}
+
+// One 16-bit extend (decoder.rs:89-93).  false = the stream is exhausted.
+__device__ __forceinline__ bool ans_extend(uint32_t& state, int64_t& ptr, const uint16_t* __restrict__ stream) {
+  if (ptr <= 0) return false;
+  --ptr;
+  state = (state << 16) | stream[ptr];
+  return true;
 }
 
 // One ANS symbol.  Restates ANSDecoder::decode (src/ans/decoder.rs:58-87) on the packed tables:
@@ -58,9 +67,13 @@ __host__ __device__ inline uint2 comp_params(const DevTables& tb, int c) {
 //   one conditional 16-bit extend                             decoder.rs:67-69, 89-93
 //   folds x { [extend]; fold=(fold<<R)|(state&(2^R-1)); state>>=R; [extend] }   decoder.rs:74-85
 //   result = (base << folds*R) | fold                         decoder.rs:86 with quasi_fold (model4decoder.rs:56-68)
+// The fold loop of the reference takes R bits per trip (up to 38 trips).  Between two extends the trips
+// only shift the state, so they are done here in one step per extend: with n = bit length of the state,
+// the next j = ceil((n-16)/R) trips need no extend (the state stays >= 2^16 until the j-th shift), they
+// consume the low j*R bits, and the chunks enter `fold` first-taken-highest, i.e. in reversed group order.
 // LUT / ENT are pointers to the component-indexed packed tables (global or shared memory); cp = comp_params(c).
 template <class LutPtr, class EntPtr>
-__device__ __forceinline__ uint64_t ans_decode_cp(const uint2 cp, LutPtr lut, EntPtr ent, uint32_t& state,
+__device__ __forceinline__ uint64_t ans_decode_cp(const uint4 cp, LutPtr lut, EntPtr ent, uint32_t& state,
                                                   int64_t& ptr, const uint16_t* __restrict__ stream, uint32_t& err) {
   const uint32_t L = (cp.x >> 16) & 31u;
   const uint32_t slot = state & ((1u << L) - 1u);
@@ -71,36 +84,36 @@ __device__ __forceinline__ uint64_t ans_decode_cp(const uint2 cp, LutPtr lut, En
     ++j;
     e = ent[eo + j];
   }
-  uint32_t folds = e.y >> 16;
+  const uint32_t folds = e.y >> 16;
   if (folds == 0xFFFFu) {  // sentinel: slot beyond the sum of frequencies
     err |= ERR_CORRUPT;
     return 0;
   }
   state = (state >> L) * (e.x >> 16) + slot - (e.x & 0xFFFFu);
-  if (state < WGA_LOWER_BOUND) {
-    if (ptr <= 0) { err |= ERR_CORRUPT; return 0; }
-    --ptr;
-    state = (state << 16) | stream[ptr];
-  }
+  if (state < WGA_LOWER_BOUND && !ans_extend(state, ptr, stream)) { err |= ERR_CORRUPT; return 0; }
   uint64_t sym = e.y & 0xFFFFu;
   if (folds) {
     const uint32_t R = cp.x >> 26;
     const uint32_t rmask = (1u << R) - 1u;
+    uint32_t rem = folds;
     uint64_t fold = 0;
-    for (uint32_t i = 0; i < folds; ++i) {
-      if (state < WGA_LOWER_BOUND) {
-        if (ptr <= 0) { err |= ERR_CORRUPT; return 0; }
-        --ptr;
-        state = (state << 16) | stream[ptr];
+    do {
+      const uint32_t n = 32u - (uint32_t)__clz((int)state);     // 17..32 (state >= 2^16 here)
+      uint32_t t = ((n - 16u + R - 1u) * cp.z) >> 16;            // ceil((n-16)/R): trips until state < 2^16
+      t = max(min(t, rem), 1u);  // >= 1 also on corrupt input (state < 2^16 after an extend)
+      const uint32_t nb = t * R;                                 // <= 25 bits
+      uint32_t bits = state & ((1u << nb) - 1u);
+      state >>= nb;
+      uint32_t grp;
+      if (R == 1) grp = __brev(bits) >> (32u - nb);
+      else {
+        grp = 0;
+        for (uint32_t q = 0; q < t; ++q) { grp = (grp << R) | (bits & rmask); bits >>= R; }
       }
-      fold = (fold << R) | (uint64_t)(state & rmask);
-      state >>= R;
-      if (state < WGA_LOWER_BOUND) {
-        if (ptr <= 0) { err |= ERR_CORRUPT; return 0; }
-        --ptr;
-        state = (state << 16) | stream[ptr];
-      }
-    }
+      fold = (fold << nb) | grp;
+      rem -= t;
+      if (state < WGA_LOWER_BOUND && !ans_extend(state, ptr, stream)) { err |= ERR_CORRUPT; return 0; }
+    } while (rem);
     sym = (sym << (folds * R)) | fold;
   }
   return sym;
