@@ -18,6 +18,7 @@ void debug_expand_table(wga_graph* g, int c, void* h_out, uint64_t n_slots);
 void debug_decode_symbols(wga_graph* g, const uint8_t* h_comps, uint64_t n, uint64_t ptr, uint32_t state,
                           uint64_t* h_out, uint64_t* h_end_ptr, uint32_t* h_end_state);
 int set_tuning(const char* key, uint64_t value);
+void last_stats(uint64_t* out16);
 uint64_t successors_workspace_size(const wga_graph* g, uint64_t n_queries, uint64_t max_total_arcs);
 void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t n_queries, uint64_t* d_offsets,
                       uint32_t* d_succ, uint64_t succ_capacity, void* ws, uint64_t ws_bytes, uint64_t* h_arcs,
@@ -314,6 +315,8 @@ int wga_debug_set_tuning(const char* key, uint64_t value) {
   if (rc != WGA_OK) set_last_error("unknown tuning key");
   return rc;
 }
+
+void wga_debug_last_stats(uint64_t* h_out16) { last_stats(h_out16); }
 
 // ----------------------------------------------------------------------------------------- model
 int wga_model_create(wga_model** out) {

@@ -41,8 +41,11 @@ struct Tuning {
   uint32_t k2_tpb = 256;      // threads per K2 block (warp 0 = writer)
   uint32_t ring_log2 = 13;    // K2 ring entries (u32) = 1 << ring_log2
   uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
+  uint32_t stats = 0;         // collect wait-reason counters (wga_debug_last_stats)
 };
 static Tuning g_tuning;
+static unsigned long long g_last_stats[16];
+void last_stats(uint64_t* out16) { for (int i = 0; i < 16; ++i) out16[i] = g_last_stats[i]; }
 
 int set_tuning(const char* key, uint64_t value) {
   std::string k(key ? key : "");
@@ -52,6 +55,7 @@ int set_tuning(const char* key, uint64_t value) {
   else if (k == "k2_tpb") g_tuning.k2_tpb = (uint32_t)value;
   else if (k == "ring_log2") g_tuning.ring_log2 = (uint32_t)value;
   else if (k == "force_ovf") g_tuning.force_ovf = (uint32_t)value;
+  else if (k == "stats") g_tuning.stats = (uint32_t)value;
   else if (k == "reset") g_tuning = Tuning();
   else return WGA_E_ARG;
   return WGA_OK;
@@ -84,6 +88,7 @@ struct RangeView {
   uint32_t* succ;       // caller's array: successors of nodes >= first
   uint64_t succ_cap;
   uint32_t* err;
+  unsigned long long* stats;  // optional debug counters (16 x u64), nullptr when disabled
 };
 
 // meta word written by K1:
@@ -419,47 +424,56 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
 // intervals, residuals.  `RefSrc` supplies element i of the referenced list.
 struct NodeStreams {
   // header
-  const uint16_t* blk16;
-  const uint32_t* blk32;
-  const uint32_t* pp;  // interval pairs
-  const uint32_t* rp;  // residuals
+  const uint32_t* blkw;  // in-slot header: word j = copy length 2j (low half) | skip length 2j+1 (high half)
+  const uint32_t* blk32; // overflow header: one u32 per block (nullptr when in-slot)
+  const uint32_t* pp;    // interval pairs
+  const uint32_t* rp;    // residuals
   uint32_t b, ni, nres, dref;
-  // copy stream
-  uint32_t ci, cend, bk;
+  // copy stream: [ci, cend) is the current copy block; bk = index of the next (skip) block.
+  // cur = header word holding the skip length that follows the current copy block, nxt = the word after it;
+  // both are loaded one step ahead so that the merge loop never waits for HBM/L2.
+  uint32_t ci, cend, bk, cur, nxt;
   bool cact;
-  // interval stream
-  uint32_t ik, ival, iend;
-  // residual stream
-  uint32_t rj, rval;
-
-  __device__ __forceinline__ uint32_t blk(uint32_t k) const { return blk32 ? blk32[k] : (uint32_t)blk16[k]; }
+  // interval stream (next pair prefetched)
+  uint32_t ik, ival, iend, nis, nil;
+  // residual stream (next value prefetched)
+  uint32_t rj, rval, rnext;
 
   // gs = the node's CSR slot (d entries) holding the parked header / residuals
   __device__ __forceinline__ void setup(const RangeView& rv, uint64_t m, const uint32_t* gs, uint32_t d, uint32_t dref_) {
     if (m & M_OVF) {
       const uint32_t* rec = rv.arena + (uint32_t)(m >> 19);
       b = rec[0]; ni = rec[1]; nres = rec[2];
-      blk32 = rec + 4; blk16 = nullptr;
+      blk32 = rec + 4; blkw = nullptr;
       pp = rv.arena + rec[3];
     } else {
       b = (uint32_t)(m >> 19) & (MAX_B - 1);
       ni = (uint32_t)(m >> 34) & (MAX_NI - 1);
       nres = (uint32_t)(m >> 48);
-      blk16 = reinterpret_cast<const uint16_t*>(gs); blk32 = nullptr;
+      blkw = gs; blk32 = nullptr;
       pp = gs + ((b + 1) >> 1);
     }
     rp = gs + (d - nres);
     rj = 0;
     rval = nres ? rp[0] : INF;
+    rnext = nres > 1 ? rp[1] : INF;
     ik = 0;
-    if (ni) { ival = pp[0]; iend = ival + pp[1]; } else { ival = INF; iend = INF; }
+    ival = iend = nis = nil = INF;
+    if (ni) { ival = pp[0]; iend = ival + pp[1]; }
+    if (ni > 1) { nis = pp[2]; nil = pp[3]; }
     dref = dref_;
     cact = false;
-    ci = cend = bk = 0;
+    ci = cend = bk = cur = nxt = 0;
     if ((uint32_t)(m & 0xFFFFu)) {
-      if (b == 0) cend = dref;
-      else { cend = blk(0); bk = 1; }
       cact = true;
+      if (b == 0) cend = dref;
+      else if (blk32) { cend = blk32[0]; bk = 1; }
+      else {
+        cur = blkw[0];
+        nxt = b > 2 ? blkw[1] : 0u;
+        cend = cur & 0xFFFFu;
+        bk = 1;
+      }
       if (ci >= cend) next_copy_block();
     }
   }
@@ -467,17 +481,34 @@ struct NodeStreams {
   // when the block count is even)
   __device__ __forceinline__ void next_copy_block() {
     if (bk >= b) { cact = false; return; }
-    ci += blk(bk); ++bk;
-    if (bk < b) { cend = ci + blk(bk); ++bk; } else cend = dref;
+    if (blk32) {
+      ci += blk32[bk]; ++bk;
+      if (bk < b) { cend = ci + blk32[bk]; ++bk; } else cend = dref;
+    } else {
+      ci += cur >> 16; ++bk;           // skip block bk (odd) lives in the high half of the current word
+      cur = nxt;
+      if (bk < b) {
+        cend = ci + (cur & 0xFFFFu); ++bk;  // copy block bk (even): low half of the next word
+        nxt = (bk + 1 < b) ? blkw[(bk + 1) >> 1] : 0u;
+      } else cend = dref;
+    }
     if (ci >= cend) cact = false;
   }
   __device__ __forceinline__ void take_copy() { if (++ci == cend) next_copy_block(); }
   __device__ __forceinline__ void take_interval() {
     if (++ival == iend) {
-      if (++ik < ni) { ival = pp[2 * ik]; iend = ival + pp[2 * ik + 1]; } else ival = INF;
+      ++ik;
+      ival = nis;
+      iend = nis + nil;
+      if (ik >= ni) ival = INF;
+      if (ik + 1 < ni) { nis = pp[2 * ik + 2]; nil = pp[2 * ik + 3]; } else nis = INF;
     }
   }
-  __device__ __forceinline__ void take_residual() { rval = (++rj < nres) ? rp[rj] : INF; }
+  __device__ __forceinline__ void take_residual() {
+    ++rj;
+    rval = rnext;
+    rnext = (rj + 1 < nres) ? rp[rj + 1] : INF;
+  }
 };
 
 constexpr uint32_t FLN = 512;  // per-block window of in-flight nodes (power of two)
@@ -507,7 +538,7 @@ struct MergeShared {
   uint32_t free_rpos;   // ring positions below this one may be overwritten
 };
 
-__global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_t span, uint32_t ring_mask,
+__global__ void __launch_bounds__(256, 4) k_merge(DevGraph g, RangeView rv, uint32_t span, uint32_t ring_mask,
                                                 uint32_t dbig) {
   extern __shared__ __align__(16) uint8_t smraw[];
   MergeShared& S = *reinterpret_cast<MergeShared*>(smraw);
@@ -535,7 +566,7 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
 
   if (threadIdx.x < 32) {
     // ------------------------------------------------ warp 0: dispatcher (runs ahead) + writer (in-order retirement)
-    uint32_t kd = 0, kw = 0, rbase = 0, spins = 0;
+    uint32_t kd = 0, kw = 0, rbase = 0, spins = 0, w_iter = 0, w_disp = 0, w_retire = 0, w_idle = 0;
     // software-pipelined loads of the next dispatch batch
     uint64_t nm = M_DIRECT, np0 = 0, np1 = 0;
     auto prefetch = [&](uint32_t k0) {
@@ -546,6 +577,7 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
     prefetch(0);
     while (kw < nspan) {
       bool progressed = false;
+      ++w_iter;
       // ---- dispatch one batch of 32 nodes when the window has room for it
       if (kd < nspan && kd + 32 + W + 2 <= kw + FLN) {
         const uint32_t k = kd + lane;
@@ -571,6 +603,7 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
         __syncwarp();
         if (lane == 0) *v_disp = kd;
         progressed = true;
+        ++w_disp;
       }
       // ---- retire the longest prefix of finished nodes
       {
@@ -610,16 +643,22 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
             *v_flushed = kw;
           }
           progressed = true;
+          ++w_retire;
         }
       }
       if (progressed) spins = 0;
       else {
+        ++w_idle;
         __nanosleep(32);
         if (++spins > SPIN_LIMIT) {
           if (lane == 0) atomicOr(rv.err, ERR_INTERNAL);
           return;
         }
       }
+    }
+    if (rv.stats && lane == 0) {
+      atomicAdd(rv.stats + 8, w_iter); atomicAdd(rv.stats + 9, w_disp); atomicAdd(rv.stats + 10, w_retire);
+      atomicAdd(rv.stats + 11, w_idle);
     }
     return;
   }
@@ -637,11 +676,15 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
   const uint32_t* refg = nullptr;
   bool havec = false;
   NodeStreams ns;
+  uint32_t n_iter = 0, n_ctl = 0, n_wdisp = 0, n_wspace = 0, n_wref = 0, n_mstall = 0, n_mwork = 0, n_done = 0;
   for (;; ++it) {
     const uint32_t ctl = __ballot_sync(FULL, st != S_MERGE && st != S_DONE);
     const uint32_t mrg = __ballot_sync(FULL, st == S_MERGE);
     if ((ctl | mrg) == 0) break;  // every lane is done
+    ++n_iter;
+    if (st == S_DONE) ++n_done;
     if (__popc(ctl) >= CTL_BATCH || mrg == 0 || (ctl && (it & 7u) == 0)) {
+      ++n_ctl;
       if (st == S_FETCH) {
         k = atomicAdd(&S.next, 1u);
         st = k >= nspan ? S_DONE : S_DISPATCH;
@@ -667,7 +710,7 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
             jtag = (k - r + 1) & 0xFFFFu;
             st = S_WAIT;
           }
-        } else ++idle;  // the dispatcher has not reached this node yet
+        } else { ++idle; ++n_wdisp; }  // the dispatcher has not reached this node yet
       }
       if (st == S_WAIT) {
         bool ready = (wb + d - *v_free) <= C;
@@ -677,7 +720,7 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
           ready = (w >> 16) == jtag;
           js = (w >> 14) & 3u;
         }
-        if (!ready) ++idle;
+        if (!ready) { ++idle; if ((wb + d - *v_free) > C) ++n_wspace; else ++n_wref; }
         else if (r && js == ST_POISON) {
           pend_push(rv, A + k, m);
           flag[kslot] = ktag | (ST_POISON << 14);
@@ -723,12 +766,18 @@ __global__ void __launch_bounds__(256) k_merge(DevGraph g, RangeView rv, uint32_
         flag[kslot] = ktag | p;
         if (p == d) st = S_FETCH;
         idle = 0;
-      } else ++idle;
+        ++n_mwork;
+      } else { ++idle; ++n_mstall; }
     }
     if (idle > SPIN_LIMIT) {
       atomicOr(rv.err, ERR_INTERNAL);
       st = S_DONE;
     }
+  }
+  if (rv.stats) {
+    atomicAdd(rv.stats + 0, n_iter); atomicAdd(rv.stats + 1, n_ctl); atomicAdd(rv.stats + 2, n_wdisp);
+    atomicAdd(rv.stats + 3, n_wspace); atomicAdd(rv.stats + 4, n_wref); atomicAdd(rv.stats + 5, n_mstall);
+    atomicAdd(rv.stats + 6, n_mwork); atomicAdd(rv.stats + 7, n_done);
   }
 }
 
@@ -834,6 +883,8 @@ struct Scalars {
   uint64_t lo;                // k_halo result
   uint32_t maxlevel;
   uint32_t pend_count;
+  uint64_t pad[5];
+  unsigned long long stats[16];  // offset 64
 };
 
 struct WorkspacePlan {
@@ -964,6 +1015,7 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   rv.halo_cap = p.halo_cap;
   rv.succ = d_succ; rv.succ_cap = succ_capacity;
   rv.err = g->d_err;
+  rv.stats = tn.stats ? sc->stats : nullptr;
   // ---- K0 + scan
   k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, lo, (uint32_t)n, rv.outdeg, g->d_err);
   count_launch();
@@ -1020,6 +1072,7 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
     throw Error(WGA_E_WORKSPACE, "d_succ too small: need " + std::to_string(tot[1] - tot[0]) + " elements");
   }
+  if (tn.stats) WGA_CUDA(cudaMemcpy(g_last_stats, sc->stats, sizeof(g_last_stats), cudaMemcpyDeviceToHost));
   check_device_error(g, herr, st);
   // ---- K2p: nodes whose reference left their span, level by level
   if (np) {
