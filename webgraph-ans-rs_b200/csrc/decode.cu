@@ -516,6 +516,14 @@ constexpr uint32_t ST_RING = 0, ST_DIRECT = 1, ST_POISON = 2;
 // flag word of node k (relative to the span): tag (k+1) in bits 16-31 | status in bits 14-15 | progress
 // (elements of the list already in the ring) in bits 0-13.  A tag mismatch means "not announced yet".
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
+// Ordering of the ring protocol.  A producer stores list elements into the ring and then its progress word;
+// a consumer loads the progress word and then the elements.  All of these are shared-memory accesses of one
+// SM, issued in program order by each thread, and the SM performs one warp's shared-memory accesses in issue
+// order, so a compiler barrier (no reordering by nvcc) is all that is needed.  A real fence
+// (__threadfence_block = MEMBAR.SC.CTA) would also wait for the thread's outstanding GLOBAL loads/stores --
+// the prefetches of the merge lanes, the output stores of the writer -- once per element: measured 2.5k
+// cycles per merge step.  Parity tests run with tiny rings / spans to exercise this protocol.
+#define SMEM_ORDER() asm volatile("" ::: "memory")
 constexpr uint32_t ERR_INTERNAL = 16u;
 
 __device__ __forceinline__ void pend_push(const RangeView& rv, uint32_t t, uint64_t m) {
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(256, 4) k_merge(DevGraph g, RangeView rv, uint
                                                 uint32_t dbig) {
   extern __shared__ __align__(16) uint8_t smraw[];
   MergeShared& S = *reinterpret_cast<MergeShared*>(smraw);
-  uint32_t* ring = reinterpret_cast<uint32_t*>(smraw + sizeof(MergeShared));
+  volatile uint32_t* ring = reinterpret_cast<volatile uint32_t*>(smraw + sizeof(MergeShared));
   volatile uint32_t* flag = S.flag;
   volatile uint32_t* v_disp = &S.disp;
   volatile uint32_t* v_flushed = &S.flushed;
@@ -599,7 +607,7 @@ __global__ void __launch_bounds__(256, 4) k_merge(DevGraph g, RangeView rv, uint
         rbase += __shfl_sync(FULL, inc, 31);
         kd = min(kd + 32, nspan);
         prefetch(kd);
-        __threadfence_block();
+        SMEM_ORDER();
         __syncwarp();
         if (lane == 0) *v_disp = kd;
         progressed = true;
@@ -638,7 +646,7 @@ __global__ void __launch_bounds__(256, 4) k_merge(DevGraph g, RangeView rv, uint
           if (lane == 0) {
             // lists of the last W retired nodes stay (they may still be referenced)
             const uint32_t fr = kw > W ? S.rpos[(kw - W) & (FLN - 1)] : 0u;
-            __threadfence_block();
+            SMEM_ORDER();
             *v_free = fr;
             *v_flushed = kw;
           }
@@ -762,7 +770,7 @@ __global__ void __launch_bounds__(256, 4) k_merge(DevGraph g, RangeView rv, uint
         } else if (mn == cv) { havec = false; ns.take_copy(); }
         else if (mn == ns.ival) ns.take_interval();
         else ns.take_residual();
-        __threadfence_block();
+        SMEM_ORDER();
         flag[kslot] = ktag | p;
         if (p == d) st = S_FETCH;
         idle = 0;
