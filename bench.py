@@ -287,15 +287,15 @@ def main():
         acc += stages
     W.lib().wga_set_profiling(g._h, 0)
     acc /= reps
-    stage_names = ["outdegree+scan(k_outdegree,cub)", "entropy_decode(k_entropy)", "merge(k_merge)+readback",
-                   "pass2(k_pend_*)"]
+    stage_names = ["outdegree+scan(k_outdegree,cub)", "entropy_decode(k_entropy)", "levels+sort(k_levels,cub)",
+                   "resolve(k_resolve x levels)"]
     kernels = {stage_names[i]: float(acc[i]) for i in range(min(4, max(0, nev - 1)))}
     peak, peak_src = measured_peak_gbs()
     step_kernel_ms = float(sum(kernels.values())) or ms
     achieved = b_alg / (step_kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "kernel": "decode step = k_outdegree + scan + k_entropy + k_merge (+ k_pend_* for span-crossing references); one launch chain per step",
+                "kernel": "decode step = k_outdegree + scan + k_entropy + k_levels + sort + k_resolve per level; one launch chain per step",
                 "algorithmic_bytes_per_step": int(b_alg), "bytes_per_arc": b_alg / max(1, arcs),
                 "stage_ms": kernels, "step_ms_events": step_kernel_ms}
 

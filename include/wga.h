@@ -138,7 +138,7 @@ int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t*
 int wga_upload(wga_graph* g, void* stream);
 uint64_t wga_upload_bytes(const wga_graph* g);
 /* Per-stage device times of the last wga_decode_range (CUDA events on the caller's stream):
- * [outdegrees+scan, entropy decode (K1), streamed merge (K2), pass 2 for span-crossing references].
+ * [outdegrees+scan, entropy decode (K1), levels+sort, resolve per level (K2)].
  * Returns the number of events. */
 int wga_set_profiling(wga_graph* g, int on);
 int wga_last_profile(const wga_graph* g, float* h_stage_ms8);
@@ -160,8 +160,8 @@ int wga_debug_decode_symbols(wga_graph* g, const uint8_t* h_components, uint64_t
                              uint64_t* h_out, uint64_t* h_end_ptr, uint32_t* h_end_state);
 
 /* Kernel tuning knobs of the decode path (process-wide; the parity tests shrink them so that small graphs
- * cross span boundaries, wrap the shared-memory ring and take the overflow paths).  Keys: "k1_span",
- * "k1_tpb", "k2_span", "k2_tpb", "ring_log2", "force_ovf", "reset". */
+ * cross span boundaries, stride the grid and take the overflow paths).  Keys: "k1_span", "k1_tpb",
+ * "k2_blocks", "force_ovf", "reset". */
 int wga_debug_set_tuning(const char* key, uint64_t value);
 /* Counters of the last wga_decode_range run with tuning "stats"=1 (16 x u64; development aid). */
 void wga_debug_last_stats(uint64_t* h_out16);

@@ -111,18 +111,18 @@ def test_graph_decode_matches_oracle(W, O, gpu, n, deg, params, seed):
 
 
 STRESS_TUNINGS = [
-    dict(k1_span=37, k1_tpb=32, k2_span=53, k2_tpb=64, ring_log2=8),    # many span crossings, tiny ring (wraps)
-    dict(k1_span=5, k2_span=3, ring_log2=6),                            # nearly every reference leaves its span
-    dict(force_ovf=1, k2_span=301, ring_log2=10),                        # every header in the overflow arena
-    dict(k2_span=32768, ring_log2=15, k2_tpb=128),
+    dict(k1_span=37, k1_tpb=32, k2_blocks=3),   # many tiny K1 spans, a K2 grid that strides many times
+    dict(k1_span=5, k2_blocks=1),
+    dict(force_ovf=1),                           # every header in the overflow arena
+    dict(k1_span=100000, k1_tpb=128, k2_blocks=5000),
 ]
 
 
 @pytest.mark.parametrize("tuning", range(len(STRESS_TUNINGS)))
 @pytest.mark.parametrize("n,deg,params,seed", [GRAPH_CASES[2], GRAPH_CASES[4], GRAPH_CASES[6], GRAPH_CASES[8]])
 def test_graph_decode_under_stress_tunings(W, O, gpu, n, deg, params, seed, tuning):
-    """Same parity check with the kernel knobs shrunk so that small graphs exercise span boundaries
-    (pass 2), ring wrap-around, nodes that do not fit the ring and the overflow-arena headers."""
+    """Same parity check with the kernel knobs changed so that small graphs exercise span boundaries,
+    grid striding and the overflow-arena headers."""
     off, succ = make_case(n, deg, seed)
     og = O.OracleGraph.store_csr(off, succ, *params)
     g = open_oracle_graph(W, og)

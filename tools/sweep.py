@@ -45,10 +45,5 @@ for spec in ["reset=1"] + sys.argv[2:]:
     chk = int(succ[:arcs].to(torch.int64).sum().item())
     if ref is None:
         ref = chk
-    if kw.get("stats") == "1":
-        st = np.zeros(16, np.uint64)
-        W.lib().wga_debug_last_stats(st.ctypes.data_as(C.c_void_p))
-        names = ["lane_iter", "ctl", "w_disp", "w_space", "w_ref", "m_stall", "m_work", "done", "wr_iter", "wr_disp", "wr_retire", "wr_idle"]
-        print("   stats:", {k: int(v) for k, v in zip(names, st)})
-    print("%-50s K0 %.3f K1 %.3f K2 %.3f P2 %.3f total %.3f ms  %s" % (spec, acc[0], acc[1], acc[2], acc[3], acc[:4].sum(),
+    print("%-50s K0 %.3f K1 %.3f LV %.3f K2 %.3f total %.3f ms  %s" % (spec, acc[0], acc[1], acc[2], acc[3], acc[:4].sum(),
                                                                     "ok" if chk == ref else "CHECKSUM MISMATCH"), flush=True)

@@ -16,14 +16,10 @@
 //                      own final CSR slot: residuals (already prefix-summed) at the tail, copy-block
 //                      lengths (u16) and interval (start,len) pairs at the head.  Nodes that are pure
 //                      residual lists are final after K1.
-//    K2  k_merge       phase two: copy-block resolution + interval expansion + 3-way merge, streamed
-//                      through a shared-memory ring that is a sliding window over the output array.
-//                      Merge lanes take nodes in order and emit one successor per step; a lane that
-//                      copies from a referenced list follows the producer's per-node progress counter
-//                      (element-level wavefront), so reference chains do not serialise.  One writer
-//                      warp per block retires finished nodes in order with coalesced stores.
-//    K2p k_pend_*      the few nodes whose reference leaves the block's span (or that do not fit the
-//                      ring) are resolved afterwards, level by level of the remaining chain depth.
+//    K2  k_levels      phase two, by reference-chain depth: depth of every node that still needs work and a
+//        cub sort      sort key (level, degree bucket) -> one segment per level, similar degrees adjacent
+//        k_resolve     per level, one node per lane: tight three-way merge (copied elements of the finished
+//                      referenced list, expanded intervals, residuals) in place into the node's CSR slot
 // =============================================================================
 #include <cub/cub.cuh>
 
@@ -36,30 +32,23 @@ std::atomic<uint64_t> g_kernel_launches{0};
 // run-time tuning (tests shrink these to exercise span boundaries, ring wrap and the overflow paths)
 struct Tuning {
   uint32_t k1_span = 2048;    // nodes per K1 block
-  uint32_t k1_tpb = 64;       // threads per K1 block
-  uint32_t k2_span = 4096;    // nodes per K2 block
-  uint32_t k2_tpb = 256;      // threads per K2 block (warp 0 = writer)
-  uint32_t ring_log2 = 13;    // K2 ring entries (u32) = 1 << ring_log2
+  uint32_t k1_tpb = 128;      // threads per K1 block
+  uint32_t k2_blocks = 148 * 12;  // K2 grid (blocks of 128 lanes striding over a level's segment)
   uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
-  uint32_t stats = 0;         // collect wait-reason counters (wga_debug_last_stats)
 };
 static Tuning g_tuning;
-static unsigned long long g_last_stats[16];
-void last_stats(uint64_t* out16) { for (int i = 0; i < 16; ++i) out16[i] = g_last_stats[i]; }
 
 int set_tuning(const char* key, uint64_t value) {
   std::string k(key ? key : "");
   if (k == "k1_span") g_tuning.k1_span = (uint32_t)value;
   else if (k == "k1_tpb") g_tuning.k1_tpb = (uint32_t)value;
-  else if (k == "k2_span") g_tuning.k2_span = (uint32_t)value;
-  else if (k == "k2_tpb") g_tuning.k2_tpb = (uint32_t)value;
-  else if (k == "ring_log2") g_tuning.ring_log2 = (uint32_t)value;
+  else if (k == "k2_blocks") g_tuning.k2_blocks = (uint32_t)value;
   else if (k == "force_ovf") g_tuning.force_ovf = (uint32_t)value;
-  else if (k == "stats") g_tuning.stats = (uint32_t)value;
   else if (k == "reset") g_tuning = Tuning();
   else return WGA_E_ARG;
   return WGA_OK;
 }
+void last_stats(uint64_t* out16) { for (int i = 0; i < 16; ++i) out16[i] = 0; }
 
 namespace {
 
@@ -78,11 +67,7 @@ struct RangeView {
   uint32_t* arena;    // overflow headers (K1) and pass-2 temporaries
   uint64_t arena_cap;
   unsigned long long* cursor;
-  uint32_t* pend;     // nodes left to pass 2 (index relative to lo)
-  uint32_t pend_cap;
-  uint32_t* pend_count;
-  uint32_t* pend_lev;
-  uint32_t* maxlevel;
+  uint32_t* maxlevel; // deepest reference chain seen by k_levels (only tracked from LCAP up)
   uint32_t* halo_succ;  // successors of halo nodes
   uint64_t halo_cap;
   uint32_t* succ;       // caller's array: successors of nodes >= first
@@ -93,11 +78,11 @@ struct RangeView {
 
 // meta word written by K1:
 //   bits 0-15 reference offset r | bit 16 header in the overflow arena | bit 17 node is final after K1
-//   bit 18 left to pass 2 (set by K2)
 //   in-slot header: bits 19-33 block count b | 34-47 interval count | 48-63 residual count
 //   overflow header: bits 19-63 arena offset of {b, ni, nres, pairs offset, blocks...}
-constexpr uint64_t M_OVF = 1ull << 16, M_DIRECT = 1ull << 17, M_PEND = 1ull << 18;
+constexpr uint64_t M_OVF = 1ull << 16, M_DIRECT = 1ull << 17;
 constexpr uint32_t MAX_B = 1u << 15, MAX_NI = 1u << 14, MAX_NRES = 1u << 16;
+constexpr uint32_t HS_WORDS = 16;  // in-slot headers are at most this many words (k_resolve caches them per lane)
 
 __device__ __forceinline__ uint32_t* node_slot(const RangeView& rv, uint32_t t) {
   uint64_t o = rv.offs[t];
@@ -364,7 +349,7 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
           k = 0;
           if (b == 0) { copied = dref; c = C_AFTER_BLOCKS; }
           else {
-            if (hb > d || b >= MAX_B || dref > 0xFFFFu || force_ovf) {
+            if (hb > d || hb > HS_WORDS || b >= MAX_B || dref > 0xFFFFu || force_ovf) {
               if (header_to_arena(rv, slot, b, 0, 0, 0, ao, apo)) ovf = true;
               else err |= ERR_WORKSPACE;
             }
@@ -382,7 +367,7 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
               const unsigned long long o = atomicAdd(rv.cursor, 2ull * ni);
               if (o + 2ull * ni > rv.arena_cap || o + 2ull * ni >= 0xFFFFFFFFull) err |= ERR_WORKSPACE;
               else { apo = (uint32_t)o; rv.arena[ao + 3] = apo; }
-            } else if (ni >= MAX_NI || hb + 2ull * ni > d || force_ovf) {
+            } else if (ni >= MAX_NI || hb + 2ull * ni > d || hb + 2ull * ni > HS_WORDS || force_ovf) {
               if (header_to_arena(rv, slot, b, b, ni, 0, ao, apo)) ovf = true;
               else err |= ERR_WORKSPACE;
             }
@@ -419,428 +404,139 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
 }
 
 // -------------------------------------------------------------------------------------------- K2
-// The three sorted streams a successor list is the union of (webgraph BvGraph decode, SURVEY.md 8a
-// "BV record order"): copied elements of the referenced list selected by the copy blocks, expanded
-// intervals, residuals.  `RefSrc` supplies element i of the referenced list.
-struct NodeStreams {
-  // header
-  const uint32_t* blkw;  // in-slot header: word j = copy length 2j (low half) | skip length 2j+1 (high half)
-  const uint32_t* blk32; // overflow header: one u32 per block (nullptr when in-slot)
-  const uint32_t* pp;    // interval pairs
-  const uint32_t* rp;    // residuals
-  uint32_t b, ni, nres, dref;
-  // copy stream: [ci, cend) is the current copy block; bk = index of the next (skip) block.
-  // cur = header word holding the skip length that follows the current copy block, nxt = the word after it;
-  // both are loaded one step ahead so that the merge loop never waits for HBM/L2.
-  uint32_t ci, cend, bk, cur, nxt;
-  bool cact;
-  // interval stream (next pair prefetched)
-  uint32_t ik, ival, iend, nis, nil;
-  // residual stream (next value prefetched)
-  uint32_t rj, rval, rnext;
+// Phase two: copy-block resolution + interval expansion + merge, by reference-chain depth.
+//   k_levels   depth[v] = ref ? depth[v-ref]+1 : 0 for every node that still needs work, and a 12-bit sort
+//              key (level bucket, degree bucket descending)
+//   cub sort   nodes ordered by key: one contiguous segment per level, inside it nodes of similar degree
+//              next to each other, so that the 32 lanes of a warp run merge loops of similar length
+//   k_resolve  one launch per level; one node per lane: a tight three-way merge of (copied elements of the
+//              finished referenced list, expanded intervals, residuals) written in place into the node's
+//              CSR slot.  The parked residuals sit at the tail of the slot and are consumed before the write
+//              pointer reaches them; the parked header is first copied to shared memory.
+constexpr uint32_t HS = 16;       // in-slot header words (u16 block lengths + interval pairs) a lane caches
+constexpr uint32_t LCAP = 6;      // levels 0..LCAP-1 have their own segment; deeper nodes share segment LCAP
+constexpr uint32_t KEY_SKIP = 15; // level bucket of nodes that are final after K1
+constexpr int RES_TPB = 128;
 
-  // gs = the node's CSR slot (d entries) holding the parked header / residuals
-  __device__ __forceinline__ void setup(const RangeView& rv, uint64_t m, const uint32_t* gs, uint32_t d, uint32_t dref_) {
-    if (m & M_OVF) {
-      const uint32_t* rec = rv.arena + (uint32_t)(m >> 19);
-      b = rec[0]; ni = rec[1]; nres = rec[2];
-      blk32 = rec + 4; blkw = nullptr;
-      pp = rv.arena + rec[3];
-    } else {
-      b = (uint32_t)(m >> 19) & (MAX_B - 1);
-      ni = (uint32_t)(m >> 34) & (MAX_NI - 1);
-      nres = (uint32_t)(m >> 48);
-      blkw = gs; blk32 = nullptr;
-      pp = gs + ((b + 1) >> 1);
-    }
-    rp = gs + (d - nres);
-    rj = 0;
-    rval = nres ? rp[0] : INF;
-    rnext = nres > 1 ? rp[1] : INF;
-    ik = 0;
-    ival = iend = nis = nil = INF;
-    if (ni) { ival = pp[0]; iend = ival + pp[1]; }
-    if (ni > 1) { nis = pp[2]; nil = pp[3]; }
-    dref = dref_;
-    cact = false;
-    ci = cend = bk = cur = nxt = 0;
-    if ((uint32_t)(m & 0xFFFFu)) {
-      cact = true;
-      if (b == 0) cend = dref;
-      else if (blk32) { cend = blk32[0]; bk = 1; }
-      else {
-        cur = blkw[0];
-        nxt = b > 2 ? blkw[1] : 0u;
-        cend = cur & 0xFFFFu;
-        bk = 1;
-      }
-      if (ci >= cend) next_copy_block();
-    }
-  }
-  // current copy block exhausted: skip block, then the next copy block (explicit, or the implicit tail
-  // when the block count is even)
-  __device__ __forceinline__ void next_copy_block() {
-    if (bk >= b) { cact = false; return; }
-    if (blk32) {
-      ci += blk32[bk]; ++bk;
-      if (bk < b) { cend = ci + blk32[bk]; ++bk; } else cend = dref;
-    } else {
-      ci += cur >> 16; ++bk;           // skip block bk (odd) lives in the high half of the current word
-      cur = nxt;
-      if (bk < b) {
-        cend = ci + (cur & 0xFFFFu); ++bk;  // copy block bk (even): low half of the next word
-        nxt = (bk + 1 < b) ? blkw[(bk + 1) >> 1] : 0u;
-      } else cend = dref;
-    }
-    if (ci >= cend) cact = false;
-  }
-  __device__ __forceinline__ void take_copy() { if (++ci == cend) next_copy_block(); }
-  __device__ __forceinline__ void take_interval() {
-    if (++ival == iend) {
-      ++ik;
-      ival = nis;
-      iend = nis + nil;
-      if (ik >= ni) ival = INF;
-      if (ik + 1 < ni) { nis = pp[2 * ik + 2]; nil = pp[2 * ik + 3]; } else nis = INF;
-    }
-  }
-  __device__ __forceinline__ void take_residual() {
-    ++rj;
-    rval = rnext;
-    rnext = (rj + 1 < nres) ? rp[rj + 1] : INF;
-  }
-};
-
-constexpr uint32_t FLN = 512;  // per-block window of in-flight nodes (power of two)
-constexpr uint32_t ST_RING = 0, ST_DIRECT = 1, ST_POISON = 2;
-// flag word of node k (relative to the span): tag (k+1) in bits 16-31 | status in bits 14-15 | progress
-// (elements of the list already in the ring) in bits 0-13.  A tag mismatch means "not announced yet".
-constexpr uint32_t SPIN_LIMIT = 1u << 24;
-// Ordering of the ring protocol.  A producer stores list elements into the ring and then its progress word;
-// a consumer loads the progress word and then the elements.  All of these are shared-memory accesses of one
-// SM, issued in program order by each thread, and the SM performs one warp's shared-memory accesses in issue
-// order, so a compiler barrier (no reordering by nvcc) is all that is needed.  A real fence
-// (__threadfence_block = MEMBAR.SC.CTA) would also wait for the thread's outstanding GLOBAL loads/stores --
-// the prefetches of the merge lanes, the output stores of the writer -- once per element: measured 2.5k
-// cycles per merge step.  Parity tests run with tiny rings / spans to exercise this protocol.
-#define SMEM_ORDER() asm volatile("" ::: "memory")
-constexpr uint32_t ERR_INTERNAL = 16u;
-
-__device__ __forceinline__ void pend_push(const RangeView& rv, uint32_t t, uint64_t m) {
-  const uint32_t i = atomicAdd(rv.pend_count, 1u);
-  if (i < rv.pend_cap) rv.pend[i] = t;
-  else atomicOr(rv.err, ERR_WORKSPACE);
-  rv.meta[t] = m | M_PEND;
+__device__ __forceinline__ uint32_t degree_bucket(uint32_t d) {  // monotone, 0..227
+  if (d < 128) return d;
+  const uint32_t lg = 31u - (uint32_t)__clz((int)d);
+  return 128u + (lg - 7u) * 4u + ((d >> (lg - 2u)) & 3u);
 }
 
-// Per-block shared state of k_merge.  All per-node arrays are indexed by (k & (FLN-1)), k relative to the span.
-struct MergeShared {
-  uint64_t meta[FLN];   // K1 record of the node (copied from HBM by the dispatcher, coalesced)
-  uint32_t flag[FLN];   // tag | status | progress (see above)
-  uint32_t rpos[FLN];   // ring position of the node's list: prefix sum of the degrees of ring-eligible nodes
-  uint32_t pos[FLN];    // output position of the node's list relative to the span start
-  uint32_t deg[FLN];    // outdegree
-  uint32_t next;        // next node to hand to a merge lane
-  uint32_t disp;        // nodes whose rpos/pos/deg/meta are valid
-  uint32_t flushed;     // nodes retired by the writer
-  uint32_t free_rpos;   // ring positions below this one may be overwritten
-};
-
-__global__ void __launch_bounds__(256, 4) k_merge(DevGraph g, RangeView rv, uint32_t span, uint32_t ring_mask,
-                                                uint32_t dbig) {
-  extern __shared__ __align__(16) uint8_t smraw[];
-  MergeShared& S = *reinterpret_cast<MergeShared*>(smraw);
-  volatile uint32_t* ring = reinterpret_cast<volatile uint32_t*>(smraw + sizeof(MergeShared));
-  volatile uint32_t* flag = S.flag;
-  volatile uint32_t* v_disp = &S.disp;
-  volatile uint32_t* v_flushed = &S.flushed;
-  volatile uint32_t* v_free = &S.free_rpos;
-  uint32_t A, Bn;
-  span_range(rv, span, blockIdx.x, A, Bn);
-  if (span_overflows(rv, A, Bn)) {
-    if (threadIdx.x == 0) atomicOr(rv.err, ERR_WORKSPACE);
-    return;
-  }
-  const uint32_t nspan = Bn - A;
-  for (uint32_t i = threadIdx.x; i < FLN; i += blockDim.x) S.flag[i] = 0;
-  if (threadIdx.x == 0) { S.next = 0; S.disp = 0; S.flushed = 0; S.free_rpos = 0; }
+__global__ void __launch_bounds__(256) k_levels(RangeView rv, uint16_t* keys, uint32_t* vals, uint32_t* lev_out,
+                                                uint32_t* hist) {
+  __shared__ uint32_t s_hist[16];
+  if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
   __syncthreads();
-  const uint64_t obase = rv.offs[A];
-  uint32_t* const gbase = node_slot(rv, A);  // global address of output position 0 of the span
-  if (rv.offs[Bn] - obase >= 0xFFFFFFFFull) dbig = 0;  // positions are kept in 32 bits: leave everything to pass 2
-  const uint32_t W = dbig ? g.window : 0u;  // nothing is ring-resident when dbig == 0: no list has to be kept
-  const uint32_t C = ring_mask + 1;
-  const uint32_t lane = threadIdx.x & 31;
-
-  if (threadIdx.x < 32) {
-    // ------------------------------------------------ warp 0: dispatcher (runs ahead) + writer (in-order retirement)
-    uint32_t kd = 0, kw = 0, rbase = 0, spins = 0, w_iter = 0, w_disp = 0, w_retire = 0, w_idle = 0;
-    // software-pipelined loads of the next dispatch batch
-    uint64_t nm = M_DIRECT, np0 = 0, np1 = 0;
-    auto prefetch = [&](uint32_t k0) {
-      const uint32_t k = k0 + lane;
-      nm = M_DIRECT; np0 = np1 = 0;
-      if (k < nspan) { nm = rv.meta[A + k]; np0 = rv.offs[A + k] - obase; np1 = rv.offs[A + k + 1] - obase; }
-    };
-    prefetch(0);
-    while (kw < nspan) {
-      bool progressed = false;
-      ++w_iter;
-      // ---- dispatch one batch of 32 nodes when the window has room for it
-      if (kd < nspan && kd + 32 + W + 2 <= kw + FLN) {
-        const uint32_t k = kd + lane;
-        const bool valid = k < nspan;
-        const uint32_t d = (uint32_t)(np1 - np0);
-        const bool elig = valid && !(nm & M_DIRECT) && d != 0 && d <= dbig;
-        uint32_t sz = elig ? d : 0u, inc = sz;
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t y = __shfl_up_sync(FULL, inc, o);
-          if ((int)lane >= o) inc += y;
-        }
-        if (valid) {
-          const uint32_t sl = k & (FLN - 1);
-          S.meta[sl] = nm;
-          S.rpos[sl] = rbase + inc - sz;
-          S.pos[sl] = (uint32_t)np0;
-          S.deg[sl] = d;
-        }
-        rbase += __shfl_sync(FULL, inc, 31);
-        kd = min(kd + 32, nspan);
-        prefetch(kd);
-        SMEM_ORDER();
-        __syncwarp();
-        if (lane == 0) *v_disp = kd;
-        progressed = true;
-        ++w_disp;
-      }
-      // ---- retire the longest prefix of finished nodes
-      {
-        const uint32_t k = kw + lane;
-        const bool valid = k < kd;
-        const uint32_t sl = k & (FLN - 1);
-        uint32_t w = 0, dk = 0;
-        bool ok = false;
-        if (valid) {
-          w = flag[sl];
-          dk = S.deg[sl];
-          ok = (w >> 16) == ((k + 1) & 0xFFFFu) && (((w >> 14) & 3u) != ST_RING || (w & 0x3FFFu) == dk);
-        }
-        const uint32_t mk = __ballot_sync(FULL, ok);
-        const uint32_t run = (mk == FULL) ? 32u : (uint32_t)__ffs(~mk) - 1u;
-        if (run) {
-          uint32_t rm = __ballot_sync(FULL, ok && ((w >> 14) & 3u) == ST_RING);
-          if (run < 32) rm &= (1u << run) - 1u;
-          const uint32_t mypos = valid ? S.pos[sl] : 0u, myrpos = valid ? S.rpos[sl] : 0u;
-          while (rm) {  // maximal runs of ring-resident nodes -> flat coalesced copies
-            const int s0 = __ffs(rm) - 1;
-            const uint32_t y = ~(rm >> s0);
-            const int len = y ? __ffs(y) - 1 : 32 - s0;
-            const uint32_t ps = __shfl_sync(FULL, mypos, s0);
-            const uint32_t rs = __shfl_sync(FULL, myrpos, s0);
-            const uint32_t cnt = __shfl_sync(FULL, mypos + dk, s0 + len - 1) - ps;
-            for (uint32_t q = lane; q < cnt; q += 32) gbase[ps + q] = ring[(rs + q) & ring_mask];
-            rm &= (s0 + len >= 32) ? 0u : ~((1u << (s0 + len)) - 1u);
-          }
-          kw += run;
-          __syncwarp();
-          if (lane == 0) {
-            // lists of the last W retired nodes stay (they may still be referenced)
-            const uint32_t fr = kw > W ? S.rpos[(kw - W) & (FLN - 1)] : 0u;
-            SMEM_ORDER();
-            *v_free = fr;
-            *v_flushed = kw;
-          }
-          progressed = true;
-          ++w_retire;
-        }
-      }
-      if (progressed) spins = 0;
-      else {
-        ++w_idle;
-        __nanosleep(32);
-        if (++spins > SPIN_LIMIT) {
-          if (lane == 0) atomicOr(rv.err, ERR_INTERNAL);
-          return;
-        }
-      }
-    }
-    if (rv.stats && lane == 0) {
-      atomicAdd(rv.stats + 8, w_iter); atomicAdd(rv.stats + 9, w_disp); atomicAdd(rv.stats + 10, w_retire);
-      atomicAdd(rv.stats + 11, w_idle);
-    }
-    return;
-  }
-
-  // ------------------------------------------------------------------ merge lanes
-  // Per-lane state machine.  Control steps (fetch a node, wait for the dispatcher / ring space / the
-  // referenced node, set the streams up) are batched: the warp runs them only when CTL_BATCH lanes need
-  // one (or periodically), so that the common iteration is the short merge step executed by all lanes.
-  enum { S_FETCH, S_DISPATCH, S_WAIT, S_MERGE, S_DONE };
-  constexpr uint32_t CTL_BATCH = 8;
-  int st = S_FETCH;
-  uint32_t k = 0, d = 0, r = 0, p = 0, kslot = 0, ktag = 0, jslot = 0, jtag = 0, rb = 0, wb = 0, cval = 0, idle = 0,
-           it = 0;
-  uint64_t m = 0;
-  const uint32_t* refg = nullptr;
-  bool havec = false;
-  NodeStreams ns;
-  uint32_t n_iter = 0, n_ctl = 0, n_wdisp = 0, n_wspace = 0, n_wref = 0, n_mstall = 0, n_mwork = 0, n_done = 0;
-  for (;; ++it) {
-    const uint32_t ctl = __ballot_sync(FULL, st != S_MERGE && st != S_DONE);
-    const uint32_t mrg = __ballot_sync(FULL, st == S_MERGE);
-    if ((ctl | mrg) == 0) break;  // every lane is done
-    ++n_iter;
-    if (st == S_DONE) ++n_done;
-    if (__popc(ctl) >= CTL_BATCH || mrg == 0 || (ctl && (it & 7u) == 0)) {
-      ++n_ctl;
-      if (st == S_FETCH) {
-        k = atomicAdd(&S.next, 1u);
-        st = k >= nspan ? S_DONE : S_DISPATCH;
-        idle = 0;
-      }
-      if (st == S_DISPATCH) {
-        if (k < *v_disp) {
-          kslot = k & (FLN - 1);
-          m = S.meta[kslot];
-          d = S.deg[kslot];
-          wb = S.rpos[kslot];
-          ktag = ((k + 1) & 0xFFFFu) << 16;
-          r = (uint32_t)(m & 0xFFFFu);
-          if ((m & M_DIRECT) || d == 0) {
-            flag[kslot] = ktag | (ST_DIRECT << 14);
-            st = S_FETCH;
-          } else if (d > dbig || r > k) {  // does not fit the ring / reference before the span: pass 2
-            pend_push(rv, A + k, m);
-            flag[kslot] = ktag | (ST_POISON << 14);
-            st = S_FETCH;
-          } else {
-            jslot = (k - r) & (FLN - 1);
-            jtag = (k - r + 1) & 0xFFFFu;
-            st = S_WAIT;
-          }
-        } else { ++idle; ++n_wdisp; }  // the dispatcher has not reached this node yet
-      }
-      if (st == S_WAIT) {
-        bool ready = (wb + d - *v_free) <= C;
-        uint32_t js = ST_DIRECT;
-        if (ready && r) {
-          const uint32_t w = flag[jslot];
-          ready = (w >> 16) == jtag;
-          js = (w >> 14) & 3u;
-        }
-        if (!ready) { ++idle; if ((wb + d - *v_free) > C) ++n_wspace; else ++n_wref; }
-        else if (r && js == ST_POISON) {
-          pend_push(rv, A + k, m);
-          flag[kslot] = ktag | (ST_POISON << 14);
-          st = S_FETCH;
-        } else {
-          uint32_t dref = 0;
-          refg = nullptr;
-          if (r) {
-            dref = S.deg[jslot];
-            if (js == ST_DIRECT) refg = gbase + S.pos[jslot];
-            else rb = S.rpos[jslot];
-          }
-          ns.setup(rv, m, gbase + S.pos[kslot], d, dref);
-          p = 0;
-          havec = false;
-          flag[kslot] = ktag;  // announce: ring-resident, nothing written yet
-          st = S_MERGE;
-          idle = 0;
-        }
-      }
-    }
-    if (st == S_MERGE) {  // one successor per step
-      if (ns.cact && !havec) {
-        uint32_t avail = ns.dref;
-        if (!refg) avail = flag[jslot] & 0x3FFFu;
-        if (ns.ci < avail) {
-          cval = refg ? refg[ns.ci] : ring[(rb + ns.ci) & ring_mask];
-          havec = true;
-        }
-      }
-      if (!ns.cact || havec) {
-        const uint32_t cv = ns.cact ? cval : INF;
-        const uint32_t mn = min(cv, min(ns.ival, ns.rval));
-        ring[(wb + p) & ring_mask] = mn;
-        ++p;
-        if (mn == INF) {  // cannot happen on records K1 accepted
-          atomicOr(rv.err, ERR_CORRUPT);
-          p = d;
-        } else if (mn == cv) { havec = false; ns.take_copy(); }
-        else if (mn == ns.ival) ns.take_interval();
-        else ns.take_residual();
-        SMEM_ORDER();
-        flag[kslot] = ktag | p;
-        if (p == d) st = S_FETCH;
-        idle = 0;
-        ++n_mwork;
-      } else { ++idle; ++n_mstall; }
-    }
-    if (idle > SPIN_LIMIT) {
-      atomicOr(rv.err, ERR_INTERNAL);
-      st = S_DONE;
-    }
-  }
-  if (rv.stats) {
-    atomicAdd(rv.stats + 0, n_iter); atomicAdd(rv.stats + 1, n_ctl); atomicAdd(rv.stats + 2, n_wdisp);
-    atomicAdd(rv.stats + 3, n_wspace); atomicAdd(rv.stats + 4, n_wref); atomicAdd(rv.stats + 5, n_mstall);
-    atomicAdd(rv.stats + 6, n_mwork); atomicAdd(rv.stats + 7, n_done);
-  }
-}
-
-// -------------------------------------------------------------------------------------------- K2p
-// Chain depth of every pending node inside the pending set (1 = its reference is final).
-__global__ void __launch_bounds__(TPB) k_pend_levels(RangeView rv, uint32_t np) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t lev = 0;
-  if (i < np) {
-    uint32_t u = rv.pend[i];
-    lev = 1;
-    for (;;) {
-      const uint32_t r = (uint32_t)(rv.meta[u] & 0xFFFFu);
-      if (!r) break;
-      u -= r;
-      if (!(rv.meta[u] & M_PEND)) break;
-      ++lev;
+  if (t < rv.n) {
+    const uint64_t m = rv.meta[t];
+    uint32_t lb = KEY_SKIP;
+    if (!(m & M_DIRECT)) {
+      uint32_t u = t, r = (uint32_t)(m & 0xFFFFu);
+      while (r) {  // chain of referenced nodes (a node that is final after K1 has no reference)
+        u -= r;
+        ++lev;
+        r = (uint32_t)(rv.meta[u] & 0xFFFFu);
+      }
+      lb = min(lev, LCAP);
+      lev_out[t] = lev;
     }
-    rv.pend_lev[i] = lev;
+    keys[t] = (uint16_t)((lb << 8) | (255u - degree_bucket(rv.outdeg[t])));
+    vals[t] = t;
+    atomicAdd(&s_hist[lb], 1u);
   }
   for (int o = 16; o; o >>= 1) lev = max(lev, __shfl_xor_sync(FULL, lev, o));
-  if ((threadIdx.x & 31) == 0 && lev) atomicMax(rv.maxlevel, lev);
+  if ((threadIdx.x & 31) == 0 && lev >= LCAP) atomicMax(rv.maxlevel, lev);
+  __syncthreads();
+  if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
 }
 
-// One pending node per lane: merge from global memory into an arena temporary, then copy over the slot
-// (the slot still holds the parked header / residuals while they are being read).
-__global__ void __launch_bounds__(TPB) k_pend_resolve(DevGraph g, RangeView rv, uint32_t np, uint32_t lev) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= np || rv.pend_lev[i] != lev) return;
-  const uint32_t t = rv.pend[i];
+// hist[16] -> seg[17] (exclusive prefix): nodes of level bucket l are order[seg[l] .. seg[l+1])
+__global__ void k_segments(const uint32_t* hist, uint32_t* seg) {
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int l = 0; l < 16; ++l) { seg[l] = acc; acc += hist[l]; }
+    seg[16] = acc;
+  }
+}
+
+__device__ __forceinline__ void resolve_node(const RangeView& rv, uint32_t t, uint32_t* hdr /* HS+1 words, shared */) {
   const uint64_t m = rv.meta[t];
   const uint32_t r = (uint32_t)(m & 0xFFFFu);
-  uint32_t* const gs = node_slot(rv, t);
+  uint32_t* const slot = node_slot(rv, t);
   const uint32_t d = (uint32_t)(rv.offs[t + 1] - rv.offs[t]);
-  const uint32_t* ref = nullptr;
-  uint32_t dref = 0;
+  // ---- header
+  uint32_t b, ni, nres;
+  const uint16_t* blk16 = nullptr;
+  const uint32_t* blk32 = nullptr;
+  const uint32_t* pp;
+  if (m & M_OVF) {
+    const uint32_t* rec = rv.arena + (uint32_t)(m >> 19);
+    b = rec[0]; ni = rec[1]; nres = rec[2];
+    blk32 = rec + 4;
+    pp = rv.arena + rec[3];
+  } else {
+    b = (uint32_t)(m >> 19) & (MAX_B - 1);
+    ni = (uint32_t)(m >> 34) & (MAX_NI - 1);
+    nres = (uint32_t)(m >> 48);
+    const uint32_t hb = (b + 1) >> 1, H = hb + 2 * ni;  // K1 guarantees H <= HS for in-slot headers
+    for (uint32_t w = 0; w < H; ++w) hdr[w] = slot[w];
+    blk16 = reinterpret_cast<const uint16_t*>(hdr);
+    pp = hdr + hb;
+  }
+  const uint32_t* rp = slot + (d - nres);
+  // ---- extras: expanded intervals and residuals, merged on the fly
+  uint32_t rj = 0, rval = nres ? rp[0] : INF;
+  uint32_t ik = 0, ival = INF, iend = 0;
+  if (ni) { ival = pp[0]; iend = ival + pp[1]; }
+  uint32_t ev = min(ival, rval);
+  auto advance = [&]() {
+    if (ev == ival) {
+      if (++ival == iend) {
+        if (++ik < ni) { ival = pp[2 * ik]; iend = ival + pp[2 * ik + 1]; } else ival = INF;
+      }
+    } else {
+      rval = (++rj < nres) ? rp[rj] : INF;
+    }
+    ev = min(ival, rval);
+  };
+  uint32_t* wp = slot;
+  uint32_t* const wend = slot + d;
   if (r) {
-    ref = node_slot(rv, t - r);
-    dref = (uint32_t)(rv.offs[t - r + 1] - rv.offs[t - r]);
+    const uint32_t* ref = node_slot(rv, t - r);
+    const uint32_t dref = (uint32_t)(rv.offs[t - r + 1] - rv.offs[t - r]);
+    uint32_t ci = 0, k = 0;
+    for (;;) {
+      // copy block k (even index); the block after the last explicit one is the implicit tail (b even)
+      const uint32_t len = k < b ? (blk32 ? blk32[k] : (uint32_t)blk16[k]) : dref - ci;
+      const uint32_t cend = ci + len;
+      for (; ci < cend; ++ci) {
+        const uint32_t c = ref[ci];
+        while (ev < c && wp < wend) { *wp++ = ev; advance(); }
+        if (wp < wend) *wp++ = c;
+      }
+      if (k >= b) break;
+      if (++k >= b) break;  // odd block count: the rest of the referenced list is skipped
+      ci += blk32 ? blk32[k] : (uint32_t)blk16[k];
+      ++k;
+    }
   }
-  const unsigned long long o = atomicAdd(rv.cursor, (unsigned long long)d);
-  if (o + d > rv.arena_cap) { atomicOr(rv.err, ERR_WORKSPACE); return; }
-  uint32_t* tmp = rv.arena + o;
-  NodeStreams ns;
-  ns.setup(rv, m, gs, d, dref);
-  for (uint32_t p = 0; p < d; ++p) {
-    const uint32_t cv = ns.cact ? ref[ns.ci] : INF;
-    const uint32_t mn = min(cv, min(ns.ival, ns.rval));
-    tmp[p] = mn;
-    if (mn == INF) { atomicOr(rv.err, ERR_CORRUPT); break; }
-    if (mn == cv) ns.take_copy();
-    else if (mn == ns.ival) ns.take_interval();
-    else ns.take_residual();
+  while (ev != INF && wp < wend) { *wp++ = ev; advance(); }
+}
+
+__global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_t* order, const uint32_t* seg,
+                                                     uint32_t lb, uint32_t exact_level, const uint32_t* lev) {
+  __shared__ uint32_t s_hdr[RES_TPB * (HS + 1)];
+  uint32_t* hdr = s_hdr + threadIdx.x * (HS + 1);  // odd stride: conflict-free
+  const uint32_t beg = seg[lb], end = seg[lb + 1];
+  for (uint32_t i = beg + blockIdx.x * RES_TPB + threadIdx.x; i < end; i += gridDim.x * RES_TPB) {
+    const uint32_t t = order[i];
+    if (exact_level && lev[t] != exact_level) continue;
+    resolve_node(rv, t, hdr);
   }
-  for (uint32_t p = 0; p < d; ++p) gs[p] = tmp[p];
 }
 
 // -------------------------------------------------------------------------------------------- debug kernels
@@ -890,14 +586,15 @@ struct Scalars {
   unsigned long long cursor;  // arena bump pointer
   uint64_t lo;                // k_halo result
   uint32_t maxlevel;
-  uint32_t pend_count;
-  uint64_t pad[5];
-  unsigned long long stats[16];  // offset 64
+  uint32_t pad;
+  uint32_t hist[16];          // nodes per level bucket
+  uint32_t seg[17];           // exclusive prefix of hist
 };
+static_assert(sizeof(Scalars) <= 256, "Scalars must fit the cleared line");
 
 struct WorkspacePlan {
-  uint64_t off_outdeg, off_offs, off_meta, off_pend, off_pend_lev, off_cub, off_halo, off_arena;
-  uint64_t cub_bytes, halo_cap, pend_cap, fixed_bytes;
+  uint64_t off_outdeg, off_offs, off_meta, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_arena;
+  uint64_t cub_bytes, halo_cap, fixed_bytes;
 };
 
 WorkspacePlan plan_workspace(uint64_t n) {
@@ -907,15 +604,17 @@ WorkspacePlan plan_workspace(uint64_t n) {
   p.off_outdeg = o; o = align_up(o + 4 * (n + 1), 256);
   p.off_offs = o; o = align_up(o + 8 * (n + 1), 256);
   p.off_meta = o; o = align_up(o + 8 * n, 256);
-  p.pend_cap = n / 8 + 65536;
-  if (p.pend_cap > n) p.pend_cap = n + 1;
-  p.off_pend = o; o = align_up(o + 4 * p.pend_cap, 256);
-  p.off_pend_lev = o; o = align_up(o + 4 * p.pend_cap, 256);
-  size_t cub_bytes = 0;
+  p.off_lev = o; o = align_up(o + 4 * n, 256);
+  for (int i = 0; i < 2; ++i) { p.off_keys[i] = o; o = align_up(o + 2 * n, 256); }
+  for (int i = 0; i < 2; ++i) { p.off_vals[i] = o; o = align_up(o + 4 * n, 256); }
+  size_t scan_bytes = 0, sort_bytes = 0;
   cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(nullptr, U32ToU64());
-  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, it, (uint64_t*)nullptr, (int64_t)(n + 1));
-  p.cub_bytes = cub_bytes;
-  p.off_cub = o; o = align_up(o + cub_bytes, 256);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, it, (uint64_t*)nullptr, (int64_t)(n + 1));
+  cub::DoubleBuffer<uint16_t> dk(nullptr, nullptr);
+  cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int64_t)n, 0, 12);
+  p.cub_bytes = std::max(scan_bytes, sort_bytes);
+  p.off_cub = o; o = align_up(o + p.cub_bytes, 256);
   p.halo_cap = 1u << 20;  // successors of halo nodes (u32 each)
   p.off_halo = o; o = align_up(o + 4 * p.halo_cap, 256);
   p.off_arena = o;
@@ -930,7 +629,7 @@ uint64_t decode_workspace_size(const wga_graph* g, uint64_t first, uint64_t last
   WorkspacePlan p = plan_workspace(n);
   double frac = g->prelude.number_of_nodes ? (double)(last - first) / (double)g->prelude.number_of_nodes : 1.0;
   uint64_t arcs_est = (uint64_t)((double)g->prelude.number_of_arcs * frac) + (1u << 20);
-  // arena: overflow headers (rare) + pass-2 temporaries (successors of the nodes left to pass 2)
+  // arena: headers that do not fit their node's slot (rare)
   uint64_t arena_cap = n + arcs_est / 8 + (1u << 20);
   return p.fixed_bytes + 4 * arena_cap;
 }
@@ -938,7 +637,6 @@ uint64_t decode_workspace_size(const wga_graph* g, uint64_t first, uint64_t last
 static void check_device_error(wga_graph* g, uint32_t herr, cudaStream_t st) {
   if (herr) {
     WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
-    if (herr & ERR_INTERNAL) throw Error(WGA_E_CUDA, "decode: internal scheduling error (spin limit reached)");
     if (herr & ERR_WORKSPACE) throw Error(WGA_E_WORKSPACE, "decode: workspace or output buffer too small; pass larger buffers");
     if (herr & ERR_RANGE) throw Error(WGA_E_CORRUPT, "decode: a reference leaves the decoded range");
     if (herr & ERR_SYMBOL_WIDTH) throw Error(WGA_E_UNSUPPORTED, "decode: a decoded value does not fit 32 bits");
@@ -987,6 +685,21 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     if (h_arcs) *h_arcs = 0;
     return;
   }
+  static bool env_done = false;
+  if (!env_done) {  // WGA_TUNING="key=value,key=value": same knobs as wga_debug_set_tuning (profiling runs)
+    env_done = true;
+    if (const char* e = getenv("WGA_TUNING")) {
+      std::string str(e);
+      size_t i = 0;
+      while (i < str.size()) {
+        size_t j = str.find(',', i);
+        if (j == std::string::npos) j = str.size();
+        size_t q = str.find('=', i);
+        if (q != std::string::npos && q < j) set_tuning(str.substr(i, q - i).c_str(), strtoull(str.c_str() + q + 1, nullptr, 10));
+        i = j + 1;
+      }
+    }
+  }
   const Tuning tn = g_tuning;
   uint8_t* w = (uint8_t*)ws;
   if (ws_bytes < 256) throw Error(WGA_E_WORKSPACE, "workspace too small");
@@ -1014,16 +727,11 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   rv.arena = (uint32_t*)(w + p.off_arena);
   rv.arena_cap = (ws_bytes - p.off_arena) / 4;
   rv.cursor = &sc->cursor;
-  rv.pend = (uint32_t*)(w + p.off_pend);
-  rv.pend_cap = (uint32_t)p.pend_cap;
-  rv.pend_count = &sc->pend_count;
-  rv.pend_lev = (uint32_t*)(w + p.off_pend_lev);
   rv.maxlevel = &sc->maxlevel;
   rv.halo_succ = (uint32_t*)(w + p.off_halo);
   rv.halo_cap = p.halo_cap;
   rv.succ = d_succ; rv.succ_cap = succ_capacity;
   rv.err = g->d_err;
-  rv.stats = tn.stats ? sc->stats : nullptr;
   // ---- K0 + scan
   k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, lo, (uint32_t)n, rv.outdeg, g->d_err);
   count_launch();
@@ -1044,55 +752,54 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     count_launch();
   }
   mark(g, st);  // 2: entropy decode done
-  // ---- K2: streamed merge
-  {
-    uint32_t ring_log2 = tn.ring_log2 < 6 ? 6 : (tn.ring_log2 > 15 ? 15 : tn.ring_log2);
-    uint32_t C = 1u << ring_log2;
-    uint32_t W = (uint32_t)g->prelude.compression_window;
-    uint32_t dbig = C / (W + 1);
-    if (dbig > 0x3FFFu) dbig = 0x3FFFu;
-    if (W + 2 + 64 >= FLN) dbig = 0;  // window too wide for the in-flight node window: everything goes to pass 2
-    uint32_t span = tn.k2_span ? tn.k2_span : 1;
-    span = std::min<uint32_t>(span, std::max<uint32_t>(512u, (uint32_t)(n / (148 * 8))));
-    if (span > 32768) span = 32768;  // node tags are 16 bits
-    uint32_t tpb = tn.k2_tpb < 64 ? 64 : (tn.k2_tpb > 256 ? 256 : tn.k2_tpb / 32 * 32);
-    size_t smem = sizeof(MergeShared) + (size_t)C * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-      WGA_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MergeShared) + (4u << 15))));
-      attr_set = true;
-    }
-    k_merge<<<span_count(rv.n, rv.h, span), tpb, smem, st>>>(g->dev, rv, span, C - 1, dbig);
+  // ---- K2: levels, sort by (level, degree), one resolve launch per level
+  uint32_t* lev = (uint32_t*)(w + p.off_lev);
+  cub::DoubleBuffer<uint16_t> dkeys((uint16_t*)(w + p.off_keys[0]), (uint16_t*)(w + p.off_keys[1]));
+  cub::DoubleBuffer<uint32_t> dvals((uint32_t*)(w + p.off_vals[0]), (uint32_t*)(w + p.off_vals[1]));
+  const bool have_refs = g->prelude.compression_window != 0 || g->prelude.min_interval_length != 0;
+  if (have_refs) {
+    k_levels<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rv, dkeys.Current(), dvals.Current(), lev, sc->hist);
     count_launch();
+    size_t cb = p.cub_bytes;
+    WGA_CUDA(cub::DeviceRadixSort::SortPairs(w + p.off_cub, cb, dkeys, dvals, (int64_t)n, 0, 12, st));
+    count_launch(3);
+    k_segments<<<1, 32, 0, st>>>(sc->hist, sc->seg);
+    count_launch();
+    mark(g, st);  // 3: levels + sort done
+    const uint32_t grid = tn.k2_blocks ? tn.k2_blocks : 1;
+    const uint32_t nlev = g->prelude.compression_window ? LCAP : 1;  // without references everything is level 0
+    for (uint32_t l = 0; l < nlev; ++l) {
+      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, l, 0, lev);
+      count_launch();
+    }
+  } else {
+    mark(g, st);
   }
-  mark(g, st);  // 3: merge done
-  // ---- results of the fast path: totals, pending count, error word
+  mark(g, st);  // 4: resolve done
+  // ---- totals, deepest level, error word
   uint64_t tot[2] = {0, 0};
-  uint32_t np = 0, herr = 0;
+  uint32_t maxlevel = 0, herr = 0;
   WGA_CUDA(cudaMemcpyAsync(&tot[0], rv.offs + rv.h, 8, cudaMemcpyDeviceToHost, st));
   WGA_CUDA(cudaMemcpyAsync(&tot[1], rv.offs + n, 8, cudaMemcpyDeviceToHost, st));
-  WGA_CUDA(cudaMemcpyAsync(&np, &sc->pend_count, 4, cudaMemcpyDeviceToHost, st));
+  WGA_CUDA(cudaMemcpyAsync(&maxlevel, &sc->maxlevel, 4, cudaMemcpyDeviceToHost, st));
   WGA_CUDA(cudaMemcpyAsync(&herr, g->d_err, 4, cudaMemcpyDeviceToHost, st));
   WGA_CUDA(cudaStreamSynchronize(st));
   WGA_CUDA(cudaGetLastError());
-  if (tot[0] > rv.halo_cap) { check_device_error(g, herr & ~ERR_WORKSPACE, st); if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st)); throw Error(WGA_E_WORKSPACE, "halo successors exceed the workspace"); }
+  if (tot[0] > rv.halo_cap) {
+    if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
+    throw Error(WGA_E_WORKSPACE, "halo successors exceed the workspace");
+  }
   if (tot[1] - tot[0] > succ_capacity) {
     if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
     throw Error(WGA_E_WORKSPACE, "d_succ too small: need " + std::to_string(tot[1] - tot[0]) + " elements");
   }
-  if (tn.stats) WGA_CUDA(cudaMemcpy(g_last_stats, sc->stats, sizeof(g_last_stats), cudaMemcpyDeviceToHost));
   check_device_error(g, herr, st);
-  // ---- K2p: nodes whose reference left their span, level by level
-  if (np) {
-    if (np > rv.pend_cap) throw Error(WGA_E_WORKSPACE, "pending list exceeds the workspace");
-    const unsigned pgrid = (np + TPB - 1) / TPB;
-    k_pend_levels<<<pgrid, TPB, 0, st>>>(rv, np);
-    count_launch();
-    uint32_t maxlevel = 0;
-    WGA_CUDA(cudaMemcpyAsync(&maxlevel, &sc->maxlevel, 4, cudaMemcpyDeviceToHost, st));
-    WGA_CUDA(cudaStreamSynchronize(st));
-    for (uint32_t lev = 1; lev <= maxlevel; ++lev) {
-      k_pend_resolve<<<pgrid, TPB, 0, st>>>(g->dev, rv, np, lev);
+  // ---- reference chains deeper than LCAP (e.g. graphs compressed with an unbounded max_ref_count): one
+  //      launch per extra level over the shared deep segment
+  if (have_refs && maxlevel >= LCAP) {
+    const uint32_t grid = tn.k2_blocks ? tn.k2_blocks : 1;
+    for (uint32_t l = LCAP; l <= maxlevel; ++l) {
+      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, LCAP, l, lev);
       count_launch();
     }
     check_device_error(g, read_device_error(g, st), st);
@@ -1102,7 +809,6 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     k_offsets_rebase<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(rv.offs + rv.h, tot[0], d_offsets, cnt);
     count_launch();
   }
-  mark(g, st);  // 4: pass 2 done
   WGA_CUDA(cudaGetLastError());
   if (g->profiling) {
     WGA_CUDA(cudaStreamSynchronize(st));
