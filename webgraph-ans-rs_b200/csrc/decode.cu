@@ -35,6 +35,8 @@ struct Tuning {
   uint32_t k1_tpb = 128;      // threads per K1 block
   uint32_t k2_blocks = 148 * 12;  // K2 grid (blocks of 128 lanes striding over a level's segment)
   uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
+  uint32_t sort_degree = 0;   // K2: 1 = sort key includes the degree bucket; 0 = level only, node order kept
+                              // (measured: locality of neighbouring nodes beats equal loop lengths, 2.9 vs 6.6 ms)
 };
 static Tuning g_tuning;
 
@@ -44,6 +46,7 @@ int set_tuning(const char* key, uint64_t value) {
   else if (k == "k1_tpb") g_tuning.k1_tpb = (uint32_t)value;
   else if (k == "k2_blocks") g_tuning.k2_blocks = (uint32_t)value;
   else if (k == "force_ovf") g_tuning.force_ovf = (uint32_t)value;
+  else if (k == "sort_degree") g_tuning.sort_degree = (uint32_t)value;
   else if (k == "reset") g_tuning = Tuning();
   else return WGA_E_ARG;
   return WGA_OK;
@@ -425,7 +428,7 @@ __device__ __forceinline__ uint32_t degree_bucket(uint32_t d) {  // monotone, 0.
 }
 
 __global__ void __launch_bounds__(256) k_levels(RangeView rv, uint16_t* keys, uint32_t* vals, uint32_t* lev_out,
-                                                uint32_t* hist) {
+                                                uint32_t* hist, uint32_t sort_degree) {
   __shared__ uint32_t s_hist[16];
   if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
   __syncthreads();
@@ -444,7 +447,7 @@ __global__ void __launch_bounds__(256) k_levels(RangeView rv, uint16_t* keys, ui
       lb = min(lev, LCAP);
       lev_out[t] = lev;
     }
-    keys[t] = (uint16_t)((lb << 8) | (255u - degree_bucket(rv.outdeg[t])));
+    keys[t] = (uint16_t)((lb << 8) | (sort_degree ? 255u - degree_bucket(rv.outdeg[t]) : 0u));
     vals[t] = t;
     atomicAdd(&s_hist[lb], 1u);
   }
@@ -758,7 +761,7 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   cub::DoubleBuffer<uint32_t> dvals((uint32_t*)(w + p.off_vals[0]), (uint32_t*)(w + p.off_vals[1]));
   const bool have_refs = g->prelude.compression_window != 0 || g->prelude.min_interval_length != 0;
   if (have_refs) {
-    k_levels<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rv, dkeys.Current(), dvals.Current(), lev, sc->hist);
+    k_levels<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rv, dkeys.Current(), dvals.Current(), lev, sc->hist, tn.sort_degree);
     count_launch();
     size_t cb = p.cub_bytes;
     WGA_CUDA(cub::DeviceRadixSort::SortPairs(w + p.off_cub, cb, dkeys, dvals, (int64_t)n, 0, 12, st));
