@@ -144,6 +144,16 @@ int wga_set_profiling(wga_graph* g, int on);
 int wga_last_profile(const wga_graph* g, float* h_stage_ms8);
 
 /* ---------------------------------------------------------------- random access (successors(v)) - */
+/* graph.successors(v) for a batch of query nodes (examples/bench_random_access.rs:30-38): the reference
+ * creates one decoder per query (bvgraph_decoder_factory.rs:46-58) and webgraph follows the reference chain
+ * recursively; here the reference closure of all queries is decoded once and the query lists are gathered.
+ *   d_nodes[n_queries]      query node ids (duplicates allowed, any order)
+ *   d_offsets[n_queries+1]  CSR offsets of the answer (d_offsets[0] == 0)
+ *   d_succ                  successors of query i at d_succ[d_offsets[i] .. d_offsets[i+1]); NULL = sizing call:
+ *                           only d_offsets and *h_arcs are produced (one symbol per query is decoded)
+ * Workspace: wga_successors_workspace_size(g, n_queries, max_total_arcs) with max_total_arcs >= the *h_arcs of
+ * the sizing call (0 is enough for the sizing call itself).  The decoded closure may hold up to 4x that many
+ * arcs and 8x n_queries nodes; deeper reference chains return WGA_E_WORKSPACE (retry with a larger bound). */
 uint64_t wga_successors_workspace_size(const wga_graph* g, uint64_t n_queries, uint64_t max_total_arcs);
 int wga_successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t n_queries, uint64_t* d_offsets,
                          uint32_t* d_succ, uint64_t succ_capacity, void* d_workspace, uint64_t workspace_bytes,

@@ -196,6 +196,27 @@ def test_iter_and_successor_api(W, O, gpu, head):
         assert (s == head["succ"][head["offsets"][v]:head["offsets"][v + 1]]).all()
 
 
+@pytest.mark.parametrize("params", [(7, 3, 4), (16, 1 << 30, 4), (0, 3, 4), (7, 3, 0)])
+def test_random_access_batch_matches_oracle(W, O, gpu, params):
+    """examples/bench_random_access.rs: successors(v) of random nodes == the sequential decode's lists."""
+    off, succ = make_case(20000, 10, 41)
+    og = O.OracleGraph.store_csr(off, succ, *params)
+    g = open_oracle_graph(W, og)
+    rng = np.random.default_rng(5)
+    for q in (rng.integers(0, 20000, 5000), np.array([0, 19999, 0, 7, 7, 7]), np.arange(100, 160), np.zeros(0, np.int64)):
+        d_off, d_succ = g.successors_batch(q)
+        d_off = d_off.cpu().numpy().astype(np.uint64)
+        d_succ = d_succ.cpu().numpy().view(np.uint32)
+        assert d_off.size == q.size + 1 and d_off[0] == 0
+        exp = [succ[off[v]:off[v + 1]] for v in q]
+        assert (np.diff(d_off) == np.array([e.size for e in exp], np.uint64)).all()
+        if q.size:
+            assert (d_succ[:int(d_off[-1])] == np.concatenate(exp)).all()
+    assert (g.successors(12345) == succ[off[12345]:off[12346]]).all()
+    with pytest.raises(W.WgaError):
+        g.successors_batch([20000])
+
+
 @pytest.mark.parametrize("kind,n,deg", [("web", 300_000, 34.3), ("social", 200_000, 35.3)])
 def test_synthetic_shapes_roundtrip(W, O, gpu, kind, n, deg):
     """Bench-shaped graphs at a size the oracle finishes in seconds: GPU decode == oracle decode == source."""

@@ -63,6 +63,7 @@ struct RangeView {
   uint64_t lo;        // first decoded node (halo start)
   uint64_t first;     // first node the caller asked for
   uint32_t n;         // nodes decoded: last - lo
+  const uint32_t* nodes;  // nullptr: node t is lo + t; else a sorted, duplicate-free list of node ids (random access)
   uint32_t h;         // halo nodes: first - lo
   uint32_t* outdeg;   // n+1
   uint64_t* offs;     // n+1, relative to lo
@@ -86,6 +87,25 @@ struct RangeView {
 constexpr uint64_t M_OVF = 1ull << 16, M_DIRECT = 1ull << 17;
 constexpr uint32_t MAX_B = 1u << 15, MAX_NI = 1u << 14, MAX_NRES = 1u << 16;
 constexpr uint32_t HS_WORDS = 16;  // in-slot headers are at most this many words (k_resolve caches them per lane)
+
+constexpr uint32_t NOT_FOUND = 0xFFFFFFFFu;
+__device__ __forceinline__ uint64_t node_of(const RangeView& rv, uint32_t t) {
+  return rv.nodes ? (uint64_t)rv.nodes[t] : rv.lo + t;
+}
+// Index of the node referenced by node t with reference offset r (r != 0).  In a sorted duplicate-free
+// list the node (id - r) sits at most r positions before t.
+__device__ __forceinline__ uint32_t ref_index(const RangeView& rv, uint32_t t, uint32_t r) {
+  if (!rv.nodes) return r <= t ? t - r : NOT_FOUND;
+  const uint32_t id = rv.nodes[t];
+  if (r > id) return NOT_FOUND;
+  const uint32_t target = id - r;
+  uint32_t lo = t >= r ? t - r : 0u, hi = t;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (rv.nodes[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  return (lo < t && rv.nodes[lo] == target) ? lo : NOT_FOUND;
+}
 
 __device__ __forceinline__ uint32_t* node_slot(const RangeView& rv, uint32_t t) {
   uint64_t o = rv.offs[t];
@@ -124,12 +144,12 @@ __device__ __forceinline__ void load_phase(const DevGraph& g, uint64_t v, uint32
 }
 
 // -------------------------------------------------------------------------------------------- K0
-__global__ void __launch_bounds__(TPB) k_outdegree(DevGraph g, uint64_t lo, uint32_t n, uint32_t* outdeg,
-                                                   uint32_t* err_out) {
+__global__ void __launch_bounds__(TPB) k_outdegree(DevGraph g, uint64_t lo, const uint32_t* nodes, uint32_t n,
+                                                   uint32_t* outdeg, uint32_t* err_out) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n) return;
   if (t == n) { outdeg[n] = 0; return; }
-  uint64_t v = lo + t;
+  uint64_t v = nodes ? (uint64_t)nodes[t] : lo + t;
   uint32_t state, err = 0;
   int64_t ptr;
   load_phase(g, v, state, ptr, err);
@@ -256,7 +276,7 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
       t = atomicAdd(&s_next, 1u);
       if (t >= Bn) c = C_IDLE;
       else {
-        v = (int64_t)(rv.lo + t);
+        v = (int64_t)node_of(rv, t);
         load_phase(g, (uint64_t)v, state, ptr, err);
         c = Outdegree;
         r = b = ni = copied = hb = nres = 0;
@@ -336,12 +356,16 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
           }
         }
       } else if (c == ReferenceOffset) {
+        uint32_t ri = t;
         if (xl > window) err |= ERR_CORRUPT;
-        else if (xl > t) err |= ERR_RANGE;
+        else if (xl) {
+          ri = ref_index(rv, t, xl);
+          if (ri == NOT_FOUND) err |= ERR_RANGE;  // the referenced node is not part of this decode
+        }
         if (!err) {
           r = xl;
           if (r == 0) c = c_extras;
-          else { dref = rv.outdeg[t - r]; c = BlockCount; }
+          else { dref = rv.outdeg[ri]; c = BlockCount; }
         }
       } else if (c == BlockCount) {
         if (x > (uint64_t)dref + 1) err |= ERR_CORRUPT;
@@ -440,7 +464,7 @@ __global__ void __launch_bounds__(256) k_levels(RangeView rv, uint16_t* keys, ui
     if (!(m & M_DIRECT)) {
       uint32_t u = t, r = (uint32_t)(m & 0xFFFFu);
       while (r) {  // chain of referenced nodes (a node that is final after K1 has no reference)
-        u -= r;
+        u = ref_index(rv, u, r);
         ++lev;
         r = (uint32_t)(rv.meta[u] & 0xFFFFu);
       }
@@ -509,8 +533,9 @@ __device__ __forceinline__ void resolve_node(const RangeView& rv, uint32_t t, ui
   uint32_t* wp = slot;
   uint32_t* const wend = slot + d;
   if (r) {
-    const uint32_t* ref = node_slot(rv, t - r);
-    const uint32_t dref = (uint32_t)(rv.offs[t - r + 1] - rv.offs[t - r]);
+    const uint32_t tr = ref_index(rv, t, r);  // exists: K1 rejected the record otherwise
+    const uint32_t* ref = node_slot(rv, tr);
+    const uint32_t dref = (uint32_t)(rv.offs[tr + 1] - rv.offs[tr]);
     uint32_t ci = 0, k = 0;
     for (;;) {
       // copy block k (even index); the block after the last explicit one is the implicit tail (b even)
@@ -539,6 +564,84 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
     const uint32_t t = order[i];
     if (exact_level && lev[t] != exact_level) continue;
     resolve_node(rv, t, hdr);
+  }
+}
+
+// -------------------------------------------------------------------------------------------- random access
+// graph.successors(v) for a batch of query nodes (examples/bench_random_access.rs:30-38).  The reference
+// builds one decoder per query (bvgraph_decoder_factory.rs:46-58) and webgraph recurses into the referenced
+// node.  Here: the closure of the queries under "referenced node" is built on the device (one round per
+// chain level), sorted and de-duplicated, decoded with the same K0/K1/K2 pipeline as a node LIST, and the
+// query lists are gathered into the caller's CSR.
+__global__ void __launch_bounds__(256) k_query_ids(const uint64_t* q, uint64_t nq, uint64_t res_first, uint64_t res_last,
+                                                   uint32_t* out, uint32_t* err) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const uint64_t v = q[i];
+  if (v < res_first || v >= res_last) { atomicOr(err, ERR_RANGE); out[i] = (uint32_t)res_first; return; }
+  out[i] = (uint32_t)v;
+}
+
+// frontier -> referenced nodes of the frontier (outdegree + reference offset of every node: two symbols)
+__global__ void __launch_bounds__(TPB) k_closure_step(DevGraph g, const uint32_t* in, uint32_t n_in, uint32_t* out,
+                                                      uint32_t* count, uint32_t cap, uint64_t res_first, uint32_t* err_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t target = NOT_FOUND, err = 0;
+  if (i < n_in && g.window != 0) {
+    const uint64_t v = in[i];
+    uint32_t state;
+    int64_t ptr;
+    load_phase(g, v, state, ptr, err);
+    const uint64_t d = ans_decode(g.tb, g.tb.lut, g.tb.ent, Outdegree, state, ptr, g.stream, err);
+    if (d != 0 && !err) {
+      const uint64_t r = ans_decode(g.tb, g.tb.lut, g.tb.ent, ReferenceOffset, state, ptr, g.stream, err);
+      if (r > g.window) err |= ERR_CORRUPT;
+      else if (r != 0 && !err) {
+        if (r > v || v - r < res_first) err |= ERR_RANGE;
+        else target = (uint32_t)(v - r);
+      }
+    }
+  }
+  // warp-aggregated append
+  const uint32_t mask = __ballot_sync(FULL, target != NOT_FOUND);
+  if (mask) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(count, (uint32_t)__popc(mask));
+    base = __shfl_sync(FULL, base, __ffs(mask) - 1);
+    if (target != NOT_FOUND) {
+      const uint32_t pos = base + __popc(mask & ((1u << lane) - 1u));
+      if (pos < cap) out[pos] = target; else err |= ERR_WORKSPACE;
+    }
+  }
+  if (err) atomicOr(err_out, err);
+}
+
+// query i -> index in the sorted node list U; its outdegree goes to offsets[i] (scanned afterwards)
+__global__ void __launch_bounds__(256) k_query_lookup(const uint32_t* qid, uint64_t nq, const uint32_t* U, uint32_t nU,
+                                                      const uint64_t* offsU, uint32_t* qidx, uint64_t* offsets) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nq) return;
+  if (i == nq) { offsets[nq] = 0; return; }
+  const uint32_t v = qid[i];
+  uint32_t lo = 0, hi = nU;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (U[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  qidx[i] = lo;  // present by construction
+  offsets[i] = offsU[lo + 1] - offsU[lo];
+}
+
+// one warp per query: coalesced copy of its list
+__global__ void __launch_bounds__(256) k_query_gather(const uint32_t* qidx, uint64_t nq, const uint64_t* offsU,
+                                                      const uint32_t* succU, const uint64_t* offsets, uint32_t* succ,
+                                                      uint64_t succ_cap) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq; i += ((uint64_t)gridDim.x * blockDim.x) >> 5) {
+    const uint64_t src = offsU[qidx[i]], dst = offsets[i], d = offsets[i + 1] - dst;
+    if (dst + d > succ_cap) continue;  // reported by the host from the total
+    for (uint64_t k = lane; k < d; k += 32) succ[dst + k] = succU[src + k];
   }
 }
 
@@ -663,7 +766,7 @@ void outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets
   if (ws_bytes < p.fixed_bytes) throw Error(WGA_E_WORKSPACE, "workspace too small");
   uint8_t* w = (uint8_t*)ws;
   uint32_t* outdeg = (uint32_t*)(w + p.off_outdeg);
-  k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, first, (uint32_t)n, outdeg, g->d_err);
+  k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, first, nullptr, (uint32_t)n, outdeg, g->d_err);
   count_launch();
   size_t cb = p.cub_bytes;
   cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(outdeg, U32ToU64());
@@ -676,6 +779,85 @@ static void mark(wga_graph* g, cudaStream_t st) {
   if (!g->profiling || g->n_ev >= 8) return;
   if (!g->ev[g->n_ev]) cudaEventCreate(&g->ev[g->n_ev]);
   cudaEventRecord(g->ev[g->n_ev++], st);
+}
+
+// K0 .. K2 on the nodes described by rv (a contiguous range, or a sorted node list), then one host
+// synchronisation that reads back the totals (tot[0] = halo arcs, tot[1] = all arcs), the deepest level and
+// the error word.
+static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const WorkspacePlan& p, Scalars* sc,
+                         const Tuning& tn, cudaStream_t st, uint64_t tot[2]) {
+  const uint64_t n = rv.n;
+  // ---- K0 + scan
+  k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, rv.lo, rv.nodes, (uint32_t)n, rv.outdeg, g->d_err);
+  count_launch();
+  {
+    size_t cb = p.cub_bytes;
+    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(rv.outdeg, U32ToU64());
+    WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_cub, cb, it, rv.offs, (int64_t)(n + 1), st));
+    count_launch(2);
+  }
+  mark(g, st);  // 1: outdegrees + scan done
+  // ---- K1: entropy decode (spans that would overflow the output are skipped and reported)
+  {
+    uint32_t tpb = tn.k1_tpb < 32 ? 32 : (tn.k1_tpb > 128 ? 128 : tn.k1_tpb / 32 * 32);
+    uint32_t span = tn.k1_span ? tn.k1_span : 1;
+    // small ranges: shrink the spans so that the grid still fills the machine (148 SMs x 32 blocks)
+    span = std::min<uint32_t>(span, std::max<uint32_t>(128u, (uint32_t)(n / (148 * 32))));
+    k_entropy<<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
+    count_launch();
+  }
+  mark(g, st);  // 2: entropy decode done
+  // ---- K2: levels, sort by (level, degree), one resolve launch per level
+  uint32_t* lev = (uint32_t*)(w + p.off_lev);
+  cub::DoubleBuffer<uint16_t> dkeys((uint16_t*)(w + p.off_keys[0]), (uint16_t*)(w + p.off_keys[1]));
+  cub::DoubleBuffer<uint32_t> dvals((uint32_t*)(w + p.off_vals[0]), (uint32_t*)(w + p.off_vals[1]));
+  const bool have_refs = g->prelude.compression_window != 0 || g->prelude.min_interval_length != 0;
+  if (have_refs) {
+    k_levels<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rv, dkeys.Current(), dvals.Current(), lev, sc->hist, tn.sort_degree);
+    count_launch();
+    size_t cb = p.cub_bytes;
+    WGA_CUDA(cub::DeviceRadixSort::SortPairs(w + p.off_cub, cb, dkeys, dvals, (int64_t)n, 0, 12, st));
+    count_launch(3);
+    k_segments<<<1, 32, 0, st>>>(sc->hist, sc->seg);
+    count_launch();
+    mark(g, st);  // 3: levels + sort done
+    const uint32_t grid = tn.k2_blocks ? tn.k2_blocks : 1;
+    const uint32_t nlev = g->prelude.compression_window ? LCAP : 1;  // without references everything is level 0
+    for (uint32_t l = 0; l < nlev; ++l) {
+      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, l, 0, lev);
+      count_launch();
+    }
+  } else {
+    mark(g, st);
+  }
+  mark(g, st);  // 4: resolve done
+  // ---- totals, deepest level, error word
+  uint32_t maxlevel = 0, herr = 0;
+  WGA_CUDA(cudaMemcpyAsync(&tot[0], rv.offs + rv.h, 8, cudaMemcpyDeviceToHost, st));
+  WGA_CUDA(cudaMemcpyAsync(&tot[1], rv.offs + n, 8, cudaMemcpyDeviceToHost, st));
+  WGA_CUDA(cudaMemcpyAsync(&maxlevel, &sc->maxlevel, 4, cudaMemcpyDeviceToHost, st));
+  WGA_CUDA(cudaMemcpyAsync(&herr, g->d_err, 4, cudaMemcpyDeviceToHost, st));
+  WGA_CUDA(cudaStreamSynchronize(st));
+  WGA_CUDA(cudaGetLastError());
+  if (tot[0] > rv.halo_cap) {
+    if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
+    throw Error(WGA_E_WORKSPACE, "halo successors exceed the workspace");
+  }
+  if (tot[1] - tot[0] > rv.succ_cap) {
+    if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
+    throw Error(WGA_E_WORKSPACE, "d_succ too small: need " + std::to_string(tot[1] - tot[0]) + " elements");
+  }
+  check_device_error(g, herr, st);
+  // ---- reference chains deeper than LCAP (e.g. graphs compressed with an unbounded max_ref_count): one
+  //      launch per extra level over the shared deep segment
+  if (have_refs && maxlevel >= LCAP) {
+    const uint32_t grid = tn.k2_blocks ? tn.k2_blocks : 1;
+    for (uint32_t l = LCAP; l <= maxlevel; ++l) {
+      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, LCAP, l, lev);
+      count_launch();
+    }
+    check_device_error(g, read_device_error(g, st), st);
+  }
 }
 
 void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets, uint32_t* d_succ,
@@ -735,78 +917,8 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   rv.halo_cap = p.halo_cap;
   rv.succ = d_succ; rv.succ_cap = succ_capacity;
   rv.err = g->d_err;
-  // ---- K0 + scan
-  k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, lo, (uint32_t)n, rv.outdeg, g->d_err);
-  count_launch();
-  {
-    size_t cb = p.cub_bytes;
-    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(rv.outdeg, U32ToU64());
-    WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_cub, cb, it, rv.offs, (int64_t)(n + 1), st));
-    count_launch(2);
-  }
-  mark(g, st);  // 1: outdegrees + scan done
-  // ---- K1: entropy decode (spans that would overflow the output are skipped and reported)
-  {
-    uint32_t tpb = tn.k1_tpb < 32 ? 32 : (tn.k1_tpb > 128 ? 128 : tn.k1_tpb / 32 * 32);
-    uint32_t span = tn.k1_span ? tn.k1_span : 1;
-    // small ranges: shrink the spans so that the grid still fills the machine (148 SMs x 32 blocks)
-    span = std::min<uint32_t>(span, std::max<uint32_t>(128u, (uint32_t)(n / (148 * 32))));
-    k_entropy<<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
-    count_launch();
-  }
-  mark(g, st);  // 2: entropy decode done
-  // ---- K2: levels, sort by (level, degree), one resolve launch per level
-  uint32_t* lev = (uint32_t*)(w + p.off_lev);
-  cub::DoubleBuffer<uint16_t> dkeys((uint16_t*)(w + p.off_keys[0]), (uint16_t*)(w + p.off_keys[1]));
-  cub::DoubleBuffer<uint32_t> dvals((uint32_t*)(w + p.off_vals[0]), (uint32_t*)(w + p.off_vals[1]));
-  const bool have_refs = g->prelude.compression_window != 0 || g->prelude.min_interval_length != 0;
-  if (have_refs) {
-    k_levels<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rv, dkeys.Current(), dvals.Current(), lev, sc->hist, tn.sort_degree);
-    count_launch();
-    size_t cb = p.cub_bytes;
-    WGA_CUDA(cub::DeviceRadixSort::SortPairs(w + p.off_cub, cb, dkeys, dvals, (int64_t)n, 0, 12, st));
-    count_launch(3);
-    k_segments<<<1, 32, 0, st>>>(sc->hist, sc->seg);
-    count_launch();
-    mark(g, st);  // 3: levels + sort done
-    const uint32_t grid = tn.k2_blocks ? tn.k2_blocks : 1;
-    const uint32_t nlev = g->prelude.compression_window ? LCAP : 1;  // without references everything is level 0
-    for (uint32_t l = 0; l < nlev; ++l) {
-      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, l, 0, lev);
-      count_launch();
-    }
-  } else {
-    mark(g, st);
-  }
-  mark(g, st);  // 4: resolve done
-  // ---- totals, deepest level, error word
   uint64_t tot[2] = {0, 0};
-  uint32_t maxlevel = 0, herr = 0;
-  WGA_CUDA(cudaMemcpyAsync(&tot[0], rv.offs + rv.h, 8, cudaMemcpyDeviceToHost, st));
-  WGA_CUDA(cudaMemcpyAsync(&tot[1], rv.offs + n, 8, cudaMemcpyDeviceToHost, st));
-  WGA_CUDA(cudaMemcpyAsync(&maxlevel, &sc->maxlevel, 4, cudaMemcpyDeviceToHost, st));
-  WGA_CUDA(cudaMemcpyAsync(&herr, g->d_err, 4, cudaMemcpyDeviceToHost, st));
-  WGA_CUDA(cudaStreamSynchronize(st));
-  WGA_CUDA(cudaGetLastError());
-  if (tot[0] > rv.halo_cap) {
-    if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
-    throw Error(WGA_E_WORKSPACE, "halo successors exceed the workspace");
-  }
-  if (tot[1] - tot[0] > succ_capacity) {
-    if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
-    throw Error(WGA_E_WORKSPACE, "d_succ too small: need " + std::to_string(tot[1] - tot[0]) + " elements");
-  }
-  check_device_error(g, herr, st);
-  // ---- reference chains deeper than LCAP (e.g. graphs compressed with an unbounded max_ref_count): one
-  //      launch per extra level over the shared deep segment
-  if (have_refs && maxlevel >= LCAP) {
-    const uint32_t grid = tn.k2_blocks ? tn.k2_blocks : 1;
-    for (uint32_t l = LCAP; l <= maxlevel; ++l) {
-      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, LCAP, l, lev);
-      count_launch();
-    }
-    check_device_error(g, read_device_error(g, st), st);
-  }
+  run_pipeline(g, rv, w, p, sc, tn, st, tot);
   if (rv.h) {  // hand the caller offsets relative to `first`
     const uint64_t cnt = last - first + 1;
     k_offsets_rebase<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(rv.offs + rv.h, tot[0], d_offsets, cnt);
@@ -819,6 +931,155 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     for (int i = 1; i < g->n_ev; ++i) cudaEventElapsedTime(&g->stage_ms[i - 1], g->ev[i - 1], g->ev[i]);
   }
   if (h_arcs) *h_arcs = tot[1] - tot[0];
+}
+
+// ---------------------------------------------------------------------------------------------- random access
+namespace {
+struct BatchPlan {
+  uint64_t cap_nodes, cap_arcs;
+  uint64_t off_scal, off_qid, off_all[2], off_U, off_qidx, off_cub, off_offsU, off_succU, off_inner;
+  uint64_t cub_bytes, inner_bytes, total;
+};
+BatchPlan plan_batch(uint64_t nq, uint64_t max_total_arcs) {
+  BatchPlan b{};
+  b.cap_nodes = 8 * nq + 4096;       // queries + every node on their reference chains
+  if (b.cap_nodes > 0xFFFFFFF0ull) b.cap_nodes = 0xFFFFFFF0ull;
+  b.cap_arcs = 4 * max_total_arcs + 65536;
+  uint64_t o = 0;
+  b.off_scal = o; o += 256;
+  b.off_qid = o; o = align_up(o + 4 * (nq + 1), 256);
+  for (int i = 0; i < 2; ++i) { b.off_all[i] = o; o = align_up(o + 4 * b.cap_nodes, 256); }
+  b.off_U = o; o = align_up(o + 4 * b.cap_nodes, 256);
+  b.off_qidx = o; o = align_up(o + 4 * (nq + 1), 256);
+  size_t c1 = 0, c2 = 0, c3 = 0;
+  cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr);
+  cub::DeviceRadixSort::SortKeys(nullptr, c1, dk, (int64_t)b.cap_nodes, 0, 32);
+  cub::DeviceSelect::Unique(nullptr, c2, (const uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)b.cap_nodes);
+  cub::DeviceScan::ExclusiveSum(nullptr, c3, (uint64_t*)nullptr, (uint64_t*)nullptr, (int64_t)(nq + 1));
+  b.cub_bytes = std::max(c1, std::max(c2, c3)) + 4096;
+  b.off_cub = o; o = align_up(o + b.cub_bytes, 256);
+  b.off_offsU = o; o = align_up(o + 8 * (b.cap_nodes + 1), 256);
+  b.off_succU = o; o = align_up(o + 4 * b.cap_arcs, 256);
+  WorkspacePlan p = plan_workspace(b.cap_nodes);
+  b.inner_bytes = p.fixed_bytes + 4 * (b.cap_nodes / 4 + b.cap_arcs / 8 + (1u << 20));
+  b.off_inner = o; o += b.inner_bytes;
+  b.total = o;
+  return b;
+}
+}  // namespace
+
+uint64_t successors_workspace_size(const wga_graph*, uint64_t n_queries, uint64_t max_total_arcs) {
+  return plan_batch(n_queries, max_total_arcs).total;
+}
+
+void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64_t* d_offsets, uint32_t* d_succ,
+                      uint64_t succ_capacity, void* ws, uint64_t ws_bytes, uint64_t* h_arcs, cudaStream_t st) {
+  if (!g->on_device) throw Error(WGA_E_CUDA, "graph was opened host-only");
+  if (nq >= 0xFFFFFFF0ull) throw Error(WGA_E_UNSUPPORTED, "too many queries for one call");
+  if (nq == 0) {
+    WGA_CUDA(cudaMemsetAsync(d_offsets, 0, 8, st));
+    if (h_arcs) *h_arcs = 0;
+    return;
+  }
+  // the caller sizes the workspace with an upper bound of the arcs it expects; recover it from the size
+  BatchPlan b = plan_batch(nq, 0);
+  if (ws_bytes < b.total) throw Error(WGA_E_WORKSPACE, "workspace too small");
+  {  // largest arc bound whose plan fits this workspace (the plan grows by ~18 bytes per arc)
+    uint64_t A = (ws_bytes - b.total) / 18;
+    BatchPlan b2 = plan_batch(nq, A);
+    while (b2.total > ws_bytes && A) { A = A / 16 * 15; b2 = plan_batch(nq, A); }
+    if (b2.total <= ws_bytes) b = b2;
+  }
+  const Tuning tn = g_tuning;
+  uint8_t* w = (uint8_t*)ws;
+  uint32_t* scal = (uint32_t*)(w + b.off_scal);  // [0] closure count, [1] unique count
+  WGA_CUDA(cudaMemsetAsync(scal, 0, 256, st));
+  uint32_t* qid = (uint32_t*)(w + b.off_qid);
+  uint32_t* all = (uint32_t*)(w + b.off_all[0]);
+  k_query_ids<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(d_nodes, nq, g->res_first, g->res_last, qid, g->d_err);
+  count_launch();
+  if (!d_succ) {  // sizing call: only the outdegrees of the queries (first symbol of each record)
+    uint32_t* deg = all;
+    k_outdegree<<<(unsigned)((nq + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, 0, qid, (uint32_t)nq, deg, g->d_err);
+    size_t cbs = b.cub_bytes;
+    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(deg, U32ToU64());
+    WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + b.off_cub, cbs, it, d_offsets, (int64_t)(nq + 1), st));
+    count_launch(3);
+    uint64_t arcs0 = 0;
+    WGA_CUDA(cudaMemcpyAsync(&arcs0, d_offsets + nq, 8, cudaMemcpyDeviceToHost, st));
+    check_device_error(g, read_device_error(g, st), st);
+    if (h_arcs) *h_arcs = arcs0;
+    return;
+  }
+  WGA_CUDA(cudaMemcpyAsync(all, qid, 4 * nq, cudaMemcpyDeviceToDevice, st));
+  // ---- closure under "referenced node": one round per chain level
+  uint64_t total = nq, n_in = nq, in_off = 0;
+  while (n_in) {
+    if (total >= b.cap_nodes) throw Error(WGA_E_WORKSPACE, "reference closure exceeds the workspace");
+    WGA_CUDA(cudaMemsetAsync(scal, 0, 4, st));
+    k_closure_step<<<(unsigned)((n_in + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, all + in_off, (uint32_t)n_in, all + total,
+                                                                       scal, (uint32_t)(b.cap_nodes - total),
+                                                                       g->res_first, g->d_err);
+    count_launch();
+    uint32_t cnt = 0;
+    WGA_CUDA(cudaMemcpyAsync(&cnt, scal, 4, cudaMemcpyDeviceToHost, st));
+    WGA_CUDA(cudaStreamSynchronize(st));
+    if (total + cnt > b.cap_nodes) throw Error(WGA_E_WORKSPACE, "reference closure exceeds the workspace");
+    in_off = total;
+    n_in = cnt;
+    total += cnt;
+  }
+  // ---- sort + unique -> U
+  cub::DoubleBuffer<uint32_t> dk(all, (uint32_t*)(w + b.off_all[1]));
+  size_t cb = b.cub_bytes;
+  int end_bit = 1;
+  while (end_bit < 32 && (g->prelude.number_of_nodes >> end_bit)) ++end_bit;
+  WGA_CUDA(cub::DeviceRadixSort::SortKeys(w + b.off_cub, cb, dk, (int64_t)total, 0, end_bit, st));
+  uint32_t* U = (uint32_t*)(w + b.off_U);
+  cb = b.cub_bytes;
+  WGA_CUDA(cub::DeviceSelect::Unique(w + b.off_cub, cb, dk.Current(), U, scal + 1, (int64_t)total, st));
+  count_launch(6);
+  uint32_t nU = 0;
+  WGA_CUDA(cudaMemcpyAsync(&nU, scal + 1, 4, cudaMemcpyDeviceToHost, st));
+  WGA_CUDA(cudaStreamSynchronize(st));
+  check_device_error(g, read_device_error(g, st), st);
+  // ---- decode the node list U into a temporary CSR
+  uint8_t* iw = w + b.off_inner;
+  WGA_CUDA(cudaMemsetAsync(iw, 0, 256, st));
+  WorkspacePlan p = plan_workspace(nU);
+  if (p.fixed_bytes + 4096 > b.inner_bytes) throw Error(WGA_E_WORKSPACE, "workspace too small");
+  Scalars* sc = (Scalars*)iw;
+  RangeView rv{};
+  rv.lo = 0; rv.first = 0; rv.n = nU; rv.h = 0; rv.nodes = U;
+  rv.outdeg = (uint32_t*)(iw + p.off_outdeg);
+  rv.offs = (uint64_t*)(w + b.off_offsU);
+  rv.meta = (uint64_t*)(iw + p.off_meta);
+  rv.arena = (uint32_t*)(iw + p.off_arena);
+  rv.arena_cap = (b.inner_bytes - p.off_arena) / 4;
+  rv.cursor = &sc->cursor;
+  rv.maxlevel = &sc->maxlevel;
+  rv.halo_succ = nullptr; rv.halo_cap = 0;
+  rv.succ = (uint32_t*)(w + b.off_succU); rv.succ_cap = b.cap_arcs;
+  rv.err = g->d_err;
+  g->n_ev = 0;
+  uint64_t tot[2] = {0, 0};
+  const bool prof = g->profiling;
+  g->profiling = false;
+  try { run_pipeline(g, rv, iw, p, sc, tn, st, tot); } catch (...) { g->profiling = prof; throw; }
+  g->profiling = prof;
+  // ---- gather the query lists
+  uint32_t* qidx = (uint32_t*)(w + b.off_qidx);
+  k_query_lookup<<<(unsigned)((nq + 1 + 255) / 256), 256, 0, st>>>(qid, nq, U, nU, rv.offs, qidx, d_offsets);
+  cb = b.cub_bytes;
+  WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + b.off_cub, cb, d_offsets, d_offsets, (int64_t)(nq + 1), st));
+  uint64_t arcs = 0;
+  WGA_CUDA(cudaMemcpyAsync(&arcs, d_offsets + nq, 8, cudaMemcpyDeviceToHost, st));
+  k_query_gather<<<148 * 8, 256, 0, st>>>(qidx, nq, rv.offs, rv.succ, d_offsets, d_succ, succ_capacity);
+  count_launch(4);
+  WGA_CUDA(cudaStreamSynchronize(st));
+  WGA_CUDA(cudaGetLastError());
+  if (arcs > succ_capacity) throw Error(WGA_E_WORKSPACE, "d_succ too small: need " + std::to_string(arcs) + " elements");
+  if (h_arcs) *h_arcs = arcs;
 }
 
 void debug_expand_table(wga_graph* g, int c, void* h_out, uint64_t n_slots) {

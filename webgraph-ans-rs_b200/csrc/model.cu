@@ -647,12 +647,4 @@ void ModelBuilder::build(ComponentModel out[WGA_COMPONENTS], double* h_original_
   }
 }
 
-// -------------------------------------------------------------------------------------------------
-// random access is implemented in decode.cu's successor file; kept here until then
-uint64_t successors_workspace_size(const wga_graph*, uint64_t, uint64_t) { return 0; }
-void successors_batch(wga_graph*, const uint64_t*, uint64_t, uint64_t*, uint32_t*, uint64_t, void*, uint64_t,
-                      uint64_t*, cudaStream_t) {
-  throw Error(WGA_E_UNSUPPORTED, "successors_batch: not implemented yet");
-}
-
 }  // namespace wga
