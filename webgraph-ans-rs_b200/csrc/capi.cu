@@ -288,7 +288,7 @@ int wga_successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t n_queri
                          uint32_t* d_succ, uint64_t succ_capacity, void* d_workspace, uint64_t workspace_bytes,
                          uint64_t* h_arcs, void* stream) {
   return guarded([&] {
-    if (!g || !d_nodes || !d_offsets || !d_workspace) throw Error(WGA_E_ARG, "null argument");
+    if (!g || (!d_nodes && n_queries) || !d_offsets || (!d_workspace && n_queries)) throw Error(WGA_E_ARG, "null argument");
     successors_batch(g, d_nodes, n_queries, d_offsets, d_succ, succ_capacity, d_workspace, workspace_bytes, h_arcs,
                      (cudaStream_t)stream);
   });
