@@ -490,80 +490,139 @@ __global__ void k_segments(const uint32_t* hist, uint32_t* seg) {
   }
 }
 
-__device__ __forceinline__ void resolve_node(const RangeView& rv, uint32_t t, uint32_t* hdr /* HS+1 words, shared */) {
-  const uint64_t m = rv.meta[t];
-  const uint32_t r = (uint32_t)(m & 0xFFFFu);
-  uint32_t* const slot = node_slot(rv, t);
-  const uint32_t d = (uint32_t)(rv.offs[t + 1] - rv.offs[t]);
-  // ---- header
-  uint32_t b, ni, nres;
-  const uint16_t* blk16 = nullptr;
-  const uint32_t* blk32 = nullptr;
-  const uint32_t* pp;
-  if (m & M_OVF) {
-    const uint32_t* rec = rv.arena + (uint32_t)(m >> 19);
-    b = rec[0]; ni = rec[1]; nres = rec[2];
-    blk32 = rec + 4;
-    pp = rv.arena + rec[3];
-  } else {
-    b = (uint32_t)(m >> 19) & (MAX_B - 1);
-    ni = (uint32_t)(m >> 34) & (MAX_NI - 1);
-    nres = (uint32_t)(m >> 48);
-    const uint32_t hb = (b + 1) >> 1, H = hb + 2 * ni;  // K1 guarantees H <= HS for in-slot headers
-    for (uint32_t w = 0; w < H; ++w) hdr[w] = slot[w];
-    blk16 = reinterpret_cast<const uint16_t*>(hdr);
-    pp = hdr + hb;
-  }
-  const uint32_t* rp = slot + (d - nres);
-  // ---- extras: expanded intervals and residuals, merged on the fly
-  uint32_t rj = 0, rval = nres ? rp[0] : INF;
-  uint32_t ik = 0, ival = INF, iend = 0;
-  if (ni) { ival = pp[0]; iend = ival + pp[1]; }
-  uint32_t ev = min(ival, rval);
-  auto advance = [&]() {
-    if (ev == ival) {
-      if (++ival == iend) {
-        if (++ik < ni) { ival = pp[2 * ik]; iend = ival + pp[2 * ik + 1]; } else ival = INF;
-      }
-    } else {
-      rval = (++rj < nres) ? rp[rj] : INF;
-    }
-    ev = min(ival, rval);
-  };
-  uint32_t* wp = slot;
-  uint32_t* const wend = slot + d;
-  if (r) {
-    const uint32_t tr = ref_index(rv, t, r);  // exists: K1 rejected the record otherwise
-    const uint32_t* ref = node_slot(rv, tr);
-    const uint32_t dref = (uint32_t)(rv.offs[tr + 1] - rv.offs[tr]);
-    uint32_t ci = 0, k = 0;
-    for (;;) {
-      // copy block k (even index); the block after the last explicit one is the implicit tail (b even)
-      const uint32_t len = k < b ? (blk32 ? blk32[k] : (uint32_t)blk16[k]) : dref - ci;
-      const uint32_t cend = ci + len;
-      for (; ci < cend; ++ci) {
-        const uint32_t c = ref[ci];
-        while (ev < c && wp < wend) { *wp++ = ev; advance(); }
-        if (wp < wend) *wp++ = c;
-      }
-      if (k >= b) break;
-      if (++k >= b) break;  // odd block count: the rest of the referenced list is skipped
-      ci += blk32 ? blk32[k] : (uint32_t)blk16[k];
-      ++k;
-    }
-  }
-  while (ev != INF && wp < wend) { *wp++ = ev; advance(); }
-}
-
+// One level of phase two.  Lane-per-node state machine (same shape as K1): every lane holds one node and
+// emits ONE successor per iteration -- the minimum of the three stream heads (copied element, interval
+// element, residual) -- so that all lanes of a warp run the same short merge step regardless of how their
+// lists are composed.  Lanes that finish a node wait until SETUP_BATCH lanes are free and then fetch + set up
+// their next nodes together (the set-up is several dependent HBM loads and ~100 instructions).
+// Each block owns a contiguous chunk of the level's segment and hands its nodes out in order, so that the
+// lanes of a warp work on neighbouring nodes (their records, offsets and referenced lists share sectors).
 __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_t* order, const uint32_t* seg,
                                                      uint32_t lb, uint32_t exact_level, const uint32_t* lev) {
   __shared__ uint32_t s_hdr[RES_TPB * (HS + 1)];
-  uint32_t* hdr = s_hdr + threadIdx.x * (HS + 1);  // odd stride: conflict-free
+  __shared__ uint32_t s_next;
+  uint32_t* const hdr = s_hdr + threadIdx.x * (HS + 1);  // odd stride: conflict-free
   const uint32_t beg = seg[lb], end = seg[lb + 1];
-  for (uint32_t i = beg + blockIdx.x * RES_TPB + threadIdx.x; i < end; i += gridDim.x * RES_TPB) {
-    const uint32_t t = order[i];
-    if (exact_level && lev[t] != exact_level) continue;
-    resolve_node(rv, t, hdr);
+  const uint32_t len = end - beg;
+  const uint32_t chunk = (len + gridDim.x - 1) / gridDim.x;
+  const uint32_t cb = beg + min(len, blockIdx.x * chunk), ce = beg + min(len, (blockIdx.x + 1) * chunk);
+  if (cb >= ce) return;
+  if (threadIdx.x == 0) s_next = cb;
+  __syncthreads();
+  constexpr uint32_t SETUP_BATCH = 8;
+  enum { S_FETCH, S_MERGE, S_IDLE };
+  int st = S_FETCH;
+  // streams of the current node
+  uint32_t* wp = nullptr;
+  uint32_t* wend = nullptr;
+  uint32_t* vbeg = nullptr;         // [vbeg, vend): 16-byte aligned part of the slot
+  uint32_t* vend = nullptr;
+  uint4 buf = make_uint4(0, 0, 0, 0);
+  const uint32_t* cptr = nullptr;   // next element of the referenced list
+  const uint32_t* cendp = nullptr;  // end of the current copy block
+  const uint32_t* refend = nullptr;
+  const uint32_t* blk32 = nullptr;  // block lengths in the overflow arena (else u16 in hdr)
+  const uint32_t* pp = nullptr;     // interval pairs (hdr or arena)
+  const uint32_t* rptr = nullptr;   // next residual
+  uint32_t cval = INF, ival = INF, iend = 0, rval = INF, b = 0, bk = 0, ni = 0, ik = 0;
+  // the current copy block is exhausted: skip block bk, then copy block bk+1 (or the implicit tail)
+  auto next_copy_block = [&]() {
+    cval = INF;
+    if (bk < b) {
+      cptr += blk32 ? blk32[bk] : (uint32_t) reinterpret_cast<const uint16_t*>(hdr)[bk];
+      ++bk;
+      if (bk < b) {
+        cendp = cptr + (blk32 ? blk32[bk] : (uint32_t) reinterpret_cast<const uint16_t*>(hdr)[bk]);
+        ++bk;
+      } else cendp = refend;
+      if (cptr < cendp) cval = *cptr;
+    }
+  };
+  for (;;) {
+    const uint32_t fetchers = __ballot_sync(FULL, st == S_FETCH);
+    const uint32_t mergers = __ballot_sync(FULL, st == S_MERGE);
+    if ((fetchers | mergers) == 0) break;
+    if (fetchers && (mergers == 0 || __popc(fetchers) >= SETUP_BATCH)) {
+      if (st == S_FETCH) {
+        uint32_t i = atomicAdd(&s_next, 1u);
+        uint32_t t = 0;
+        bool have = false;
+        while (i < ce) {  // (levels deeper than LCAP share a segment: skip nodes of other levels)
+          t = order[i];
+          if (!exact_level || lev[t] == exact_level) { have = true; break; }
+          i = atomicAdd(&s_next, 1u);
+        }
+        if (!have) st = S_IDLE;
+        else {
+          const uint64_t m = rv.meta[t];
+          const uint32_t r = (uint32_t)(m & 0xFFFFu);
+          uint32_t* const slot = node_slot(rv, t);
+          const uint32_t d = (uint32_t)(rv.offs[t + 1] - rv.offs[t]);
+          uint32_t nres;
+          if (m & M_OVF) {
+            const uint32_t* rec = rv.arena + (uint32_t)(m >> 19);
+            b = rec[0]; ni = rec[1]; nres = rec[2];
+            blk32 = rec + 4;
+            pp = rv.arena + rec[3];
+          } else {
+            b = (uint32_t)(m >> 19) & (MAX_B - 1);
+            ni = (uint32_t)(m >> 34) & (MAX_NI - 1);
+            nres = (uint32_t)(m >> 48);
+            const uint32_t hb = (b + 1) >> 1, H = hb + 2 * ni;  // K1 guarantees H <= HS for in-slot headers
+            for (uint32_t w = 0; w < H; ++w) hdr[w] = slot[w];
+            blk32 = nullptr;
+            pp = hdr + hb;
+          }
+          wp = slot;
+          wend = slot + d;
+          vbeg = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(slot) + 15) & ~(uintptr_t)15);
+          vend = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(wend) & ~(uintptr_t)15);
+          rptr = slot + (d - nres);
+          rval = nres ? *rptr : INF;
+          ik = 0;
+          ival = INF;
+          if (ni) { ival = pp[0]; iend = ival + pp[1]; }
+          cval = INF;
+          if (r) {
+            const uint32_t tr = ref_index(rv, t, r);  // exists: K1 rejected the record otherwise
+            cptr = node_slot(rv, tr);
+            refend = cptr + (uint32_t)(rv.offs[tr + 1] - rv.offs[tr]);
+            bk = 0;
+            cendp = refend;
+            if (b) {
+              cendp = cptr + (blk32 ? blk32[0] : (uint32_t) reinterpret_cast<const uint16_t*>(hdr)[0]);
+              bk = 1;
+            }
+            if (cptr < cendp) cval = *cptr;
+            else next_copy_block();  // empty first copy block
+          }
+          st = (d != 0) ? S_MERGE : S_FETCH;
+        }
+      }
+    }
+    if (st == S_MERGE) {
+      const uint32_t mn = min(cval, min(ival, rval));
+      // 16-byte stores for the aligned middle of the slot (one L2 write transaction per 4 successors instead
+      // of 4), scalar stores for the unaligned head and tail
+      if (wp >= vbeg && wp < vend) {
+        const uint32_t q = (uint32_t)(reinterpret_cast<uintptr_t>(wp) >> 2) & 3u;
+        if (q == 0) buf.x = mn; else if (q == 1) buf.y = mn; else if (q == 2) buf.z = mn;
+        else { buf.w = mn; *reinterpret_cast<uint4*>(wp - 3) = buf; }
+      } else *wp = mn;
+      ++wp;
+      if (mn == cval) {
+        if (++cptr == cendp) next_copy_block();
+        else cval = *cptr;
+      } else if (mn == rval) {
+        ++rptr;
+        rval = rptr < wend ? *rptr : INF;
+      } else {
+        if (++ival == iend) {
+          if (++ik < ni) { ival = pp[2 * ik]; iend = ival + pp[2 * ik + 1]; } else ival = INF;
+        }
+      }
+      if (wp == wend) st = S_FETCH;
+    }
   }
 }
 
