@@ -33,7 +33,8 @@ std::atomic<uint64_t> g_kernel_launches{0};
 struct Tuning {
   uint32_t k1_span = 2048;    // nodes per K1 block
   uint32_t k1_tpb = 128;      // threads per K1 block
-  uint32_t k2_blocks = 148 * 12;  // K2 grid (blocks of 128 lanes striding over a level's segment)
+  uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
+                              // equal chunk of the level, so a partial second wave would double the time
   uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
   uint32_t sort_degree = 0;   // K2: 1 = sort key includes the degree bucket; 0 = level only, node order kept
                               // (measured: locality of neighbouring nodes beats equal loop lengths, 2.9 vs 6.6 ms)
@@ -840,6 +841,19 @@ static void mark(wga_graph* g, cudaStream_t st) {
   cudaEventRecord(g->ev[g->n_ev++], st);
 }
 
+static uint32_t resolve_grid(const Tuning& tn) {
+  if (tn.k2_blocks) return tn.k2_blocks;
+  static uint32_t cached = 0;
+  if (!cached) {
+    int dev = 0, sms = 148, per_sm = 8;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resolve, RES_TPB, 0);
+    cached = (uint32_t)(sms * (per_sm > 0 ? per_sm : 1));
+  }
+  return cached;
+}
+
 // K0 .. K2 on the nodes described by rv (a contiguous range, or a sorted node list), then one host
 // synchronisation that reads back the totals (tot[0] = halo arcs, tot[1] = all arcs), the deepest level and
 // the error word.
@@ -880,7 +894,7 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
     k_segments<<<1, 32, 0, st>>>(sc->hist, sc->seg);
     count_launch();
     mark(g, st);  // 3: levels + sort done
-    const uint32_t grid = tn.k2_blocks ? tn.k2_blocks : 1;
+    const uint32_t grid = resolve_grid(tn);
     const uint32_t nlev = g->prelude.compression_window ? LCAP : 1;  // without references everything is level 0
     for (uint32_t l = 0; l < nlev; ++l) {
       k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, l, 0, lev);
@@ -910,7 +924,7 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
   // ---- reference chains deeper than LCAP (e.g. graphs compressed with an unbounded max_ref_count): one
   //      launch per extra level over the shared deep segment
   if (have_refs && maxlevel >= LCAP) {
-    const uint32_t grid = tn.k2_blocks ? tn.k2_blocks : 1;
+    const uint32_t grid = resolve_grid(tn);
     for (uint32_t l = LCAP; l <= maxlevel; ++l) {
       k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, LCAP, l, lev);
       count_launch();
