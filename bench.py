@@ -35,6 +35,8 @@ WORKLOADS = {
     "web-1m": ("web", 1_000_000, 34.3, 0x5EED0010),
     "tiny": ("web", 100_000, 34.3, 0x5EED0011),
 }
+# measured DRAM traffic of one decode step (sum over the kernels of the chain), see profiles/r01_*_ncu_*.txt
+NCU_DRAM_BYTES_PER_STEP = {}
 BVCOMP = dict(compression_window=7, max_ref_count=3, min_interval_length=4)  # CLI defaults
 CHUNK_NODES = 65536
 
@@ -203,6 +205,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="eu-2015-host-shaped", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--random-nodes", type=int, default=1_000_000,
+                    help="queries of the random-access leg (reference: 10M on twitter-2010)")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -293,11 +297,50 @@ def main():
     peak, peak_src = measured_peak_gbs()
     step_kernel_ms = float(sum(kernels.values())) or ms
     achieved = b_alg / (step_kernel_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of the whole launch chain from the committed ncu --set full
+    # capture (profiles/, one step of this workload); None for workloads that were not captured
+    traffic = NCU_DRAM_BYTES_PER_STEP.get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "kernel": "decode step = k_outdegree + scan + k_entropy + k_levels + sort + k_resolve per level; one launch chain per step",
                 "algorithmic_bytes_per_step": int(b_alg), "bytes_per_arc": b_alg / max(1, arcs),
                 "stage_ms": kernels, "step_ms_events": step_kernel_ms}
+
+    # ---- random access (examples/bench_random_access.rs:15,30-38): uniformly random nodes, seed 0,
+    #      ns/arc = device time of wga_successors_batch / sum of outdegrees
+    ra = None
+    try:
+        nq = int(min(args.random_nodes, max(1000, n)))
+        rng = np.random.default_rng(0)
+        q_t = torch.from_numpy(rng.integers(0, n, nq).astype(np.int64)).cuda()
+        q_off = torch.empty(nq + 1, dtype=torch.int64, device="cuda")
+        sz_ws = torch.empty(g.successors_workspace_size(nq, 0), dtype=torch.uint8, device="cuda")
+        got_arcs = C.c_uint64(0)
+        rc = W.lib().wga_successors_batch(g._h, C.c_void_p(q_t.data_ptr()), C.c_uint64(nq), C.c_void_p(q_off.data_ptr()),
+                                          None, C.c_uint64(0), C.c_void_p(sz_ws.data_ptr()), C.c_uint64(sz_ws.numel()),
+                                          C.byref(got_arcs), C.c_void_p(stream))
+        assert rc == 0, W.lib().wga_last_error()
+        q_arcs = got_arcs.value
+        del sz_ws
+        q_succ = torch.empty(q_arcs + 1024, dtype=torch.int32, device="cuda")
+        q_ws = torch.empty(g.successors_workspace_size(nq, q_arcs), dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            g.successors_batch_into(q_t, q_off, q_succ, q_ws, stream=stream)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(3):
+            g.successors_batch_into(q_t, q_off, q_succ, q_ws, stream=stream)
+        r1.record()
+        torch.cuda.synchronize()
+        ra_ms = r0.elapsed_time(r1) / 3
+        ra = {"queries": nq, "arcs": int(q_arcs), "ms": ra_ms, "ns_per_arc": ra_ms * 1e6 / max(1, q_arcs),
+              "Garcs_per_s": q_arcs / (ra_ms * 1e-3) / 1e9}
+        ra_check = (q_t.cpu().numpy(), q_off.cpu().numpy().astype(np.uint64), q_succ[:q_arcs].cpu().numpy().view(np.uint32))
+        del q_succ, q_ws
+    except Exception as e:  # reported, not fatal: the headline metric is the full decode
+        log("random access leg failed:", e)
+        ra_check = None
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D inputs + decode + D2H result
     h_off = torch.empty(n + 1, dtype=torch.int64).pin_memory()
@@ -345,6 +388,17 @@ def main():
             ok = bool((h_succ.numpy()[:arcs].view(np.uint32) == ref_succ).all())  # e2e result (host)
             ok = ok and bool(torch.equal(succ[:arcs].cpu(), torch.from_numpy(ref_succ.view(np.int32))))  # device result
             ok = ok and bool((h_off.numpy().astype(np.uint64) == d_off).all()) and int(d_off[-1]) == arcs
+            if ok and ra_check is not None:  # random access result == the same lists of the sequential decode
+                qn, qo, qs = ra_check
+                exp_deg = (d_off[qn + 1] - d_off[qn]).astype(np.uint64)
+                ok = bool((np.diff(qo) == exp_deg).all())
+                sample = np.random.default_rng(1).integers(0, qn.size, min(qn.size, 20000))
+                for i in sample:
+                    v = int(qn[i])
+                    if not (qs[int(qo[i]):int(qo[i + 1])] == ref_succ[int(d_off[v]):int(d_off[v + 1])]).all():
+                        ok = False
+                        break
+                ra["verified_bit_exact"] = ok
             verified = ok
             log(f"verification vs oracle: {'bit-exact' if ok else 'MISMATCH'} ({time.time() - t0:.1f}s)")
             if not ok:
@@ -373,7 +427,8 @@ def main():
                            "bits_per_link": meta["bits_per_link"], "symbols_per_gpu": meta["symbols"],
                            "l2": "inputs+outputs (%.2f GB per step) exceed the 126 MB L2; no flush needed" % (b_alg / 1e9),
                            "sharding": "one independent graph of this shape per rank; shared model from NCCL all-reduced histograms"},
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "random_access": ra,
+                "gpu_launches": int(launches),
                 "clocks": clocks, "verified_bit_exact": verified,
                 "aggregate": {"arcs": arcs_all, "algorithmic_bytes": bytes_all,
                               "achieved_gbs_all_gpus": bytes_all / (ms_max * 1e-3) / 1e9,

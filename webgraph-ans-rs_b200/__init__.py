@@ -263,6 +263,20 @@ class BvGraph:
                                         C.byref(cap), st))
         return off, succ[:cap.value]
 
+    def successors_batch_into(self, nodes_t, offsets, succ, workspace, stream=None):
+        """wga_successors_batch with caller-owned cuda tensors (no allocation on the timed path); -> arcs."""
+        torch = _torch()
+        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        arcs = C.c_uint64(0)
+        _chk(lib().wga_successors_batch(self._h, C.c_void_p(nodes_t.data_ptr()), C.c_uint64(nodes_t.numel()),
+                                        C.c_void_p(offsets.data_ptr()), C.c_void_p(succ.data_ptr()),
+                                        C.c_uint64(succ.numel()), C.c_void_p(workspace.data_ptr()),
+                                        C.c_uint64(workspace.numel()), C.byref(arcs), st))
+        return arcs.value
+
+    def successors_workspace_size(self, n_queries, max_total_arcs):
+        return int(lib().wga_successors_workspace_size(self._h, C.c_uint64(n_queries), C.c_uint64(max_total_arcs)))
+
     def successors(self, v):
         """Ascending successors of node v (BvGraph::successors)."""
         off, succ = self.successors_batch([v])
@@ -284,6 +298,33 @@ class BvGraph:
         _chk(lib().wga_debug_decode_symbols(self._h, _np(comps), C.c_uint64(comps.size), p, C.c_uint32(state),
                                             _np(out), C.byref(ep), C.byref(es)))
         return out, ep.value, es.value
+
+
+def shard_ranges(pointers, world):
+    """Contiguous node ranges [(first, last)] for `world` ranks, balanced by compressed stream words.
+    `pointers` is the expanded .pointers array in file order (entry i = node N-1-i, random_access.rs:225-231):
+    the record of node v occupies stream words [pointers[N-1-(v+1)], pointers[N-1-v]), so a binary search on
+    the (monotone) pointers splits the stream evenly."""
+    ptr = np.asarray(pointers, np.uint64)
+    n = ptr.size
+    if n == 0:
+        return [(0, 0)] * world
+    total = int(ptr[-1])  # pointer of node 0 = stream length
+    by_node = ptr[::-1]   # by_node[v] = start pointer of node v, non-increasing in v
+    cuts = [0]
+    for k in range(1, world):
+        target = total - total * k // world  # words left to the right of the cut
+        # first node whose start pointer is <= target
+        v = int(np.searchsorted(-by_node.astype(np.int64), -int(target), side="left"))
+        cuts.append(min(max(v, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[k], cuts[k + 1]) for k in range(world)]
+
+
+def shard_resident_range(first, last, compression_window, margin_chains=64):
+    """Nodes whose inputs a rank must hold to decode [first, last): the range plus a margin on the left for
+    the reference chains that leave it (window x chain depth; k_halo finds the exact closure at decode time)."""
+    return max(0, first - max(1, compression_window) * margin_chains), last
 
 
 def _open(basename, flags=0, shard=None):

@@ -516,9 +516,6 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
   // streams of the current node
   uint32_t* wp = nullptr;
   uint32_t* wend = nullptr;
-  uint32_t* vbeg = nullptr;         // [vbeg, vend): 16-byte aligned part of the slot
-  uint32_t* vend = nullptr;
-  uint4 buf = make_uint4(0, 0, 0, 0);
   const uint32_t* cptr = nullptr;   // next element of the referenced list
   const uint32_t* cendp = nullptr;  // end of the current copy block
   const uint32_t* refend = nullptr;
@@ -576,8 +573,6 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
           }
           wp = slot;
           wend = slot + d;
-          vbeg = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(slot) + 15) & ~(uintptr_t)15);
-          vend = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(wend) & ~(uintptr_t)15);
           rptr = slot + (d - nres);
           rval = nres ? *rptr : INF;
           ik = 0;
@@ -603,14 +598,7 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
     }
     if (st == S_MERGE) {
       const uint32_t mn = min(cval, min(ival, rval));
-      // 16-byte stores for the aligned middle of the slot (one L2 write transaction per 4 successors instead
-      // of 4), scalar stores for the unaligned head and tail
-      if (wp >= vbeg && wp < vend) {
-        const uint32_t q = (uint32_t)(reinterpret_cast<uintptr_t>(wp) >> 2) & 3u;
-        if (q == 0) buf.x = mn; else if (q == 1) buf.y = mn; else if (q == 2) buf.z = mn;
-        else { buf.w = mn; *reinterpret_cast<uint4*>(wp - 3) = buf; }
-      } else *wp = mn;
-      ++wp;
+      *wp++ = mn;  // (buffering 4 successors for 16-byte stores was measured: no gain, the kernel is issue-bound)
       if (mn == cval) {
         if (++cptr == cendp) next_copy_block();
         else cval = *cptr;
