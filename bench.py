@@ -308,7 +308,7 @@ def main():
 
     # ---- random access (examples/bench_random_access.rs:15,30-38): uniformly random nodes, seed 0,
     #      ns/arc = device time of wga_successors_batch / sum of outdegrees
-    ra = None
+    ra_gpu = None
     try:
         nq = int(min(args.random_nodes, max(1000, n)))
         rng = np.random.default_rng(0)
@@ -334,7 +334,7 @@ def main():
         r1.record()
         torch.cuda.synchronize()
         ra_ms = r0.elapsed_time(r1) / 3
-        ra = {"queries": nq, "arcs": int(q_arcs), "ms": ra_ms, "ns_per_arc": ra_ms * 1e6 / max(1, q_arcs),
+        ra_gpu = {"queries": nq, "arcs": int(q_arcs), "ms": ra_ms, "ns_per_arc": ra_ms * 1e6 / max(1, q_arcs),
               "Garcs_per_s": q_arcs / (ra_ms * 1e-3) / 1e9}
         ra_check = (q_t.cpu().numpy(), q_off.cpu().numpy().astype(np.uint64), q_succ[:q_arcs].cpu().numpy().view(np.uint32))
         del q_succ, q_ws
@@ -398,7 +398,7 @@ def main():
                     if not (qs[int(qo[i]):int(qo[i + 1])] == ref_succ[int(d_off[v]):int(d_off[v + 1])]).all():
                         ok = False
                         break
-                ra["verified_bit_exact"] = ok
+                ra_gpu["verified_bit_exact"] = ok
             verified = ok
             log(f"verification vs oracle: {'bit-exact' if ok else 'MISMATCH'} ({time.time() - t0:.1f}s)")
             if not ok:
@@ -427,7 +427,7 @@ def main():
                            "bits_per_link": meta["bits_per_link"], "symbols_per_gpu": meta["symbols"],
                            "l2": "inputs+outputs (%.2f GB per step) exceed the 126 MB L2; no flush needed" % (b_alg / 1e9),
                            "sharding": "one independent graph of this shape per rank; shared model from NCCL all-reduced histograms"},
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "random_access": ra,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "random_access": ra_gpu,
                 "gpu_launches": int(launches),
                 "clocks": clocks, "verified_bit_exact": verified,
                 "aggregate": {"arcs": arcs_all, "algorithmic_bytes": bytes_all,
