@@ -129,12 +129,15 @@ int wga_decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_of
  * and their exclusive prefix sum. d_offsets[last-first+1]. */
 int wga_outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets, void* d_workspace,
                    uint64_t workspace_bytes, void* stream);
-/* End-to-end variant with HOST buffers: H2D of nothing but the request, D2H of offsets + successors. */
+/* End-to-end variant with HOST buffers (pinned memory recommended): D2H of offsets + successors.  Ranges
+ * larger than one chunk (2^20 nodes) are pipelined: chunk i is decoded while the results of chunk i-1 travel
+ * to the host and, after wga_upload(g, NULL), while the inputs of later chunks are still arriving. */
 int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t* h_offsets, uint32_t* h_succ,
                           uint64_t succ_capacity, uint64_t* h_arcs);
 
 /* Re-copies the decode inputs of the resident range (stream words, states, pointers) from the handle's
- * pinned host copy to the device: the host->device leg of an end-to-end step. */
+ * pinned host copy to the device: the host->device leg of an end-to-end step.  stream == NULL: asynchronous,
+ * in node-range chunks on a stream of the handle; the next wga_decode_range_host overlaps with it. */
 int wga_upload(wga_graph* g, void* stream);
 uint64_t wga_upload_bytes(const wga_graph* g);
 /* Per-stage device times of the last wga_decode_range (CUDA events on the caller's stream):
@@ -171,7 +174,7 @@ int wga_debug_decode_symbols(wga_graph* g, const uint8_t* h_components, uint64_t
 
 /* Kernel tuning knobs of the decode path (process-wide; the parity tests shrink them so that small graphs
  * cross span boundaries, stride the grid and take the overflow paths).  Keys: "k1_span", "k1_tpb",
- * "k2_blocks", "force_ovf", "reset". */
+ * "k2_blocks", "force_ovf", "sort_degree", "e2e_chunk", "reset". */
 int wga_debug_set_tuning(const char* key, uint64_t value);
 /* Counters of the last wga_decode_range run with tuning "stats"=1 (16 x u64; development aid). */
 void wga_debug_last_stats(uint64_t* h_out16);

@@ -32,6 +32,23 @@ def test_golden_head_full_decode(W, O, gpu, head):
     assert (off2 == head["offsets"]).all() and (succ2 == head["succ"]).all()
 
 
+def test_host_entry_point_pipelined_in_chunks(W, O, gpu, head):
+    """wga_upload(NULL) + wga_decode_range_host with small chunks: upload / decode / download overlap on three
+    streams with double-buffered chunk outputs; result identical to the one-shot decode."""
+    import ctypes as C
+    g = W.ANSBvGraph.load(head["base"])
+    try:
+        for chunk in (4096, 7000, 29999):
+            W.set_tuning(e2e_chunk=chunk)
+            for first, last in ((0, 30000), (1234, 25001)):
+                assert W.lib().wga_upload(g._h, C.c_void_p(0)) == 0
+                off, succ = g.decode_range_host(first, last)
+                assert (off == head["offsets"][first:last + 1] - head["offsets"][first]).all()
+                assert (succ == head["succ"][head["offsets"][first]:head["offsets"][last]]).all()
+    finally:
+        W.set_tuning(reset=1)
+
+
 def test_packed_tables_equal_reference_decoder_tables(W, O, gpu, head):
     """K3 parity: per slot (freq, cumul_freq, quasi_folded) == ANSModel4Decoder::new (model4decoder.rs:18-68)."""
     g = W.ANSBvGraph.load(head["base"])

@@ -18,6 +18,8 @@ void debug_expand_table(wga_graph* g, int c, void* h_out, uint64_t n_slots);
 void debug_decode_symbols(wga_graph* g, const uint8_t* h_comps, uint64_t n, uint64_t ptr, uint32_t state,
                           uint64_t* h_out, uint64_t* h_end_ptr, uint32_t* h_end_state);
 int set_tuning(const char* key, uint64_t value);
+uint64_t tuning_e2e_chunk();
+void launch_offsets_add(uint64_t* off, uint64_t n, uint64_t base, cudaStream_t st);
 void last_stats(uint64_t* out16);
 uint64_t successors_workspace_size(const wga_graph* g, uint64_t n_queries, uint64_t max_total_arcs);
 void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t n_queries, uint64_t* d_offsets,
@@ -218,11 +220,82 @@ int wga_outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offs
   });
 }
 
+// Host-buffer entry point.  Ranges larger than one chunk are pipelined: the node range is cut into chunks of
+// e2e_chunk_nodes nodes; chunk i is decoded on s_dec into one of two device buffers while the results of chunk
+// i-1 travel to the host on s_down (and, after wga_upload(g, NULL), while the inputs of later chunks are still
+// arriving on s_up).  PCIe is full duplex, so the step costs about max(download, upload + decode).
+static void decode_range_host_pipelined(wga_graph* g, uint64_t first, uint64_t last, uint64_t* h_offsets,
+                                        uint32_t* h_succ, uint64_t succ_capacity, uint64_t* h_arcs) {
+  g->ensure_pipeline();
+  const uint64_t CH = g->e2e_chunk_nodes;
+  const uint64_t N = g->prelude.number_of_nodes;
+  const double avg = N ? (double)g->prelude.number_of_arcs / (double)N : 0.0;
+  const uint64_t chunk_cap = (uint64_t)(avg * (double)CH * 1.5) + (4u << 20);
+  const uint64_t ws_bytes = decode_workspace_size(g, 0, CH) + 8 * chunk_cap;  // arena sized for the chunk buffer
+  if (g->e2e_ws_bytes < ws_bytes) {
+    if (g->e2e_ws) cudaFree(g->e2e_ws);
+    g->e2e_ws = nullptr; g->e2e_ws_bytes = 0;
+    WGA_CUDA(cudaMalloc(&g->e2e_ws, ws_bytes));
+    g->e2e_ws_bytes = ws_bytes;
+  }
+  if (g->pipe_off_n < CH + 1 || g->pipe_succ_n < chunk_cap) {
+    for (int i = 0; i < 2; ++i) {
+      if (g->pipe_off[i]) cudaFree(g->pipe_off[i]);
+      if (g->pipe_succ[i]) cudaFree(g->pipe_succ[i]);
+      g->pipe_off[i] = nullptr; g->pipe_succ[i] = nullptr;
+    }
+    g->pipe_off_n = g->pipe_succ_n = 0;
+    for (int i = 0; i < 2; ++i) {
+      WGA_CUDA(cudaMalloc((void**)&g->pipe_off[i], (CH + 1) * 8));
+      WGA_CUDA(cudaMalloc((void**)&g->pipe_succ[i], chunk_cap * 4));
+    }
+    g->pipe_off_n = CH + 1; g->pipe_succ_n = chunk_cap;
+  }
+  uint64_t base = 0;
+  int i = 0;
+  for (uint64_t a = first; a < last; a += CH, ++i) {
+    const uint64_t b = std::min(last, a + CH);
+    const int j = i & 1;
+    if (g->up_pending) {  // inputs of this chunk (and of the halo just before it) must have arrived
+      const uint64_t c1 = (b - 1 - g->res_first) / CH, c0 = a > g->res_first ? (a - 1 - g->res_first) / CH : 0;
+      for (uint64_t c = c0; c <= c1 && c < g->up_ev.size(); ++c) WGA_CUDA(cudaStreamWaitEvent(g->s_dec, g->up_ev[c], 0));
+    }
+    if (i >= 2) WGA_CUDA(cudaStreamWaitEvent(g->s_dec, g->down_done[j], 0));  // buffer j is free again
+    uint64_t arcs = 0;
+    decode_range(g, a, b, g->pipe_off[j], g->pipe_succ[j], g->pipe_succ_n, g->e2e_ws, g->e2e_ws_bytes, &arcs, g->s_dec);
+    if (base + arcs > succ_capacity && h_succ)
+      throw Error(WGA_E_WORKSPACE, "h_succ too small: need more than " + std::to_string(base + arcs) + " elements");
+    launch_offsets_add(g->pipe_off[j], b - a + 1, base, g->s_dec);
+    WGA_CUDA(cudaEventRecord(g->dec_done[j], g->s_dec));
+    WGA_CUDA(cudaStreamWaitEvent(g->s_down, g->dec_done[j], 0));
+    // offsets: the last entry of a chunk equals the first of the next one
+    WGA_CUDA(cudaMemcpyAsync(h_offsets + (a - first), g->pipe_off[j], (b - a + (b == last ? 1 : 0)) * 8,
+                             cudaMemcpyDeviceToHost, g->s_down));
+    if (arcs && h_succ)
+      WGA_CUDA(cudaMemcpyAsync(h_succ + base, g->pipe_succ[j], arcs * 4, cudaMemcpyDeviceToHost, g->s_down));
+    WGA_CUDA(cudaEventRecord(g->down_done[j], g->s_down));
+    base += arcs;
+  }
+  WGA_CUDA(cudaStreamSynchronize(g->s_down));
+  g->up_pending = false;
+  if (h_arcs) *h_arcs = base;
+}
+
 int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t* h_offsets, uint32_t* h_succ,
                           uint64_t succ_capacity, uint64_t* h_arcs) {
   return guarded([&] {
     if (!g || !h_offsets) throw Error(WGA_E_ARG, "null argument");
     if (!g->on_device) throw Error(WGA_E_CUDA, "graph was opened host-only");
+    if (first > last || last > g->res_last || first < g->res_first) throw Error(WGA_E_ARG, "range outside the resident nodes");
+    g->e2e_chunk_nodes = std::max<uint64_t>(1, tuning_e2e_chunk());
+    if (last - first > g->e2e_chunk_nodes) {
+      decode_range_host_pipelined(g, first, last, h_offsets, h_succ, succ_capacity, h_arcs);
+      return;
+    }
+    if (g->up_pending) {  // a chunked upload is in flight: wait for it
+      WGA_CUDA(cudaStreamSynchronize(g->s_up));
+      g->up_pending = false;
+    }
     // grow-only device buffers owned by the handle: no allocation on the steady-state path
     uint64_t ws_bytes = decode_workspace_size(g, first, last);
     if (g->e2e_ws_bytes < ws_bytes) {
@@ -254,10 +327,13 @@ int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t*
   });
 }
 
+// stream == NULL: chunked upload on the handle's own stream, overlapped by a following wga_decode_range_host
 int wga_upload(wga_graph* g, void* stream) {
   return guarded([&] {
     if (!g) throw Error(WGA_E_ARG, "null argument");
-    g->reupload((cudaStream_t)stream);
+    g->e2e_chunk_nodes = std::max<uint64_t>(1, tuning_e2e_chunk());
+    if (stream) g->reupload((cudaStream_t)stream);
+    else g->reupload_chunked();
   });
 }
 

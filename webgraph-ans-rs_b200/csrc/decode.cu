@@ -36,6 +36,7 @@ struct Tuning {
   uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
                               // equal chunk of the level, so a partial second wave would double the time
   uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
+  uint32_t e2e_chunk = 1u << 20;  // nodes per chunk of the pipelined host entry point
   uint32_t sort_degree = 0;   // K2: 1 = sort key includes the degree bucket; 0 = level only, node order kept
                               // (measured: locality of neighbouring nodes beats equal loop lengths, 2.9 vs 6.6 ms)
 };
@@ -48,10 +49,12 @@ int set_tuning(const char* key, uint64_t value) {
   else if (k == "k2_blocks") g_tuning.k2_blocks = (uint32_t)value;
   else if (k == "force_ovf") g_tuning.force_ovf = (uint32_t)value;
   else if (k == "sort_degree") g_tuning.sort_degree = (uint32_t)value;
+  else if (k == "e2e_chunk") g_tuning.e2e_chunk = (uint32_t)value;
   else if (k == "reset") g_tuning = Tuning();
   else return WGA_E_ARG;
   return WGA_OK;
 }
+uint64_t tuning_e2e_chunk() { return g_tuning.e2e_chunk; }
 void last_stats(uint64_t* out16) { for (int i = 0; i < 16; ++i) out16[i] = 0; }
 
 namespace {
@@ -733,6 +736,11 @@ __global__ void k_offsets_rebase(const uint64_t* src, uint64_t base, uint64_t* d
   if (i < n) dst[i] = src[i] - base;
 }
 
+__global__ void k_offsets_add(uint64_t* off, uint64_t n, uint64_t base) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) off[i] += base;
+}
+
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 // Scalars at the head of the workspace (one 256-byte line, cleared per call).
@@ -1141,6 +1149,12 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   WGA_CUDA(cudaGetLastError());
   if (arcs > succ_capacity) throw Error(WGA_E_WORKSPACE, "d_succ too small: need " + std::to_string(arcs) + " elements");
   if (h_arcs) *h_arcs = arcs;
+}
+
+void launch_offsets_add(uint64_t* off, uint64_t n, uint64_t base, cudaStream_t st) {
+  if (!base || !n) return;
+  k_offsets_add<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(off, n, base);
+  count_launch();
 }
 
 void debug_expand_table(wga_graph* g, int c, void* h_out, uint64_t n_slots) {

@@ -83,12 +83,72 @@ wga_graph::~wga_graph() {
     if (e2e_ws) cudaFree(e2e_ws);
     if (e2e_off) cudaFree(e2e_off);
     if (e2e_succ) cudaFree(e2e_succ);
+    for (int i = 0; i < 2; ++i) {
+      if (pipe_off[i]) cudaFree(pipe_off[i]);
+      if (pipe_succ[i]) cudaFree(pipe_succ[i]);
+      if (dec_done[i]) cudaEventDestroy(dec_done[i]);
+      if (down_done[i]) cudaEventDestroy(down_done[i]);
+    }
+    for (auto& e : up_ev) if (e) cudaEventDestroy(e);
+    if (s_up) cudaStreamDestroy(s_up);
+    if (s_dec) cudaStreamDestroy(s_dec);
+    if (s_down) cudaStreamDestroy(s_down);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (pinned) {
       if (!prelude.stream.empty()) cudaHostUnregister(prelude.stream.data());
       if (!phases.states.empty()) cudaHostUnregister(phases.states.data());
       if (!phases.pointers.empty()) cudaHostUnregister(phases.pointers.data());
     }
+  }
+}
+
+void wga_graph::ensure_pipeline() {
+  if (s_up) return;
+  WGA_CUDA(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
+  WGA_CUDA(cudaStreamCreateWithFlags(&s_dec, cudaStreamNonBlocking));
+  WGA_CUDA(cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    WGA_CUDA(cudaEventCreateWithFlags(&dec_done[i], cudaEventDisableTiming));
+    WGA_CUDA(cudaEventCreateWithFlags(&down_done[i], cudaEventDisableTiming));
+  }
+}
+
+// Same bytes as reupload(), but in node-range chunks (lowest nodes first) on the handle's upload stream, with
+// one event per chunk, so that wga_decode_range_host can start on chunk 0 while the rest is still in flight.
+void wga_graph::reupload_chunked() {
+  if (!on_device) throw Error(WGA_E_CUDA, "graph was opened host-only");
+  ensure_pipeline();
+  reupload_pin();
+  const uint64_t N = prelude.number_of_nodes;
+  const uint64_t n_res = res_last - res_first;
+  const uint64_t nchunks = (n_res + e2e_chunk_nodes - 1) / e2e_chunk_nodes;
+  while (up_ev.size() < nchunks) {
+    cudaEvent_t e;
+    WGA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    up_ev.push_back(e);
+  }
+  for (uint64_t c = 0; c < nchunks; ++c) {
+    const uint64_t a = res_first + c * e2e_chunk_nodes, b = std::min(res_last, a + e2e_chunk_nodes);
+    // node v: file entry N-1-v, device entry res_last-1-v ; its record = stream words [ptr(v+1), ptr(v))
+    const uint64_t w_hi = phases.pointers[N - 1 - a], w_lo = b < N ? phases.pointers[N - 1 - b] : 0;
+    if (w_hi > w_lo)
+      WGA_CUDA(cudaMemcpyAsync(d_stream + (w_lo - stream_base), prelude.stream.data() + w_lo, (w_hi - w_lo) * 2,
+                               cudaMemcpyHostToDevice, s_up));
+    WGA_CUDA(cudaMemcpyAsync(d_states + (res_last - b), phases.states.data() + (N - b), (b - a) * 4, cudaMemcpyHostToDevice, s_up));
+    WGA_CUDA(cudaMemcpyAsync(d_ptrs + (res_last - b), phases.pointers.data() + (N - b), (b - a) * 8, cudaMemcpyHostToDevice, s_up));
+    WGA_CUDA(cudaEventRecord(up_ev[c], s_up));
+  }
+  up_pending = true;
+}
+
+void wga_graph::reupload_pin() {
+  if (!pinned) {  // pin the host copies once so the copies run at full PCIe speed
+    bool ok = true;
+    if (!prelude.stream.empty()) ok &= cudaHostRegister(prelude.stream.data(), prelude.stream.size() * 2, cudaHostRegisterDefault) == cudaSuccess;
+    if (!phases.states.empty()) ok &= cudaHostRegister(phases.states.data(), phases.states.size() * 4, cudaHostRegisterDefault) == cudaSuccess;
+    if (!phases.pointers.empty()) ok &= cudaHostRegister(phases.pointers.data(), phases.pointers.size() * 8, cudaHostRegisterDefault) == cudaSuccess;
+    cudaGetLastError();
+    pinned = ok;
   }
 }
 

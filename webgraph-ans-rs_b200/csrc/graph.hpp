@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <vector>
 
 #include "common.hpp"
 #include "device.cuh"
@@ -49,6 +50,18 @@ struct wga_graph {
   void* e2e_ws = nullptr; uint64_t e2e_ws_bytes = 0;
   uint64_t* e2e_off = nullptr; uint64_t e2e_off_n = 0;
   uint32_t* e2e_succ = nullptr; uint64_t e2e_succ_n = 0;
+  // pipelined host entry point (wga_decode_range_host): node-range chunks flow through upload -> decode ->
+  // download on three streams with double-buffered chunk outputs
+  uint64_t e2e_chunk_nodes = 1ull << 20;   // tuning knob "e2e_chunk" (tests shrink it)
+  cudaStream_t s_up = nullptr, s_dec = nullptr, s_down = nullptr;
+  std::vector<cudaEvent_t> up_ev;   // one per upload chunk (chunk c = nodes [res_first + c*CHUNK, ...))
+  bool up_pending = false;          // the events above belong to an upload that has not been consumed yet
+  cudaEvent_t dec_done[2] = {}, down_done[2] = {};
+  uint64_t* pipe_off[2] = {}; uint64_t pipe_off_n = 0;
+  uint32_t* pipe_succ[2] = {}; uint64_t pipe_succ_n = 0;
+  void ensure_pipeline();
+  void reupload_chunked();          // H2D in node-range chunks on s_up, one event per chunk
+  void reupload_pin();
 
   ~wga_graph();
   void upload();
