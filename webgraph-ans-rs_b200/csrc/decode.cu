@@ -736,6 +736,17 @@ __global__ void k_offsets_rebase(const uint64_t* src, uint64_t base, uint64_t* d
   if (i < n) dst[i] = src[i] - base;
 }
 
+// scalars the host needs after a decode -> mapped host memory (no DMA copy: see wga_graph::h_pub)
+__global__ void k_publish(const uint64_t* tot0, const uint64_t* tot1, const uint32_t* maxlevel, const uint32_t* err,
+                          uint64_t* pub) {
+  if (threadIdx.x == 0) {
+    pub[1] = *tot0;
+    pub[2] = *tot1;
+    pub[3] = *maxlevel;
+    pub[4] = *err;
+  }
+}
+
 __global__ void k_offsets_add(uint64_t* off, uint64_t n, uint64_t base) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) off[i] += base;
@@ -902,12 +913,14 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
   mark(g, st);  // 4: resolve done
   // ---- totals, deepest level, error word
   uint32_t maxlevel = 0, herr = 0;
-  WGA_CUDA(cudaMemcpyAsync(&tot[0], rv.offs + rv.h, 8, cudaMemcpyDeviceToHost, st));
-  WGA_CUDA(cudaMemcpyAsync(&tot[1], rv.offs + n, 8, cudaMemcpyDeviceToHost, st));
-  WGA_CUDA(cudaMemcpyAsync(&maxlevel, &sc->maxlevel, 4, cudaMemcpyDeviceToHost, st));
-  WGA_CUDA(cudaMemcpyAsync(&herr, g->d_err, 4, cudaMemcpyDeviceToHost, st));
+  k_publish<<<1, 32, 0, st>>>(rv.offs + rv.h, rv.offs + n, &sc->maxlevel, g->d_err, g->d_pub);
+  count_launch();
   WGA_CUDA(cudaStreamSynchronize(st));
   WGA_CUDA(cudaGetLastError());
+  tot[0] = g->h_pub[1];
+  tot[1] = g->h_pub[2];
+  maxlevel = (uint32_t)g->h_pub[3];
+  herr = (uint32_t)g->h_pub[4];
   if (tot[0] > rv.halo_cap) {
     if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
     throw Error(WGA_E_WORKSPACE, "halo successors exceed the workspace");
@@ -964,10 +977,10 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   // ---- halo
   uint64_t lo = first;
   if (first > g->res_first && g->prelude.compression_window != 0) {
-    k_halo<<<1, 32, 0, st>>>(g->dev, first, last, &sc->lo, g->d_err);
+    k_halo<<<1, 32, 0, st>>>(g->dev, first, last, g->d_pub, g->d_err);
     count_launch();
-    WGA_CUDA(cudaMemcpyAsync(&lo, &sc->lo, 8, cudaMemcpyDeviceToHost, st));
     WGA_CUDA(cudaStreamSynchronize(st));
+    lo = g->h_pub[0];
     if (lo < g->res_first) throw Error(WGA_E_ARG, "reference chain leaves the resident shard");
   }
   const uint64_t n = last - lo;

@@ -80,6 +80,7 @@ wga_graph::~wga_graph() {
     cudaFree(d_lut);
     cudaFree(d_ent);
     cudaFree(d_err);
+    if (h_pub) cudaFreeHost((void*)h_pub);
     if (e2e_ws) cudaFree(e2e_ws);
     if (e2e_off) cudaFree(e2e_off);
     if (e2e_succ) cudaFree(e2e_succ);
@@ -208,6 +209,14 @@ void wga_graph::upload() {
   WGA_CUDA(cudaMemcpy(d_ent, packed.ent.data(), packed.ent.size() * 8, cudaMemcpyHostToDevice));
   WGA_CUDA(cudaMalloc(&d_err, 4));
   WGA_CUDA(cudaMemset(d_err, 0, 4));
+  {
+    void* hp = nullptr;
+    WGA_CUDA(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+    h_pub = (volatile uint64_t*)hp;
+    void* dp = nullptr;
+    WGA_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+    d_pub = (uint64_t*)dp;
+  }
   on_device = true;
 
   this->dev.tb.lut = d_lut;

@@ -38,6 +38,10 @@ struct wga_graph {
   uint16_t* d_lut = nullptr;
   uint2* d_ent = nullptr;
   uint32_t* d_err = nullptr;  // device error word
+  // 64 bytes of mapped pinned host memory: kernels publish the scalars the host needs (halo start, arc totals,
+  // deepest level, error word) there, so reading them never queues behind a bulk copy on a DMA engine
+  volatile uint64_t* h_pub = nullptr;
+  uint64_t* d_pub = nullptr;
   wga::DevGraph dev{};         // view passed to kernels
   uint64_t pointers_payload_bytes = 0;
   bool pinned = false;          // host copies registered with cudaHostRegister (fast re-upload)
