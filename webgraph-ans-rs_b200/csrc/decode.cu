@@ -212,7 +212,7 @@ __global__ void k_halo(DevGraph g, uint64_t first, uint64_t last, uint64_t* lo_o
 
 // -------------------------------------------------------------------------------------------- K1
 // Pseudo components of the per-lane state machine (0..8 are the BVGraphComponent values, mod.rs:46-61).
-enum : uint32_t { C_AFTER_BLOCKS = 9, C_FINISH = 10, C_FETCH = 11, C_IDLE = 12, C_FAIL = 13 };
+enum : uint32_t { C_AFTER_BLOCKS = 9, C_FINISH = 10, C_FETCH = 11, C_IDLE = 12 };
 
 // Moves the header of a node (kb block lengths, kp interval pairs already parked in the slot) to a
 // record in the overflow arena.  Returns false when the arena is full.
@@ -245,20 +245,6 @@ __device__ __forceinline__ bool header_to_arena(const RangeView& rv, const uint3
   return ok;
 }
 
-// The K1 record of a finished node (see M_*).
-__device__ __forceinline__ uint64_t finish_meta(const RangeView& rv, bool direct, bool ovf, uint32_t ao, uint32_t r,
-                                                uint32_t b, uint32_t ni, uint32_t nres) {
-  if (direct) return M_DIRECT;
-  if (ovf) {
-    rv.arena[ao + 1] = ni;
-    rv.arena[ao + 2] = nres;
-    return (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
-  }
-  return (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
-}
-
-constexpr int BURST_MIN = 6;  // lanes that must be in the same high-volume state for a burst to pay off
-
 __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint32_t span, uint32_t force_ovf) {
   __shared__ uint32_t s_next;
   __shared__ uint4 s_cp[WGA_COMPONENTS];
@@ -284,7 +270,6 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
   uint32_t* slot = nullptr;
   uint32_t* wp = nullptr;
   bool ovf = false, direct = false;
-  uint32_t burst_err = 0;
 
   // Every lane stays in the loop until the whole warp has run out of nodes: the vote at the top is the
   // per-iteration reconvergence point, so that the symbol decode below runs with all busy lanes together.
@@ -433,61 +418,18 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
         rv.meta[t] = M_DIRECT;
         c = C_FETCH;
       } else if (c == C_FINISH) {
-        rv.meta[t] = finish_meta(rv, direct, ovf, ao, r, b, ni, nres);
+        uint64_t m;
+        if (direct) m = M_DIRECT;
+        else if (ovf) {
+          rv.arena[ao + 1] = ni;
+          rv.arena[ao + 2] = nres;
+          m = (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
+        } else {
+          m = (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
+        }
+        rv.meta[t] = m;
         c = C_FETCH;
       }
-    }
-    // ---- bursts.  Residual gaps and copy-block lengths are 58 % of all symbols and their transition is
-    // trivial, while one pass through the general state machine above costs the sum of all nine case bodies.
-    // So while enough lanes of the warp sit in one of these two states, they decode in a tight loop of their
-    // own (the other lanes wait); a lane leaves the burst when its run ends.
-    while (__popc(__ballot_sync(FULL, c == Residual)) >= BURST_MIN) {
-      if (c == Residual) {
-        uint32_t e2 = 0;
-        const uint64_t x = ans_decode_cp(s_cp[Residual], lut, ent, state, ptr, g.stream, e2);
-        prev = prev + 1 + (int64_t)(uint32_t)x;
-        if ((x >> 32) != 0 || prev > 0xFFFFFFFEll) e2 |= ERR_SYMBOL_WIDTH;
-        if (e2) { burst_err = e2; c = C_FAIL; }
-        else {
-          *wp++ = (uint32_t)prev;
-          if (--extras == 0) c = C_FINISH;
-        }
-      }
-    }
-    while (__popc(__ballot_sync(FULL, c == Blocks)) >= BURST_MIN) {
-      if (c == Blocks) {
-        uint32_t e2 = 0;
-        const uint64_t x = ans_decode_cp(s_cp[Blocks], lut, ent, state, ptr, g.stream, e2);
-        const uint32_t xl = (uint32_t)x, len = xl + (k != 0);
-        if ((x >> 32) != 0 || len > dref - pos || len < xl) e2 |= ERR_CORRUPT;
-        if (e2) { burst_err = e2; c = C_FAIL; }
-        else {
-          if (ovf) rv.arena[ao + 4 + k] = len;
-          else reinterpret_cast<uint16_t*>(slot)[k] = (uint16_t)len;
-          if ((k & 1) == 0) copied += len;
-          pos += len;
-          if (++k == b) {
-            if ((b & 1) == 0) copied += dref - pos;
-            c = C_AFTER_BLOCKS;
-          }
-        }
-      }
-    }
-    // states a burst can leave behind: handled here so that the next pass starts from a regular state
-    if (c == C_AFTER_BLOCKS) {
-      if (copied > d) { burst_err = ERR_CORRUPT; c = C_FAIL; }
-      else {
-        extras = d - copied;
-        c = extras ? c_extras : (uint32_t)C_FINISH;
-      }
-    }
-    if (c == C_FAIL) {
-      atomicOr(rv.err, burst_err);
-      rv.meta[t] = M_DIRECT;
-      c = C_FETCH;
-    } else if (c == C_FINISH) {
-      rv.meta[t] = finish_meta(rv, direct, ovf, ao, r, b, ni, nres);
-      c = C_FETCH;
     }
   }
 }
