@@ -130,7 +130,7 @@ int wga_decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_of
 int wga_outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets, void* d_workspace,
                    uint64_t workspace_bytes, void* stream);
 /* End-to-end variant with HOST buffers (pinned memory recommended): D2H of offsets + successors.  Ranges
- * larger than one chunk (2^20 nodes) are pipelined: chunk i is decoded while the results of chunk i-1 travel
+ * larger than one chunk (2^19 nodes) are pipelined: chunk i is decoded while the results of chunk i-1 travel
  * to the host and, after wga_upload(g, NULL), while the inputs of later chunks are still arriving. */
 int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t* h_offsets, uint32_t* h_succ,
                           uint64_t succ_capacity, uint64_t* h_arcs);

@@ -36,7 +36,7 @@ struct Tuning {
   uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
                               // equal chunk of the level, so a partial second wave would double the time
   uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
-  uint32_t e2e_chunk = 1u << 20;  // nodes per chunk of the pipelined host entry point
+  uint32_t e2e_chunk = 1u << 19;  // nodes per chunk of the pipelined host entry point (swept: 31.6 ms at 2^19)
   uint32_t sort_degree = 0;   // K2: 1 = sort key includes the degree bucket; 0 = level only, node order kept
                               // (measured: locality of neighbouring nodes beats equal loop lengths, 2.9 vs 6.6 ms)
 };

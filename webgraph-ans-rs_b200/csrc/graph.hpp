@@ -56,7 +56,7 @@ struct wga_graph {
   uint32_t* e2e_succ = nullptr; uint64_t e2e_succ_n = 0;
   // pipelined host entry point (wga_decode_range_host): node-range chunks flow through upload -> decode ->
   // download on three streams with double-buffered chunk outputs
-  uint64_t e2e_chunk_nodes = 1ull << 20;   // tuning knob "e2e_chunk" (tests shrink it)
+  uint64_t e2e_chunk_nodes = 1ull << 19;   // tuning knob "e2e_chunk" (tests shrink it)
   cudaStream_t s_up = nullptr, s_dec = nullptr, s_down = nullptr;
   std::vector<cudaEvent_t> up_ev;   // one per upload chunk (chunk c = nodes [res_first + c*CHUNK, ...))
   bool up_pending = false;          // the events above belong to an upload that has not been consumed yet
