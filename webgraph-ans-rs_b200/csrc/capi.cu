@@ -288,7 +288,8 @@ int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t*
     if (!g->on_device) throw Error(WGA_E_CUDA, "graph was opened host-only");
     if (first > last || last > g->res_last || first < g->res_first) throw Error(WGA_E_ARG, "range outside the resident nodes");
     g->e2e_chunk_nodes = std::max<uint64_t>(1, tuning_e2e_chunk());
-    if (last - first > g->e2e_chunk_nodes) {
+    // chunks only pay off when no record is long enough to dominate a chunk (see wga_graph::longest_record)
+    if (last - first > g->e2e_chunk_nodes && g->longest_record() < 8192) {
       decode_range_host_pipelined(g, first, last, h_offsets, h_succ, succ_capacity, h_arcs);
       return;
     }
@@ -333,7 +334,8 @@ int wga_upload(wga_graph* g, void* stream) {
     if (!g) throw Error(WGA_E_ARG, "null argument");
     g->e2e_chunk_nodes = std::max<uint64_t>(1, tuning_e2e_chunk());
     if (stream) g->reupload((cudaStream_t)stream);
-    else g->reupload_chunked();
+    else if (g->longest_record() < 8192) g->reupload_chunked();
+    else g->reupload(0);
   });
 }
 

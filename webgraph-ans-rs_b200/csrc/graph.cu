@@ -103,6 +103,22 @@ wga_graph::~wga_graph() {
   }
 }
 
+// A record is one serial ANS chain (one lane decodes it symbol by symbol), so its length bounds the decode
+// time of any range that contains it.  The pipelined host entry point uses this to decide whether cutting
+// the range into chunks pays off (every chunk would wait for its own longest record).
+uint64_t wga_graph::longest_record() {
+  if (max_record_words == UINT64_MAX) {
+    const uint64_t N = prelude.number_of_nodes;
+    uint64_t mx = 0;
+    for (uint64_t v = res_first; v < res_last; ++v) {
+      const uint64_t hi = phases.pointers[N - 1 - v], lo = v + 1 < N ? phases.pointers[N - 2 - v] : 0;
+      if (hi - lo > mx) mx = hi - lo;
+    }
+    max_record_words = mx;
+  }
+  return max_record_words;
+}
+
 void wga_graph::ensure_pipeline() {
   if (s_up) return;
   WGA_CUDA(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));

@@ -63,6 +63,8 @@ struct wga_graph {
   cudaEvent_t dec_done[2] = {}, down_done[2] = {};
   uint64_t* pipe_off[2] = {}; uint64_t pipe_off_n = 0;
   uint32_t* pipe_succ[2] = {}; uint64_t pipe_succ_n = 0;
+  uint64_t max_record_words = UINT64_MAX;  // largest record of the resident range in stream words (lazy)
+  uint64_t longest_record();
   void ensure_pipeline();
   void reupload_chunked();          // H2D in node-range chunks on s_up, one event per chunk
   void reupload_pin();
