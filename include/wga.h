@@ -176,8 +176,6 @@ int wga_debug_decode_symbols(wga_graph* g, const uint8_t* h_components, uint64_t
  * cross span boundaries, stride the grid and take the overflow paths).  Keys: "k1_span", "k1_tpb",
  * "k2_blocks", "force_ovf", "sort_degree", "e2e_chunk", "reset". */
 int wga_debug_set_tuning(const char* key, uint64_t value);
-/* Counters of the last wga_decode_range run with tuning "stats"=1 (16 x u64; development aid). */
-void wga_debug_last_stats(uint64_t* h_out16);
 
 /* ---------------------------------------------------------------- model build -------------------- */
 /* ANSModel4EncoderBuilder (src/ans/model4encoder_builder.rs:39-56) with device-resident histograms. */

@@ -20,7 +20,6 @@ void debug_decode_symbols(wga_graph* g, const uint8_t* h_comps, uint64_t n, uint
 int set_tuning(const char* key, uint64_t value);
 uint64_t tuning_e2e_chunk();
 void launch_offsets_add(uint64_t* off, uint64_t n, uint64_t base, cudaStream_t st);
-void last_stats(uint64_t* out16);
 uint64_t successors_workspace_size(const wga_graph* g, uint64_t n_queries, uint64_t max_total_arcs);
 void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t n_queries, uint64_t* d_offsets,
                       uint32_t* d_succ, uint64_t succ_capacity, void* ws, uint64_t ws_bytes, uint64_t* h_arcs,
@@ -393,8 +392,6 @@ int wga_debug_set_tuning(const char* key, uint64_t value) {
   if (rc != WGA_OK) set_last_error("unknown tuning key");
   return rc;
 }
-
-void wga_debug_last_stats(uint64_t* h_out16) { last_stats(h_out16); }
 
 // ----------------------------------------------------------------------------------------- model
 int wga_model_create(wga_model** out) {

@@ -55,7 +55,6 @@ int set_tuning(const char* key, uint64_t value) {
   return WGA_OK;
 }
 uint64_t tuning_e2e_chunk() { return g_tuning.e2e_chunk; }
-void last_stats(uint64_t* out16) { for (int i = 0; i < 16; ++i) out16[i] = 0; }
 
 namespace {
 
@@ -245,6 +244,16 @@ __device__ __forceinline__ bool header_to_arena(const RangeView& rv, const uint3
   return ok;
 }
 
+// node + nat2int(x) in 32-bit arithmetic (ids are < 2^32, so a valid x is < 2^33); false on leaving [0, 2^32-2]
+__device__ __forceinline__ bool add_nat(uint32_t v, uint64_t x, uint32_t& out) {
+  const uint32_t half = (uint32_t)(x >> 1);
+  const bool neg = (x & 1) != 0;
+  out = neg ? v - half - 1u : v + half;
+  return (x >> 33) == 0 && (neg ? half < v : (out >= v && out != 0xFFFFFFFFu));
+}
+
+// LIST: node t is rv.nodes[t] (random access) instead of rv.lo + t.
+template <bool LIST>
 __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint32_t span, uint32_t force_ovf) {
   __shared__ uint32_t s_next;
   __shared__ uint4 s_cp[WGA_COMPONENTS];
@@ -262,26 +271,34 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
   const uint32_t c_extras = g.min_interval ? (uint32_t)IntervalCount : (uint32_t)FirstResidual;
   const uint32_t minint = g.min_interval;
   const uint32_t window = g.window;
+  // slot of node t = base + offs[t] (spans never straddle the halo boundary)
+  uint32_t* const slot_base = A < rv.h ? rv.halo_succ : rv.succ - rv.offs[rv.h];
+  // phases of node v: states[top - v], ptrs[top - v] (file order is reversed, bvgraph_decoder_factory.rs:49-50)
+  const uint32_t* const states_top = g.states + g.top;
+  const uint64_t* const ptrs_top = g.ptrs + g.top;
+  const uint32_t lo32 = (uint32_t)rv.lo;
 
   // per-lane record state
-  uint32_t c = C_FETCH, t = 0, state = 0, d = 0, r = 0, dref = 0, b = 0, k = 0, copied = 0, pos = 0, extras = 0,
-           ni = 0, hb = 0, nres = 0, ao = 0, apo = 0;
-  int64_t ptr = 0, v = 0, prev = 0;
+  uint32_t c = C_FETCH, t = 0, state = 0, sp = 0, v = 0, prev = 0, d = 0, r = 0, dref = 0, b = 0, k = 0, copied = 0,
+           pos = 0, extras = 0, ni = 0, hb = 0, nres = 0, ao = 0, apo = 0;
   uint32_t* slot = nullptr;
   uint32_t* wp = nullptr;
   bool ovf = false, direct = false;
 
   // Every lane stays in the loop until the whole warp has run out of nodes: the vote at the top is the
   // per-iteration reconvergence point, so that the symbol decode below runs with all busy lanes together.
-  // Each case computes a `bad` flag instead of leaving early, which keeps the cases short and single-exit.
+  // Each case computes an error flag instead of leaving early, which keeps the cases short and single-exit.
   for (;;) {
     uint32_t err = 0;
     if (c == C_FETCH) {
       t = atomicAdd(&s_next, 1u);
       if (t >= Bn) c = C_IDLE;
       else {
-        v = (int64_t)node_of(rv, t);
-        load_phase(g, (uint64_t)v, state, ptr, err);
+        v = LIST ? rv.nodes[t] : lo32 + t;
+        state = *(states_top - v);
+        const uint64_t p = *(ptrs_top - v) - g.stream_base;
+        if (p > g.stream_words) err = ERR_CORRUPT;
+        sp = (uint32_t)p;  // the resident span has < 2^32 words (checked at upload)
         c = Outdegree;
         r = b = ni = copied = hb = nres = 0;
         ovf = direct = false;
@@ -289,14 +306,14 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
     }
     if (__all_sync(FULL, c == C_IDLE)) break;
     if (c <= Residual) {
-      const uint64_t x = ans_decode_cp(s_cp[c], lut, ent, state, ptr, g.stream, err);
+      const uint64_t x = ans_decode_cp(s_cp[c], lut, ent, state, sp, g.stream, err);
       const uint32_t xl = (uint32_t)x;
-      const bool wide = (x >> 32) != 0;  // no component value of a valid record needs more than 32 bits
-      if (wide && !err) err = ERR_SYMBOL_WIDTH;  // (nat2int arguments: ids < 2^32 give x < 2^33, checked below)
+      const bool wide = (x >> 32) != 0;  // only nat2int arguments (first residual / interval start) may need 33 bits
       if (c >= FirstResidual) {
         // ---- residuals: value = node + nat2int(x) | previous + 1 + x   (most frequent symbols)
+        uint32_t val;
+        bool ok;
         if (c == FirstResidual) {
-          if (err == ERR_SYMBOL_WIDTH && x <= 0x1FFFFFFFFull) err = 0;
           nres = extras;
           direct = (r == 0 && ni == 0);
           if (!direct && !ovf && (nres >= MAX_NRES || hb + 2ull * ni > (uint64_t)(d - nres))) {
@@ -304,18 +321,20 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
             else err |= ERR_WORKSPACE;
           }
           wp = slot + (d - nres);
-          prev = v + nat2int(x);
+          ok = add_nat(v, x, val);
         } else {
-          prev = prev + 1 + (int64_t)xl;
+          val = prev + 1u + xl;
+          ok = !wide && val > prev && val != 0xFFFFFFFFu;
         }
-        if (prev < 0 || prev > 0xFFFFFFFEll) err |= ERR_SYMBOL_WIDTH;
+        if (!ok) err |= ERR_SYMBOL_WIDTH;
         if (!err) {
-          *wp++ = (uint32_t)prev;
+          prev = val;
+          *wp++ = val;
           c = --extras ? (uint32_t)Residual : (uint32_t)C_FINISH;
         }
       } else if (c == Blocks) {
         const uint32_t len = xl + (k != 0);
-        if (len > dref - pos || len < xl) err |= ERR_CORRUPT;
+        if (wide || len > dref - pos || len < xl) err |= ERR_CORRUPT;
         if (!err) {
           if (ovf) rv.arena[ao + 4 + k] = len;
           else reinterpret_cast<uint16_t*>(slot)[k] = (uint16_t)len;
@@ -328,51 +347,56 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
         }
       } else if (c >= IntervalStart) {
         if (c == IntervalStart) {
-          if (err == ERR_SYMBOL_WIDTH && x <= 0x1FFFFFFFFull) err = 0;
-          prev = k == 0 ? v + nat2int(x) : prev + 1 + (int64_t)x;  // prev: start of this interval
-          if (prev < 0 || prev > 0xFFFFFFFEll) err |= ERR_SYMBOL_WIDTH;
+          uint32_t val;
+          bool ok;
+          if (k == 0) ok = add_nat(v, x, val);
+          else { val = prev + 1u + xl; ok = !wide && val > prev && val != 0xFFFFFFFFu; }  // prev: end of the last one
+          if (!ok) err |= ERR_SYMBOL_WIDTH;
           if (!err) {
-            if (ovf) rv.arena[apo + 2 * k] = (uint32_t)prev;
-            else slot[hb + 2 * k] = (uint32_t)prev;
+            prev = val;  // start of this interval
+            if (ovf) rv.arena[apo + 2 * k] = val;
+            else slot[hb + 2 * k] = val;
             c = IntervalLen;
           }
         } else {
-          const uint64_t len = (uint64_t)xl + minint;
-          if (len > extras || len == 0) err |= ERR_CORRUPT;
-          prev += (int64_t)len;  // prev: one past the end of this interval
-          if (prev > 0xFFFFFFFFll) err |= ERR_SYMBOL_WIDTH;
+          const uint32_t len = xl + minint;
+          if (wide || len < xl || len > extras || len == 0) err |= ERR_CORRUPT;
+          const uint32_t end = prev + len;  // one past the end of this interval
+          if (end < prev) err |= ERR_SYMBOL_WIDTH;
           if (!err) {
-            if (ovf) rv.arena[apo + 2 * k + 1] = (uint32_t)len;
-            else slot[hb + 2 * k + 1] = (uint32_t)len;
-            extras -= (uint32_t)len;
+            prev = end;
+            if (ovf) rv.arena[apo + 2 * k + 1] = len;
+            else slot[hb + 2 * k + 1] = len;
+            extras -= len;
             if (++k == ni) c = extras ? (uint32_t)FirstResidual : (uint32_t)C_FINISH;
             else c = IntervalStart;
           }
         }
       } else if (c == Outdegree) {
+        if (wide) err |= ERR_SYMBOL_WIDTH;
         d = xl;
         extras = d;
         if (!err) {
           if (d == 0) { direct = true; c = C_FINISH; }
           else {
-            slot = node_slot(rv, t);
+            slot = slot_base + rv.offs[t];
             c = window ? (uint32_t)ReferenceOffset : c_extras;
           }
         }
       } else if (c == ReferenceOffset) {
-        uint32_t ri = t;
-        if (xl > window) err |= ERR_CORRUPT;
-        else if (xl) {
-          ri = ref_index(rv, t, xl);
+        uint32_t ri = t - xl;
+        if (wide || xl > window) err |= ERR_CORRUPT;
+        else if (LIST) {
+          if (xl) ri = ref_index(rv, t, xl);
           if (ri == NOT_FOUND) err |= ERR_RANGE;  // the referenced node is not part of this decode
-        }
+        } else if (xl > t) err |= ERR_RANGE;
         if (!err) {
           r = xl;
           if (r == 0) c = c_extras;
           else { dref = rv.outdeg[ri]; c = BlockCount; }
         }
       } else if (c == BlockCount) {
-        if (x > (uint64_t)dref + 1) err |= ERR_CORRUPT;
+        if (wide || (xl > dref && xl - dref > 1u)) err |= ERR_CORRUPT;  // at most dref + 1 blocks
         if (!err) {
           b = xl;
           hb = (b + 1) >> 1;
@@ -388,7 +412,7 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
           }
         }
       } else {  // IntervalCount
-        if (xl > extras) err |= ERR_CORRUPT;
+        if (wide || xl > extras) err |= ERR_CORRUPT;
         if (!err) {
           ni = xl;
           k = 0;
@@ -883,7 +907,8 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
     uint32_t span = tn.k1_span ? tn.k1_span : 1;
     // small ranges: shrink the spans so that the grid still fills the machine (148 SMs x 32 blocks)
     span = std::min<uint32_t>(span, std::max<uint32_t>(128u, (uint32_t)(n / (148 * 32))));
-    k_entropy<<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
+    if (rv.nodes) k_entropy<true><<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
+    else k_entropy<false><<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
     count_launch();
   }
   mark(g, st);  // 2: entropy decode done

@@ -53,7 +53,8 @@ __host__ __device__ inline uint4 comp_params(const DevTables& tb, int c) {
 }
 
 // One 16-bit extend (decoder.rs:89-93).  false = the stream is exhausted.
-__device__ __forceinline__ bool ans_extend(uint32_t& state, int64_t& ptr, const uint16_t* __restrict__ stream) {
+template <class PtrT>
+__device__ __forceinline__ bool ans_extend(uint32_t& state, PtrT& ptr, const uint16_t* __restrict__ stream) {
   if (ptr <= 0) return false;
   --ptr;
   state = (state << 16) | stream[ptr];
@@ -72,9 +73,10 @@ __device__ __forceinline__ bool ans_extend(uint32_t& state, int64_t& ptr, const 
 // the next j = ceil((n-16)/R) trips need no extend (the state stays >= 2^16 until the j-th shift), they
 // consume the low j*R bits, and the chunks enter `fold` first-taken-highest, i.e. in reversed group order.
 // LUT / ENT are pointers to the component-indexed packed tables (global or shared memory); cp = comp_params(c).
-template <class LutPtr, class EntPtr>
+// PtrT: index of the next word below in `stream` (int64_t, or uint32_t when the resident span has < 2^32 words).
+template <class LutPtr, class EntPtr, class PtrT>
 __device__ __forceinline__ uint64_t ans_decode_cp(const uint4 cp, LutPtr lut, EntPtr ent, uint32_t& state,
-                                                  int64_t& ptr, const uint16_t* __restrict__ stream, uint32_t& err) {
+                                                  PtrT& ptr, const uint16_t* __restrict__ stream, uint32_t& err) {
   const uint32_t L = (cp.x >> 16) & 31u;
   const uint32_t slot = state & ((1u << L) - 1u);
   uint32_t j = lut[(cp.x & 0xFFFFu) + (slot >> ((cp.x >> 21) & 31u))];

@@ -207,6 +207,7 @@ void wga_graph::upload() {
   if (hi > prelude.stream.size() || lo > hi) throw Error(WGA_E_FORMAT, "stream pointers are not monotone");
   stream_base = lo;
   stream_words = hi - lo;
+  if (stream_words >= 0xFFFFFFFFull) throw Error(WGA_E_UNSUPPORTED, "resident stream span of 2^32 words or more: open a smaller shard");
   WGA_CUDA(cudaMalloc(&d_stream, (stream_words + 8) * 2));
   WGA_CUDA(cudaMemset(d_stream, 0, (stream_words + 8) * 2));
   if (stream_words)
