@@ -33,6 +33,7 @@ std::atomic<uint64_t> g_kernel_launches{0};
 struct Tuning {
   uint32_t k1_span = 2048;    // nodes per K1 block
   uint32_t k1_tpb = 128;      // threads per K1 block
+  uint32_t k1_phased = 1;     // 1: k_entropy_phased (batch of 1024 nodes per block, phase by phase); 0: k_entropy
   uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
                               // equal chunk of the level, so a partial second wave would double the time
   uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
@@ -46,6 +47,7 @@ int set_tuning(const char* key, uint64_t value) {
   std::string k(key ? key : "");
   if (k == "k1_span") g_tuning.k1_span = (uint32_t)value;
   else if (k == "k1_tpb") g_tuning.k1_tpb = (uint32_t)value;
+  else if (k == "k1_phased") g_tuning.k1_phased = (uint32_t)value;
   else if (k == "k2_blocks") g_tuning.k2_blocks = (uint32_t)value;
   else if (k == "force_ovf") g_tuning.force_ovf = (uint32_t)value;
   else if (k == "sort_degree") g_tuning.sort_degree = (uint32_t)value;
@@ -456,6 +458,314 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
       }
     }
   }
+}
+
+// -------------------------------------------------------------------------------------------- K1 (phased)
+// Same result as k_entropy (same parking layout, same per-node record), different schedule.  k_entropy pays,
+// on almost every iteration, for the transition code of all nine components (each runs for one or two
+// lanes).  Here a block takes a batch of PH_NB nodes and walks the record grammar phase by phase, with the
+// per-node decoder contexts in shared memory:
+//   P1  uniform pass   outdegree, reference offset, block count        (1-3 symbols per node)
+//   P2  dynamic loop   copy-block runs          (lanes pull nodes with blocks; one tight body)
+//   P3  uniform pass   copied -> extras, interval count
+//   P4  dynamic loop   interval (start,len) runs
+//   P5  dynamic loop   residual runs; the record of the node is written when its run ends
+//   P6  uniform pass   records of the nodes that had no residuals
+// Every loop body is one symbol decode plus a few instructions, and long runs are started first.
+constexpr int PH_TPB = 256;
+constexpr int PH_NB = 1024;
+enum : uint32_t { PF_OVF = 1u, PF_ERR = 2u, PF_DONE = 4u };
+
+struct PhasedShared {
+  uint32_t state[PH_NB], sp[PH_NB], d[PH_NB], dref[PH_NB], aux[PH_NB];  // aux: copied, then extras
+  uint32_t b[PH_NB], ni[PH_NB], ao[PH_NB], apo[PH_NB], so[PH_NB];       // so: slot offset inside the batch
+  uint16_t r[PH_NB], flags[PH_NB];
+  uint16_t big[PH_NB], small[PH_NB];                                     // work list of the current phase
+  uint32_t nbig, nsmall, cur;
+  uint4 cp[WGA_COMPONENTS];
+};
+
+// Pushes node j to the work list of the next dynamic phase; long runs go to the list that is served first.
+__device__ __forceinline__ void ph_push(PhasedShared& S, uint32_t j, bool is_big) {
+  if (is_big) S.big[atomicAdd(&S.nbig, 1u)] = (uint16_t)j;
+  else S.small[atomicAdd(&S.nsmall, 1u)] = (uint16_t)j;
+}
+__device__ __forceinline__ bool ph_pop(PhasedShared& S, uint32_t& j) {
+  const uint32_t i = atomicAdd(&S.cur, 1u);
+  const uint32_t nb = S.nbig;
+  if (i < nb) { j = S.big[i]; return true; }
+  if (i - nb < S.nsmall) { j = S.small[i - nb]; return true; }
+  return false;
+}
+
+template <bool LIST>
+__global__ void __launch_bounds__(PH_TPB) k_entropy_phased(DevGraph g, RangeView rv, uint32_t force_ovf) {
+  extern __shared__ __align__(16) uint8_t ph_raw[];
+  PhasedShared& S = *reinterpret_cast<PhasedShared*>(ph_raw);
+  uint32_t A, Bn;
+  span_range(rv, PH_NB, blockIdx.x, A, Bn);
+  if (span_overflows(rv, A, Bn)) {
+    if (threadIdx.x == 0) atomicOr(rv.err, ERR_WORKSPACE);
+    return;
+  }
+  const uint32_t nb = Bn - A;
+  const uint64_t obase = rv.offs[A];
+  if (rv.offs[Bn] - obase >= 0xFFFFFFFFull) {
+    if (threadIdx.x == 0) atomicOr(rv.err, ERR_SYMBOL_WIDTH);
+    return;
+  }
+  if (threadIdx.x < WGA_COMPONENTS) S.cp[threadIdx.x] = comp_params(g.tb, threadIdx.x);
+  if (threadIdx.x == 0) { S.nbig = S.nsmall = S.cur = 0; }
+  __syncthreads();
+  const uint16_t* lut = g.tb.lut;
+  const uint2* ent = g.tb.ent;
+  const uint32_t minint = g.min_interval, window = g.window;
+  uint32_t* const slot0 = (A < rv.h ? rv.halo_succ : rv.succ - rv.offs[rv.h]) + obase;  // slot of node j: slot0 + so[j]
+  const uint32_t* const states_top = g.states + g.top;
+  const uint64_t* const ptrs_top = g.ptrs + g.top;
+  const uint32_t lo32 = (uint32_t)rv.lo;
+  uint32_t errs = 0;  // error bits seen by this thread (reported once at the end)
+  auto node_id = [&](uint32_t j) -> uint32_t { return LIST ? rv.nodes[A + j] : lo32 + A + j; };
+
+  // ---------------------------------------------------------------- P1: outdegree, reference, block count
+  for (uint32_t j = threadIdx.x; j < nb; j += PH_TPB) {
+    const uint32_t t = A + j, v = node_id(j);
+    uint32_t state = *(states_top - v), err = 0;
+    const uint64_t p = *(ptrs_top - v) - g.stream_base;
+    if (p > g.stream_words) err = ERR_CORRUPT;
+    uint32_t sp = (uint32_t)p;
+    uint32_t d = 0, r = 0, dref = 0, b = 0, ao = 0, apo = 0, fl = 0, copied = 0;
+    uint64_t x = ans_decode_cp(S.cp[Outdegree], lut, ent, state, sp, g.stream, err);
+    if (x >> 32) err |= ERR_SYMBOL_WIDTH;
+    d = (uint32_t)x;
+    S.so[j] = (uint32_t)(rv.offs[t] - obase);
+    if (!err && d && window) {
+      x = ans_decode_cp(S.cp[ReferenceOffset], lut, ent, state, sp, g.stream, err);
+      if (x > window) err |= ERR_CORRUPT;
+      r = (uint32_t)x;
+      if (!err && r) {
+        uint32_t ri = t - r;
+        if (LIST) ri = ref_index(rv, t, r);
+        else if (r > t) ri = NOT_FOUND;
+        if (ri == NOT_FOUND) err |= ERR_RANGE;
+        else {
+          dref = rv.outdeg[ri];
+          x = ans_decode_cp(S.cp[BlockCount], lut, ent, state, sp, g.stream, err);
+          if (x > (uint64_t)dref + 1) err |= ERR_CORRUPT;
+          b = (uint32_t)x;
+          if (!err) {
+            if (b == 0) copied = dref;
+            else {
+              const uint32_t hb = (b + 1) >> 1;
+              if (hb > d || hb > HS_WORDS || b >= MAX_B || dref > 0xFFFFu || force_ovf) {
+                if (header_to_arena(rv, slot0 + S.so[j], b, 0, 0, 0, ao, apo)) fl |= PF_OVF;
+                else err |= ERR_WORKSPACE;
+              }
+              if (!err) ph_push(S, j, b >= 16);
+            }
+          }
+        }
+      }
+    }
+    if (err) { fl |= PF_ERR; errs |= err; }
+    S.state[j] = state; S.sp[j] = sp; S.d[j] = d; S.dref[j] = dref; S.aux[j] = copied;
+    S.b[j] = b; S.ni[j] = 0; S.ao[j] = ao; S.apo[j] = apo; S.r[j] = (uint16_t)r; S.flags[j] = (uint16_t)fl;
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- P2: copy-block runs
+  {
+    bool have = false;
+    uint32_t j = 0, state = 0, sp = 0, dref = 0, b = 0, k = 0, copied = 0, pos = 0, ao = 0, err = 0;
+    bool ovf = false;
+    uint16_t* h16 = nullptr;
+    for (;;) {
+      if (!have) {
+        have = ph_pop(S, j);
+        if (have) {
+          state = S.state[j]; sp = S.sp[j]; dref = S.dref[j]; b = S.b[j]; ao = S.ao[j];
+          ovf = (S.flags[j] & PF_OVF) != 0;
+          h16 = reinterpret_cast<uint16_t*>(slot0 + S.so[j]);
+          k = copied = pos = err = 0;
+        }
+      }
+      if (!__any_sync(FULL, have)) break;
+      if (have) {
+        const uint64_t x = ans_decode_cp(S.cp[Blocks], lut, ent, state, sp, g.stream, err);
+        const uint32_t xl = (uint32_t)x, len = xl + (k != 0);
+        if ((x >> 32) || len > dref - pos || len < xl) err |= ERR_CORRUPT;
+        if (!err) {
+          if (ovf) rv.arena[ao + 4 + k] = len; else h16[k] = (uint16_t)len;
+          if ((k & 1) == 0) copied += len;
+          pos += len;
+        }
+        if (err || ++k == b) {
+          if (!err && (b & 1) == 0) copied += dref - pos;
+          S.state[j] = state; S.sp[j] = sp; S.aux[j] = copied;
+          if (err) { S.flags[j] |= PF_ERR; errs |= err; }
+          have = false;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { S.nbig = S.nsmall = S.cur = 0; }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- P3: extras, interval count
+  for (uint32_t j = threadIdx.x; j < nb; j += PH_TPB) {
+    uint32_t fl = S.flags[j];
+    const uint32_t d = S.d[j];
+    if ((fl & PF_ERR) || d == 0) continue;
+    uint32_t err = 0, extras = d, ni = 0;
+    if (S.r[j]) {
+      const uint32_t copied = S.aux[j];
+      if (copied > d) err |= ERR_CORRUPT;
+      extras = d - copied;
+    }
+    if (!err && extras && minint) {
+      uint32_t state = S.state[j], sp = S.sp[j];
+      const uint64_t x = ans_decode_cp(S.cp[IntervalCount], lut, ent, state, sp, g.stream, err);
+      if (x > extras) err |= ERR_CORRUPT;
+      ni = (uint32_t)x;
+      S.state[j] = state; S.sp[j] = sp;
+      if (!err && ni) {
+        const uint32_t b = S.b[j], hb = (b + 1) >> 1;
+        uint32_t ao = S.ao[j], apo = S.apo[j];
+        if (fl & PF_OVF) {  // header already in the arena: the pairs get their own piece
+          const unsigned long long o = atomicAdd(rv.cursor, 2ull * ni);
+          if (o + 2ull * ni > rv.arena_cap || o + 2ull * ni >= 0xFFFFFFFFull) err |= ERR_WORKSPACE;
+          else { apo = (uint32_t)o; rv.arena[ao + 3] = apo; }
+        } else if (ni >= MAX_NI || hb + 2ull * ni > d || hb + 2ull * ni > HS_WORDS || force_ovf) {
+          if (header_to_arena(rv, slot0 + S.so[j], b, b, ni, 0, ao, apo)) fl |= PF_OVF;
+          else err |= ERR_WORKSPACE;
+        }
+        S.ao[j] = ao; S.apo[j] = apo;
+        if (!err) ph_push(S, j, ni >= 8);
+      }
+    }
+    if (err) { fl |= PF_ERR; errs |= err; }
+    S.aux[j] = extras; S.ni[j] = ni; S.flags[j] = (uint16_t)fl;
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- P4: interval runs
+  {
+    bool have = false;
+    uint32_t j = 0, state = 0, sp = 0, ni = 0, k = 0, extras = 0, prev = 0, v = 0, err = 0;
+    uint32_t* pp = nullptr;
+    for (;;) {
+      if (!have) {
+        have = ph_pop(S, j);
+        if (have) {
+          state = S.state[j]; sp = S.sp[j]; ni = S.ni[j]; extras = S.aux[j]; v = node_id(j);
+          pp = (S.flags[j] & PF_OVF) ? rv.arena + S.apo[j] : slot0 + S.so[j] + ((S.b[j] + 1) >> 1);
+          k = err = 0;
+        }
+      }
+      if (!__any_sync(FULL, have)) break;
+      if (have) {
+        uint64_t x = ans_decode_cp(S.cp[IntervalStart], lut, ent, state, sp, g.stream, err);
+        uint32_t start;
+        bool ok;
+        if (k == 0) ok = add_nat(v, x, start);
+        else { start = prev + 1u + (uint32_t)x; ok = (x >> 32) == 0 && start > prev && start != 0xFFFFFFFFu; }
+        if (!ok) err |= ERR_SYMBOL_WIDTH;
+        uint32_t len = 0;
+        if (!err) {
+          x = ans_decode_cp(S.cp[IntervalLen], lut, ent, state, sp, g.stream, err);
+          len = (uint32_t)x + minint;
+          if ((x >> 32) || len < (uint32_t)x || len > extras || len == 0) err |= ERR_CORRUPT;
+          prev = start + len;
+          if (prev < start) err |= ERR_SYMBOL_WIDTH;
+        }
+        if (!err) {
+          pp[2 * k] = start;
+          pp[2 * k + 1] = len;
+          extras -= len;
+        }
+        if (err || ++k == ni) {
+          S.state[j] = state; S.sp[j] = sp; S.aux[j] = extras;
+          if (err) { S.flags[j] |= PF_ERR; errs |= err; }
+          have = false;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { S.nbig = S.nsmall = S.cur = 0; }
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < nb; j += PH_TPB)
+    if (!(S.flags[j] & PF_ERR) && S.d[j] && S.aux[j]) ph_push(S, j, S.aux[j] >= 64);
+  __syncthreads();
+
+  // ---------------------------------------------------------------- P5: residual runs (+ record of the node)
+  {
+    bool have = false, first = false;
+    uint32_t j = 0, state = 0, sp = 0, extras = 0, prev = 0, v = 0, err = 0;
+    uint32_t* wp = nullptr;
+    uint64_t m = 0;
+    for (;;) {
+      if (!have) {
+        have = ph_pop(S, j);
+        if (have) {
+          state = S.state[j]; sp = S.sp[j]; extras = S.aux[j]; v = node_id(j);
+          const uint32_t d = S.d[j], r = S.r[j], b = S.b[j], ni = S.ni[j], nres = extras, hb = (b + 1) >> 1;
+          uint32_t fl = S.flags[j], ao = S.ao[j], apo = S.apo[j];
+          uint32_t* const slot = slot0 + S.so[j];
+          err = 0;
+          const bool direct = (r == 0 && ni == 0);
+          if (!direct && !(fl & PF_OVF) && (nres >= MAX_NRES || hb + 2ull * ni > (uint64_t)(d - nres))) {
+            if (header_to_arena(rv, slot, b, b, ni, ni, ao, apo)) fl |= PF_OVF;
+            else err |= ERR_WORKSPACE;
+          }
+          if (direct) m = M_DIRECT;
+          else if (fl & PF_OVF) {
+            rv.arena[ao + 1] = ni;
+            rv.arena[ao + 2] = nres;
+            m = (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
+          } else m = (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
+          wp = slot + (d - nres);
+          first = true;
+        }
+      }
+      if (!__any_sync(FULL, have)) break;
+      if (have) {
+        const uint64_t x = ans_decode_cp(S.cp[first ? FirstResidual : Residual], lut, ent, state, sp, g.stream, err);
+        uint32_t val;
+        bool ok;
+        if (first) ok = add_nat(v, x, val);
+        else { val = prev + 1u + (uint32_t)x; ok = (x >> 32) == 0 && val > prev && val != 0xFFFFFFFFu; }
+        if (!ok) err |= ERR_SYMBOL_WIDTH;
+        first = false;
+        if (!err) { prev = val; *wp++ = val; }
+        if (err || --extras == 0) {
+          if (err) { errs |= err; m = M_DIRECT; }
+          rv.meta[A + j] = m;
+          S.flags[j] |= PF_DONE;
+          have = false;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- P6: records of nodes without residuals
+  for (uint32_t j = threadIdx.x; j < nb; j += PH_TPB) {
+    const uint32_t fl = S.flags[j];
+    if (fl & PF_DONE) continue;
+    uint64_t m = M_DIRECT;  // outdegree 0, or a rejected record
+    if (!(fl & PF_ERR) && S.d[j]) {
+      const uint32_t r = S.r[j], b = S.b[j], ni = S.ni[j], ao = S.ao[j];
+      if (fl & PF_OVF) {
+        rv.arena[ao + 1] = ni;
+        rv.arena[ao + 2] = 0;
+        m = (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
+      } else m = (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34);
+    }
+    rv.meta[A + j] = m;
+  }
+  if (errs) atomicOr(rv.err, errs);
 }
 
 // -------------------------------------------------------------------------------------------- K2
@@ -907,7 +1217,17 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
     uint32_t span = tn.k1_span ? tn.k1_span : 1;
     // small ranges: shrink the spans so that the grid still fills the machine (148 SMs x 32 blocks)
     span = std::min<uint32_t>(span, std::max<uint32_t>(128u, (uint32_t)(n / (148 * 32))));
-    if (rv.nodes) k_entropy<true><<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
+    if (tn.k1_phased) {
+      static bool attr = false;
+      if (!attr) {
+        WGA_CUDA(cudaFuncSetAttribute(k_entropy_phased<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PhasedShared)));
+        WGA_CUDA(cudaFuncSetAttribute(k_entropy_phased<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PhasedShared)));
+        attr = true;
+      }
+      const uint32_t grid = span_count(rv.n, rv.h, PH_NB);
+      if (rv.nodes) k_entropy_phased<true><<<grid, PH_TPB, sizeof(PhasedShared), st>>>(g->dev, rv, tn.force_ovf);
+      else k_entropy_phased<false><<<grid, PH_TPB, sizeof(PhasedShared), st>>>(g->dev, rv, tn.force_ovf);
+    } else if (rv.nodes) k_entropy<true><<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
     else k_entropy<false><<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
     count_launch();
   }
