@@ -33,6 +33,8 @@ std::atomic<uint64_t> g_kernel_launches{0};
 struct Tuning {
   uint32_t k1_span = 2048;    // nodes per K1 block
   uint32_t k1_tpb = 128;      // threads per K1 block
+  uint32_t k1_carveout = 100; // shared-memory carve-out (percent) requested for k_entropy_phased (swept: more
+                              // resident blocks beat a larger L1)
   uint32_t k1_phased = 1;     // 1: k_entropy_phased (batch of 1024 nodes per block, phase by phase); 0: k_entropy
   uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
                               // equal chunk of the level, so a partial second wave would double the time
@@ -48,6 +50,7 @@ int set_tuning(const char* key, uint64_t value) {
   if (k == "k1_span") g_tuning.k1_span = (uint32_t)value;
   else if (k == "k1_tpb") g_tuning.k1_tpb = (uint32_t)value;
   else if (k == "k1_phased") g_tuning.k1_phased = (uint32_t)value;
+  else if (k == "k1_carveout") g_tuning.k1_carveout = (uint32_t)value;
   else if (k == "k2_blocks") g_tuning.k2_blocks = (uint32_t)value;
   else if (k == "force_ovf") g_tuning.force_ovf = (uint32_t)value;
   else if (k == "sort_degree") g_tuning.sort_degree = (uint32_t)value;
@@ -472,8 +475,8 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
 //   P5  dynamic loop   residual runs; the record of the node is written when its run ends
 //   P6  uniform pass   records of the nodes that had no residuals
 // Every loop body is one symbol decode plus a few instructions, and long runs are started first.
-constexpr int PH_TPB = 256;
-constexpr int PH_NB = 1024;
+constexpr int PH_TPB = 128;
+constexpr int PH_NB = 512;
 enum : uint32_t { PF_OVF = 1u, PF_ERR = 2u, PF_DONE = 4u };
 
 struct PhasedShared {
@@ -1222,6 +1225,10 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
       if (!attr) {
         WGA_CUDA(cudaFuncSetAttribute(k_entropy_phased<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PhasedShared)));
         WGA_CUDA(cudaFuncSetAttribute(k_entropy_phased<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PhasedShared)));
+        // leave a good part of the SM's 228 KB to L1: the decoder tables (lut + entries, ~100 KB) live there
+        const int carve = (int)tn.k1_carveout;
+        WGA_CUDA(cudaFuncSetAttribute(k_entropy_phased<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        WGA_CUDA(cudaFuncSetAttribute(k_entropy_phased<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         attr = true;
       }
       const uint32_t grid = span_count(rv.n, rv.h, PH_NB);
