@@ -851,29 +851,31 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
   if (threadIdx.x == 0) s_next = cb;
   __syncthreads();
   constexpr uint32_t SETUP_BATCH = 8;
+  constexpr int STEPS_PER_VOTE = 2;  // merge steps between two scheduling votes
   enum { S_FETCH, S_MERGE, S_IDLE };
   int st = S_FETCH;
-  // streams of the current node
-  uint32_t* wp = nullptr;
-  uint32_t* wend = nullptr;
-  const uint32_t* cptr = nullptr;   // next element of the referenced list
-  const uint32_t* cendp = nullptr;  // end of the current copy block
-  const uint32_t* refend = nullptr;
+  // streams of the current node: 32-bit indices against three base pointers
+  uint32_t* out = nullptr;          // the node's slot; p = successors written, d = outdegree
+  const uint32_t* ref = nullptr;    // the referenced list; [ci, cend) = current copy block
+  const uint32_t* res = nullptr;    // the parked residuals (tail of the slot); rj = next one, nres = count
   const uint32_t* blk32 = nullptr;  // block lengths in the overflow arena (else u16 in hdr)
   const uint32_t* pp = nullptr;     // interval pairs (hdr or arena)
-  const uint32_t* rptr = nullptr;   // next residual
+  uint32_t p = 0, d = 0, ci = 0, cend = 0, dref = 0, rj = 0, nres = 0;
   uint32_t cval = INF, ival = INF, iend = 0, rval = INF, b = 0, bk = 0, ni = 0, ik = 0;
+  uint32_t bw0 = 0, bw1 = 0;        // first four in-slot block lengths (u16 each), kept in registers
+  auto block_len = [&](uint32_t k) -> uint32_t {
+    if (blk32) return blk32[k];
+    if (k < 4) return ((k < 2 ? bw0 : bw1) >> ((k & 1u) * 16u)) & 0xFFFFu;
+    return reinterpret_cast<const uint16_t*>(hdr)[k];
+  };
   // the current copy block is exhausted: skip block bk, then copy block bk+1 (or the implicit tail)
   auto next_copy_block = [&]() {
     cval = INF;
     if (bk < b) {
-      cptr += blk32 ? blk32[bk] : (uint32_t) reinterpret_cast<const uint16_t*>(hdr)[bk];
+      ci += block_len(bk);
       ++bk;
-      if (bk < b) {
-        cendp = cptr + (blk32 ? blk32[bk] : (uint32_t) reinterpret_cast<const uint16_t*>(hdr)[bk]);
-        ++bk;
-      } else cendp = refend;
-      if (cptr < cendp) cval = *cptr;
+      if (bk < b) { cend = ci + block_len(bk); ++bk; } else cend = dref;
+      if (ci < cend) cval = ref[ci];
     }
   };
   for (;;) {
@@ -894,9 +896,8 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
         else {
           const uint64_t m = rv.meta[t];
           const uint32_t r = (uint32_t)(m & 0xFFFFu);
-          uint32_t* const slot = node_slot(rv, t);
-          const uint32_t d = (uint32_t)(rv.offs[t + 1] - rv.offs[t]);
-          uint32_t nres;
+          out = node_slot(rv, t);
+          d = (uint32_t)(rv.offs[t + 1] - rv.offs[t]);
           if (m & M_OVF) {
             const uint32_t* rec = rv.arena + (uint32_t)(m >> 19);
             b = rec[0]; ni = rec[1]; nres = rec[2];
@@ -907,50 +908,52 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
             ni = (uint32_t)(m >> 34) & (MAX_NI - 1);
             nres = (uint32_t)(m >> 48);
             const uint32_t hb = (b + 1) >> 1, H = hb + 2 * ni;  // K1 guarantees H <= HS for in-slot headers
-            for (uint32_t w = 0; w < H; ++w) hdr[w] = slot[w];
+            for (uint32_t w = 0; w < H; ++w) hdr[w] = out[w];
+            bw0 = hdr[0];
+            bw1 = hdr[1];
             blk32 = nullptr;
             pp = hdr + hb;
           }
-          wp = slot;
-          wend = slot + d;
-          rptr = slot + (d - nres);
-          rval = nres ? *rptr : INF;
+          p = 0;
+          res = out + (d - nres);
+          rj = 0;
+          rval = nres ? res[0] : INF;
           ik = 0;
           ival = INF;
           if (ni) { ival = pp[0]; iend = ival + pp[1]; }
           cval = INF;
           if (r) {
             const uint32_t tr = ref_index(rv, t, r);  // exists: K1 rejected the record otherwise
-            cptr = node_slot(rv, tr);
-            refend = cptr + (uint32_t)(rv.offs[tr + 1] - rv.offs[tr]);
+            ref = node_slot(rv, tr);
+            dref = (uint32_t)(rv.offs[tr + 1] - rv.offs[tr]);
+            ci = 0;
             bk = 0;
-            cendp = refend;
-            if (b) {
-              cendp = cptr + (blk32 ? blk32[0] : (uint32_t) reinterpret_cast<const uint16_t*>(hdr)[0]);
-              bk = 1;
-            }
-            if (cptr < cendp) cval = *cptr;
+            cend = dref;
+            if (b) { cend = block_len(0); bk = 1; }
+            if (ci < cend) cval = ref[ci];
             else next_copy_block();  // empty first copy block
           }
           st = (d != 0) ? S_MERGE : S_FETCH;
         }
       }
     }
-    if (st == S_MERGE) {
-      const uint32_t mn = min(cval, min(ival, rval));
-      *wp++ = mn;  // (buffering 4 successors for 16-byte stores was measured: no gain, the kernel is issue-bound)
-      if (mn == cval) {
-        if (++cptr == cendp) next_copy_block();
-        else cval = *cptr;
-      } else if (mn == rval) {
-        ++rptr;
-        rval = rptr < wend ? *rptr : INF;
-      } else {
-        if (++ival == iend) {
-          if (++ik < ni) { ival = pp[2 * ik]; iend = ival + pp[2 * ik + 1]; } else ival = INF;
+#pragma unroll
+    for (int step = 0; step < STEPS_PER_VOTE; ++step) {
+      if (st == S_MERGE) {
+        const uint32_t mn = min(cval, min(ival, rval));
+        out[p] = mn;  // (buffering 4 successors for 16-byte stores was measured: no gain, the kernel is issue-bound)
+        if (mn == cval) {
+          if (++ci == cend) next_copy_block();
+          else cval = ref[ci];
+        } else if (mn == rval) {
+          rval = ++rj < nres ? res[rj] : INF;
+        } else {
+          if (++ival == iend) {
+            if (++ik < ni) { ival = pp[2 * ik]; iend = ival + pp[2 * ik + 1]; } else ival = INF;
+          }
         }
+        if (++p == d) st = S_FETCH;
       }
-      if (wp == wend) st = S_FETCH;
     }
   }
 }
