@@ -53,8 +53,9 @@ __host__ __device__ inline uint4 comp_params(const DevTables& tb, int c) {
 }
 
 // One 16-bit extend (decoder.rs:89-93).  false = the stream is exhausted.
-template <class PtrT>
-__device__ __forceinline__ bool ans_extend(uint32_t& state, PtrT& ptr, const uint16_t* __restrict__ stream) {
+// StreamT: anything indexable by the word index (a plain pointer, or WindowedStream below).
+template <class PtrT, class StreamT>
+__device__ __forceinline__ bool ans_extend(uint32_t& state, PtrT& ptr, const StreamT stream) {
   if (ptr <= 0) return false;
   --ptr;
   state = (state << 16) | stream[ptr];
@@ -75,9 +76,9 @@ __device__ __forceinline__ bool ans_extend(uint32_t& state, PtrT& ptr, const uin
 // LUT / ENT are pointers to the component-indexed packed tables (global or shared memory); cp = comp_params(c).
 // Everything after the table lookup: state update, extend, folds.  e = entry that owns `slot`.
 // PtrT: index of the next word below in `stream` (int64_t, or uint32_t when the resident span has < 2^32 words).
-template <class PtrT>
+template <class PtrT, class StreamT>
 __device__ __forceinline__ uint64_t ans_apply(const uint4 cp, const uint2 e, const uint32_t slot, uint32_t& state,
-                                              PtrT& ptr, const uint16_t* __restrict__ stream, uint32_t& err) {
+                                              PtrT& ptr, const StreamT stream, uint32_t& err) {
   const uint32_t L = (cp.x >> 16) & 31u;
   const uint32_t folds = e.y >> 16;
   if (folds == 0xFFFFu) {  // sentinel: slot beyond the sum of frequencies
@@ -125,29 +126,6 @@ __device__ __forceinline__ uint64_t ans_decode_cp(const uint4 cp, LutPtr lut, En
   while (slot - (e.x & 0xFFFFu) >= (e.x >> 16)) {  // rare: several symbols share the bucket
     ++j;
     e = ent[eo + j];
-  }
-  return ans_apply(cp, e, slot, state, ptr, stream, err);
-}
-
-// Tables of one component staged in shared memory: the whole lut, and the first `n` entries (entries are in
-// symbol order and small symbols are the frequent ones); entries beyond the cached prefix come from global.
-struct StagedComp {
-  const uint16_t* lut;  // shared
-  const uint2* ent;     // shared, n entries
-  uint32_t n;
-};
-template <class PtrT>
-__device__ __forceinline__ uint64_t ans_decode_staged(const uint4 cp, const StagedComp sc, const uint2* __restrict__ g_ent,
-                                                      uint32_t& state, PtrT& ptr, const uint16_t* __restrict__ stream,
-                                                      uint32_t& err) {
-  const uint32_t L = (cp.x >> 16) & 31u;
-  const uint32_t slot = state & ((1u << L) - 1u);
-  uint32_t j = sc.lut[slot >> ((cp.x >> 21) & 31u)];
-  const uint32_t eo = cp.y;
-  uint2 e = j < sc.n ? sc.ent[j] : g_ent[eo + j];
-  while (slot - (e.x & 0xFFFFu) >= (e.x >> 16)) {  // rare: several symbols share the bucket
-    ++j;
-    e = j < sc.n ? sc.ent[j] : g_ent[eo + j];
   }
   return ans_apply(cp, e, slot, state, ptr, stream, err);
 }
