@@ -197,8 +197,27 @@ def run_reference(args):
             "config": {"workload": args.workload, "nodes": n, "arcs": meta["arcs"], "bvcomp": BVCOMP},
             "cpu_baseline": {"value": value, "unit": "Garcs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Garcs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything that libraries print to stdout (e.g. the "NCCL version" banner) goes to stderr: stdout
+    carries exactly one line, the JSON result (emit())."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -214,6 +233,7 @@ def main():
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
@@ -438,7 +458,7 @@ def main():
                               "achieved_gbs_all_gpus": bytes_all / (ms_max * 1e-3) / 1e9,
                               "frac_of_aggregate_peak": bytes_all / (ms_max * 1e-3) / 1e9 / (peak * world)},
                 "prepare": {k: meta.get(k) for k in ("gen_s", "model_build_s", "encode_s")}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
