@@ -32,6 +32,8 @@ WORKLOADS = {
     "eu-2015-host-shaped": ("web", 11_264_052, 34.3, 0x5EED0003),
     "dblp-2011-shaped": ("social", 986_324, 6.8, 0x5EED0002),
     "twitter-2010-shaped": ("social", 41_652_230, 35.3, 0x5EED0004),
+    # one rank's share of the gsh-2015-shaped graph (988.5 M nodes / 33.9 G arcs over 8 GPUs): > 2^32 arcs per GPU
+    "gsh-2015-shard": ("web", 123_561_336, 34.3, 0x5EED0005),
     "web-1m": ("web", 1_000_000, 34.3, 0x5EED0010),
     "tiny": ("web", 100_000, 34.3, 0x5EED0011),
 }
