@@ -158,6 +158,40 @@ def test_graph_decode_under_stress_tunings(W, O, gpu, n, deg, params, seed, tuni
     assert (s_succ == succ[off[a]:off[b]]).all()
 
 
+def test_long_records_take_the_cooperative_path(W, O, gpu):
+    """Records with thousands of successors (power-law hubs): reference-free ones with intervals are merged by
+    a whole block (k_resolve_big0), the others by one lane; both must equal the oracle."""
+    rng = np.random.default_rng(11)
+    n = 60000
+    off, succ = make_case(n, 6, 77)
+    lists = [succ[off[v]:off[v + 1]] for v in range(n)]
+
+    def hub(k, runs):
+        s = set(rng.integers(0, n, k).tolist())
+        for _ in range(runs):
+            a = int(rng.integers(0, n - 300))
+            s.update(range(a, a + int(rng.integers(4, 200))))
+        return np.array(sorted(s), np.uint32)
+
+    lists[3] = hub(9000, 40)            # long, many intervals
+    lists[4] = lists[3][::2].copy()     # long, will reference node 3
+    lists[1000] = hub(30000, 3500)      # more intervals than the shared-memory budget of the cooperative path
+    lists[1001] = hub(5000, 0)          # long, residuals only
+    lists[n - 1] = hub(4500, 5)
+    off2 = np.zeros(n + 1, np.uint64)
+    off2[1:] = np.cumsum([len(x) for x in lists])
+    succ2 = np.concatenate(lists).astype(np.uint32)
+    og = O.OracleGraph.store_csr(off2, succ2, 7, 3, 4)
+    g = open_oracle_graph(W, og)
+    d_off, d_succ = gpu_csr(g)
+    assert (d_off == off2).all()
+    assert (d_succ == succ2).all()
+    q = np.array([3, 4, 1000, 1001, n - 1, 7])
+    q_off, q_succ = g.successors_batch(q)
+    exp = np.concatenate([lists[v] for v in q])
+    assert (q_succ.cpu().numpy().view(np.uint32) == exp).all()
+
+
 def test_empty_and_mostly_dangling_graphs(W, O, gpu):
     """Empty graph, and graphs where almost every record is the single Outdegree symbol 0.  (A graph
     with ONLY dangling nodes has zero entropy, which the reference cannot encode: see

@@ -784,6 +784,9 @@ __global__ void __launch_bounds__(PH_TPB) k_entropy_phased(DevGraph g, RangeView
 constexpr uint32_t HS = 16;       // in-slot header words (u16 block lengths + interval pairs) a lane caches
 constexpr uint32_t LCAP = 6;      // levels 0..LCAP-1 have their own segment; deeper nodes share segment LCAP
 constexpr uint32_t KEY_SKIP = 15; // level bucket of nodes that are final after K1
+constexpr uint32_t KEY_BIG0 = 13; // level bucket of long reference-free records with intervals (k_resolve_big0)
+constexpr uint32_t BIG0_DEGREE = 4096;   // outdegree from which a level-0 record takes the cooperative path
+constexpr uint32_t BIG0_MAX_NI = 3072;   // intervals the cooperative path keeps in shared memory (3 x 12 KB static)
 constexpr int RES_TPB = 128;
 
 __device__ __forceinline__ uint32_t degree_bucket(uint32_t d) {  // monotone, 0..227
@@ -811,6 +814,10 @@ __global__ void __launch_bounds__(256) k_levels(RangeView rv, uint16_t* keys, ui
       }
       lb = min(lev, LCAP);
       lev_out[t] = lev;
+      if (lev == 0 && rv.outdeg[t] >= BIG0_DEGREE) {  // one lane would merge this list element by element
+        const uint32_t ni = (m & M_OVF) ? rv.arena[(uint32_t)(m >> 19) + 1] : (uint32_t)(m >> 34) & (MAX_NI - 1);
+        if (ni <= BIG0_MAX_NI) lb = KEY_BIG0;
+      }
     }
     keys[t] = (uint16_t)((lb << 8) | (sort_degree ? 255u - degree_bucket(rv.outdeg[t]) : 0u));
     vals[t] = t;
@@ -954,6 +961,96 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
         }
         if (++p == d) st = S_FETCH;
       }
+    }
+  }
+}
+
+// Long reference-free records (outdegree >= BIG0_DEGREE, with intervals): one BLOCK per node instead of one
+// lane.  The list is the residuals with the expanded intervals inserted, so every element's final position
+// is its index in its own run plus the number of elements of the other run below it:
+//   residual j   -> j + (total length of the intervals that start below it)
+//   interval k,e -> (lengths of the intervals before k) + e + (number of residuals below its start)
+// In place: the residuals sit at the tail of the slot and only move towards the front, so they are moved in
+// ascending chunks (a chunk is read completely before it is written); the interval elements are filled in
+// afterwards.  Social graphs have such records (power-law degrees); one lane would need ~0.2 us per element.
+__global__ void __launch_bounds__(256) k_resolve_big0(RangeView rv, const uint32_t* order, const uint32_t* seg) {
+  __shared__ uint32_t s_start[BIG0_MAX_NI], s_pl[BIG0_MAX_NI + 1], s_below[BIG0_MAX_NI];
+  __shared__ uint32_t s_scan[256];
+  const uint32_t beg = seg[KEY_BIG0], end = seg[KEY_BIG0 + 1];
+  for (uint32_t i = beg + blockIdx.x; i < end; i += gridDim.x) {
+    const uint32_t t = order[i];
+    const uint64_t m = rv.meta[t];
+    uint32_t* const out = node_slot(rv, t);
+    const uint32_t d = (uint32_t)(rv.offs[t + 1] - rv.offs[t]);
+    uint32_t ni, nres;
+    const uint32_t* pp;
+    if (m & M_OVF) {
+      const uint32_t* rec = rv.arena + (uint32_t)(m >> 19);
+      ni = rec[1]; nres = rec[2];
+      pp = rv.arena + rec[3];
+    } else {
+      ni = (uint32_t)(m >> 34) & (MAX_NI - 1);
+      nres = (uint32_t)(m >> 48);
+      pp = out;  // reference-free: no block lengths before the pairs
+    }
+    const uint32_t* const res = out + (d - nres);
+    __syncthreads();  // shared arrays of the previous node are no longer read
+    // ---- interval starts, exclusive prefix of their lengths, residuals below each start
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < ni; base += 256) {
+      const uint32_t k = base + threadIdx.x;
+      uint32_t len = 0;
+      if (k < ni) {
+        const uint32_t st = pp[2 * k];
+        len = pp[2 * k + 1];
+        s_start[k] = st;
+        uint32_t lo = 0, hi = nres;  // residuals < st
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (res[mid] < st) lo = mid + 1; else hi = mid;
+        }
+        s_below[k] = lo;
+      }
+      s_scan[threadIdx.x] = len;
+      __syncthreads();
+      for (uint32_t o = 1; o < 256; o <<= 1) {
+        const uint32_t y = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_scan[threadIdx.x] += y;
+        __syncthreads();
+      }
+      if (k < ni) s_pl[k] = carry + s_scan[threadIdx.x] - len;
+      carry += s_scan[255];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) s_pl[ni] = carry;
+    __syncthreads();
+    const uint32_t total_iv = carry;
+    // ---- residuals, in ascending chunks
+    for (uint32_t base = 0; base < nres; base += 256) {
+      const uint32_t j = base + threadIdx.x;
+      uint32_t x = 0, shift = 0;
+      if (j < nres) {
+        x = res[j];
+        uint32_t lo = 0, hi = ni;  // intervals that start below x
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (s_start[mid] < x) lo = mid + 1; else hi = mid;
+        }
+        shift = s_pl[lo];
+      }
+      __syncthreads();  // the whole chunk is read before any of it is overwritten
+      if (j < nres) out[j + shift] = x;
+    }
+    __syncthreads();
+    // ---- interval elements
+    for (uint32_t e = threadIdx.x; e < total_iv; e += 256) {
+      uint32_t lo = 0, hi = ni;  // last interval whose prefix is <= e
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_pl[mid + 1] <= e) lo = mid + 1; else hi = mid;
+      }
+      out[e + s_below[lo]] = s_start[lo] + (e - s_pl[lo]);
     }
   }
 }
@@ -1256,6 +1353,8 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
     k_segments<<<1, 32, 0, st>>>(sc->hist, sc->seg);
     count_launch();
     mark(g, st);  // 3: levels + sort done
+    k_resolve_big0<<<296, 256, 0, st>>>(rv, dvals.Current(), sc->seg);  // (empty on graphs without long records)
+    count_launch();
     const uint32_t grid = resolve_grid(tn);
     const uint32_t nlev = g->prelude.compression_window ? LCAP : 1;  // without references everything is level 0
     for (uint32_t l = 0; l < nlev; ++l) {
