@@ -35,7 +35,7 @@ struct Tuning {
   uint32_t k1_tpb = 128;      // threads per K1 block
   uint32_t k1_carveout = 100; // shared-memory carve-out (percent) requested for k_entropy_phased (swept: more
                               // resident blocks beat a larger L1)
-  uint32_t k1_phased = 1;     // 1: k_entropy_phased (batch of 1024 nodes per block, phase by phase); 0: k_entropy
+  uint32_t k1_phased = 1;     // 1: k_entropy_phased unless the graph has long records; 2: always; 0: k_entropy
   uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
                               // equal chunk of the level, so a partial second wave would double the time
   uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
@@ -1320,7 +1320,9 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
     uint32_t span = tn.k1_span ? tn.k1_span : 1;
     // small ranges: shrink the spans so that the grid still fills the machine (148 SMs x 32 blocks)
     span = std::min<uint32_t>(span, std::max<uint32_t>(128u, (uint32_t)(n / (148 * 32))));
-    if (tn.k1_phased) {
+    // long records (one serial chain each, e.g. the hubs of social graphs) are decoded faster by the single-loop
+    // kernel: measured 85 vs 116 ms on twitter-2010-shaped, whose longest record dominates K1
+    if (tn.k1_phased && (tn.k1_phased > 1 || g->longest_record() < 8192)) {
       static bool attr = false;
       if (!attr) {
         WGA_CUDA(cudaFuncSetAttribute(k_entropy_phased<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PhasedShared)));
