@@ -97,9 +97,6 @@ constexpr uint32_t MAX_B = 1u << 15, MAX_NI = 1u << 14, MAX_NRES = 1u << 16;
 constexpr uint32_t HS_WORDS = 16;  // in-slot headers are at most this many words (k_resolve caches them per lane)
 
 constexpr uint32_t NOT_FOUND = 0xFFFFFFFFu;
-__device__ __forceinline__ uint64_t node_of(const RangeView& rv, uint32_t t) {
-  return rv.nodes ? (uint64_t)rv.nodes[t] : rv.lo + t;
-}
 // Index of the node referenced by node t with reference offset r (r != 0).  In a sorted duplicate-free
 // list the node (id - r) sits at most r positions before t.
 __device__ __forceinline__ uint32_t ref_index(const RangeView& rv, uint32_t t, uint32_t r) {
