@@ -74,6 +74,7 @@ struct RangeView {
   const uint32_t* nodes;  // nullptr: node t is lo + t; else a sorted, duplicate-free list of node ids (random access)
   uint32_t h;         // halo nodes: first - lo
   uint32_t* outdeg;   // n+1
+  uint2* phase1;      // n : decoder (state, stream index) of every node after its outdegree symbol (from K0)
   uint64_t* offs;     // n+1, relative to lo
   uint64_t* meta;     // n : per-node record of K1 (see M_*)
   uint32_t* arena;    // overflow headers (K1) and pass-2 temporaries
@@ -150,7 +151,7 @@ __device__ __forceinline__ void load_phase(const DevGraph& g, uint64_t v, uint32
 
 // -------------------------------------------------------------------------------------------- K0
 __global__ void __launch_bounds__(TPB) k_outdegree(DevGraph g, uint64_t lo, const uint32_t* nodes, uint32_t n,
-                                                   uint32_t* outdeg, uint32_t* err_out) {
+                                                   uint32_t* outdeg, uint2* phase1, uint32_t* err_out) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n) return;
   if (t == n) { outdeg[n] = 0; return; }
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(TPB) k_outdegree(DevGraph g, uint64_t lo, cons
   uint64_t d = ans_decode(g.tb, g.tb.lut, g.tb.ent, Outdegree, state, ptr, g.stream, err);
   if (d > 0xFFFFFFFFull) err |= ERR_SYMBOL_WIDTH;
   outdeg[t] = (uint32_t)d;
+  if (phase1) phase1[t] = make_uint2(state, (uint32_t)ptr);  // K1 resumes here instead of decoding the symbol again
   if (err) atomicOr(err_out, err);
 }
 
@@ -299,13 +301,19 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
       if (t >= Bn) c = C_IDLE;
       else {
         v = LIST ? rv.nodes[t] : lo32 + t;
-        state = *(states_top - v);
-        const uint64_t p = *(ptrs_top - v) - g.stream_base;
-        if (p > g.stream_words) err = ERR_CORRUPT;
-        sp = (uint32_t)p;  // the resident span has < 2^32 words (checked at upload)
-        c = Outdegree;
+        const uint2 ph = rv.phase1[t];  // K0 left the decoder right after the outdegree symbol
+        state = ph.x;
+        sp = ph.y;  // the resident span has < 2^32 words (checked at upload)
+        d = rv.outdeg[t];
+        extras = d;
         r = b = ni = copied = hb = nres = 0;
-        ovf = direct = false;
+        ovf = false;
+        direct = d == 0;
+        if (d == 0) c = C_FINISH;
+        else {
+          slot = slot_base + rv.offs[t];
+          c = window ? (uint32_t)ReferenceOffset : c_extras;
+        }
       }
     }
     if (__all_sync(FULL, c == C_IDLE)) break;
@@ -392,17 +400,6 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
             else c = IntervalStart;
           }
         }
-      } else if (c == Outdegree) {
-        if (wide) err |= ERR_SYMBOL_WIDTH;
-        d = xl;
-        extras = d;
-        if (!err) {
-          if (d == 0) { direct = true; c = C_FINISH; }
-          else {
-            slot = slot_base + rv.offs[t];
-            c = window ? (uint32_t)ReferenceOffset : c_extras;
-          }
-        }
       } else if (c == ReferenceOffset) {
         uint32_t ri = t - xl;
         if (wide || xl > window) err |= ERR_CORRUPT;
@@ -450,30 +447,30 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
           }
         }
       }
-      if (c == C_AFTER_BLOCKS && !err) {
-        if (copied > d) err |= ERR_CORRUPT;
-        else {
-          extras = d - copied;
-          c = extras ? c_extras : (uint32_t)C_FINISH;
-        }
+    }
+    if (c == C_AFTER_BLOCKS && !err) {
+      if (copied > d) err |= ERR_CORRUPT;
+      else {
+        extras = d - copied;
+        c = extras ? c_extras : (uint32_t)C_FINISH;
       }
-      if (err) {  // the record is inconsistent: leave the node out of phase two and report
-        atomicOr(rv.err, err);
-        rv.meta[t] = M_DIRECT;
-        c = C_FETCH;
-      } else if (c == C_FINISH) {
-        uint64_t m;
-        if (direct) m = M_DIRECT;
-        else if (ovf) {
-          rv.arena[ao + 1] = ni;
-          rv.arena[ao + 2] = nres;
-          m = (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
-        } else {
-          m = (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
-        }
-        rv.meta[t] = m;
-        c = C_FETCH;
+    }
+    if (err) {  // the record is inconsistent: leave the node out of phase two and report
+      atomicOr(rv.err, err);
+      rv.meta[t] = M_DIRECT;
+      c = C_FETCH;
+    } else if (c == C_FINISH) {
+      uint64_t m;
+      if (direct) m = M_DIRECT;
+      else if (ovf) {
+        rv.arena[ao + 1] = ni;
+        rv.arena[ao + 2] = nres;
+        m = (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
+      } else {
+        m = (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
       }
+      rv.meta[t] = m;
+      c = C_FETCH;
     }
   }
 }
@@ -547,15 +544,12 @@ __global__ void __launch_bounds__(PH_TPB) k_entropy_phased(DevGraph g, RangeView
 
   // ---------------------------------------------------------------- P1: outdegree, reference, block count
   for (uint32_t j = threadIdx.x; j < nb; j += PH_TPB) {
-    const uint32_t t = A + j, v = node_id(j);
-    uint32_t state = *(states_top - v), err = 0;
-    const uint64_t p = *(ptrs_top - v) - g.stream_base;
-    if (p > g.stream_words) err = ERR_CORRUPT;
-    uint32_t sp = (uint32_t)p;
-    uint32_t d = 0, r = 0, dref = 0, b = 0, ao = 0, apo = 0, fl = 0, copied = 0;
-    uint64_t x = ans_decode_cp(S.cp[Outdegree], lut, ent, state, sp, g.stream, err);
-    if (x >> 32) err |= ERR_SYMBOL_WIDTH;
-    d = (uint32_t)x;
+    const uint32_t t = A + j;
+    // K0 left the decoder right after the outdegree symbol
+    const uint2 ph = rv.phase1[t];
+    uint32_t state = ph.x, sp = ph.y, err = 0;
+    uint32_t d = rv.outdeg[t], r = 0, dref = 0, b = 0, ao = 0, apo = 0, fl = 0, copied = 0;
+    uint64_t x;
     S.so[j] = (uint32_t)(rv.offs[t] - obase);
     if (!err && d && window) {
       x = ans_decode_cp(S.cp[ReferenceOffset], lut, ent, state, sp, g.stream, err);
@@ -1218,7 +1212,7 @@ struct Scalars {
 static_assert(sizeof(Scalars) <= 256, "Scalars must fit the cleared line");
 
 struct WorkspacePlan {
-  uint64_t off_outdeg, off_offs, off_meta, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_arena;
+  uint64_t off_outdeg, off_phase1, off_offs, off_meta, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_arena;
   uint64_t cub_bytes, halo_cap, fixed_bytes;
 };
 
@@ -1227,6 +1221,7 @@ WorkspacePlan plan_workspace(uint64_t n) {
   uint64_t o = 0;
   o += 256;  // Scalars
   p.off_outdeg = o; o = align_up(o + 4 * (n + 1), 256);
+  p.off_phase1 = o; o = align_up(o + 8 * n, 256);
   p.off_offs = o; o = align_up(o + 8 * (n + 1), 256);
   p.off_meta = o; o = align_up(o + 8 * n, 256);
   p.off_lev = o; o = align_up(o + 4 * n, 256);
@@ -1285,7 +1280,7 @@ void outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets
   if (ws_bytes < p.fixed_bytes) throw Error(WGA_E_WORKSPACE, "workspace too small");
   uint8_t* w = (uint8_t*)ws;
   uint32_t* outdeg = (uint32_t*)(w + p.off_outdeg);
-  k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, first, nullptr, (uint32_t)n, outdeg, g->d_err);
+  k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, first, nullptr, (uint32_t)n, outdeg, nullptr, g->d_err);
   count_launch();
   size_t cb = p.cub_bytes;
   cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(outdeg, U32ToU64());
@@ -1320,7 +1315,7 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
                          const Tuning& tn, cudaStream_t st, uint64_t tot[2]) {
   const uint64_t n = rv.n;
   // ---- K0 + scan
-  k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, rv.lo, rv.nodes, (uint32_t)n, rv.outdeg, g->d_err);
+  k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, rv.lo, rv.nodes, (uint32_t)n, rv.outdeg, rv.phase1, g->d_err);
   count_launch();
   {
     size_t cb = p.cub_bytes;
@@ -1365,7 +1360,7 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
     k_levels<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rv, dkeys.Current(), dvals.Current(), lev, sc->hist, tn.sort_degree);
     count_launch();
     size_t cb = p.cub_bytes;
-    WGA_CUDA(cub::DeviceRadixSort::SortPairs(w + p.off_cub, cb, dkeys, dvals, (int64_t)n, 0, 12, st));
+    WGA_CUDA(cub::DeviceRadixSort::SortPairs(w + p.off_cub, cb, dkeys, dvals, (int64_t)n, tn.sort_degree ? 0 : 8, 12, st));
     count_launch(3);
     k_segments<<<1, 32, 0, st>>>(sc->hist, sc->seg);
     count_launch();
@@ -1460,6 +1455,7 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   RangeView rv{};
   rv.lo = lo; rv.first = first; rv.n = (uint32_t)n; rv.h = (uint32_t)(first - lo);
   rv.outdeg = (uint32_t*)(w + p.off_outdeg);
+  rv.phase1 = (uint2*)(w + p.off_phase1);
   rv.offs = rv.h ? (uint64_t*)(w + p.off_offs) : d_offsets;
   rv.meta = (uint64_t*)(w + p.off_meta);
   rv.arena = (uint32_t*)(w + p.off_arena);
@@ -1553,7 +1549,7 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   count_launch();
   if (!d_succ) {  // sizing call: only the outdegrees of the queries (first symbol of each record)
     uint32_t* deg = all;
-    k_outdegree<<<(unsigned)((nq + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, 0, qid, (uint32_t)nq, deg, g->d_err);
+    k_outdegree<<<(unsigned)((nq + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, 0, qid, (uint32_t)nq, deg, nullptr, g->d_err);
     size_t cbs = b.cub_bytes;
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(deg, U32ToU64());
     WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + b.off_cub, cbs, it, d_offsets, (int64_t)(nq + 1), st));
@@ -1605,6 +1601,7 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   RangeView rv{};
   rv.lo = 0; rv.first = 0; rv.n = nU; rv.h = 0; rv.nodes = U;
   rv.outdeg = (uint32_t*)(iw + p.off_outdeg);
+  rv.phase1 = (uint2*)(iw + p.off_phase1);
   rv.offs = (uint64_t*)(w + b.off_offsU);
   rv.meta = (uint64_t*)(iw + p.off_meta);
   rv.arena = (uint32_t*)(iw + p.off_arena);
