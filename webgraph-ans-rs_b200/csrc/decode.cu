@@ -35,7 +35,8 @@ struct Tuning {
   uint32_t k1_tpb = 128;      // threads per K1 block
   uint32_t k1_carveout = 100; // shared-memory carve-out (percent) requested for k_entropy_phased (swept: more
                               // resident blocks beat a larger L1)
-  uint32_t k1_phased = 1;     // 1: k_entropy_phased unless the graph has long records; 2: always; 0: k_entropy
+  uint32_t k1_phased = 0;     // 0: k_entropy (single loop; 3.12 ms on eu-2015-host-shaped); 1: k_entropy_phased
+                              // (3.22 ms) unless the graph has long records; 2: k_entropy_phased always
   uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
                               // equal chunk of the level, so a partial second wave would double the time
   uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
