@@ -132,9 +132,9 @@ STRESS_TUNINGS = [
     dict(k1_span=5, k2_blocks=1),
     dict(force_ovf=1),                           # every header in the overflow arena
     dict(k1_span=100000, k1_tpb=128, k2_blocks=5000),
-    dict(k1_phased=0),                           # the single-loop state-machine variant of K1
+    dict(k1_phased=1),                           # the phase-structured variant of K1
     dict(k1_phased=2, k2_blocks=64),             # phased K1 even when the graph has long records
-    dict(k1_phased=0, k1_span=37, k1_tpb=32, force_ovf=1),
+    dict(k1_phased=1, force_ovf=1, k2_blocks=9),
 ]
 
 
