@@ -39,9 +39,9 @@ WORKLOADS = {
 }
 # measured DRAM traffic of one decode step (sum over the kernels of the chain), see profiles/r01_*_ncu_*.txt
 NCU_DRAM_BYTES_PER_STEP = {
-    # profiles/r01_v3_ncu_full_eu-host.txt: k_outdegree 0.31 + k_entropy 1.96 + k_levels 0.17 + k_resolve levels
-    # 0..3 0.60+1.12+1.28+1.76 GB (the cub scan/sort launches, ~3 % of the step, were not captured)
-    "eu-2015-host-shaped": 7.19e9,
+    # profiles/r01_v3_ncu_full_eu-host.txt: k_outdegree 0.46 + k_entropy 2.09 + k_levels 0.15 + k_resolve levels
+    # 0..3 0.60+1.12+1.27+1.76 GB (the cub scan/sort launches, ~2 % of the step, were not captured)
+    "eu-2015-host-shaped": 7.45e9,
 }
 BVCOMP = dict(compression_window=7, max_ref_count=3, min_interval_length=4)  # CLI defaults
 CHUNK_NODES = 65536
