@@ -35,6 +35,8 @@ struct Tuning {
   uint32_t k1_tpb = 128;      // threads per K1 block
   uint32_t k1_carveout = 100; // shared-memory carve-out (percent) requested for k_entropy_phased (swept: more
                               // resident blocks beat a larger L1)
+  uint32_t k1_multipass = 1;  // 1: K1 as four single-body launches (k_mp_*) unless the graph has long records;
+                              // 2: always; 0: one kernel (see k1_phased)
   uint32_t k1_phased = 0;     // 0: k_entropy (single loop; 3.12 ms on eu-2015-host-shaped); 1: k_entropy_phased
                               // (3.22 ms) unless the graph has long records; 2: k_entropy_phased always
   uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
@@ -51,6 +53,7 @@ int set_tuning(const char* key, uint64_t value) {
   if (k == "k1_span") g_tuning.k1_span = (uint32_t)value;
   else if (k == "k1_tpb") g_tuning.k1_tpb = (uint32_t)value;
   else if (k == "k1_phased") g_tuning.k1_phased = (uint32_t)value;
+  else if (k == "k1_multipass") g_tuning.k1_multipass = (uint32_t)value;
   else if (k == "k1_carveout") g_tuning.k1_carveout = (uint32_t)value;
   else if (k == "k2_blocks") g_tuning.k2_blocks = (uint32_t)value;
   else if (k == "force_ovf") g_tuning.force_ovf = (uint32_t)value;
@@ -75,6 +78,8 @@ struct RangeView {
   const uint32_t* nodes;  // nullptr: node t is lo + t; else a sorted, duplicate-free list of node ids (random access)
   uint32_t h;         // halo nodes: first - lo
   uint32_t* outdeg;   // n+1
+  uint2* cnt;         // n : multi-pass K1: {copied, then extras ; interval count | MP_* flags}
+  uint2* ovfrec;      // n : multi-pass K1: {arena offset of the overflow header, of its pairs} when MP_OVF is set
   uint4* phase1;      // n : from K0: decoder (state, stream index) after the record's head, reference offset, block count
   uint64_t* offs;     // n+1, relative to lo
   uint64_t* meta;     // n : per-node record of K1 (see M_*)
@@ -779,6 +784,304 @@ __global__ void __launch_bounds__(PH_TPB) k_entropy_phased(DevGraph g, RangeView
   if (errs) atomicOr(rv.err, errs);
 }
 
+// -------------------------------------------------------------------------------------------- K1 (multi-pass)
+// The same result as k_entropy, as four launches with ONE decode body each (uniform single-state passes decode
+// about five times more symbols per second than the mixed state machine: compare K0).  The decoder context of
+// every node travels between the passes in global memory: rv.phase1[t] = {state, stream index, r, b} (written by
+// K0, state/index updated in place) and rv.cnt[t] = {copied -> extras, interval count | MP_* flags}.
+//   k_mp_blocks     run kernel   copy-block lengths of the nodes with b > 0            -> copied
+//   k_mp_icount     uniform      extras = d - copied; interval count; records of nodes that are complete
+//   k_mp_intervals  run kernel   (start, len) pairs of the nodes with intervals        -> extras
+//   k_mp_residuals  run kernel   residual gaps (prefix-summed into the slot tail); record of the node
+// Run kernels: lanes pull nodes of the block's span from a shared counter, skip those without work for this
+// pass, and decode the whole run of a node before pulling the next one; a warp vote ends the loop.
+constexpr uint32_t MP_OVF = 1u << 31, MP_ERR = 1u << 30, MP_MASK = (1u << 30) - 1u;
+
+struct MpCommon {
+  uint32_t A, Bn;
+  uint32_t* slot_base;
+  uint32_t lo32;
+};
+__device__ __forceinline__ bool mp_begin(const RangeView& rv, uint32_t span, MpCommon& mc, uint32_t* s_next) {
+  span_range(rv, span, blockIdx.x, mc.A, mc.Bn);
+  if (span_overflows(rv, mc.A, mc.Bn)) return false;  // reported by K0's caller check / k_mp_icount
+  if (threadIdx.x == 0) *s_next = mc.A;
+  __syncthreads();
+  mc.slot_base = mc.A < rv.h ? rv.halo_succ : rv.succ - rv.offs[rv.h];
+  mc.lo32 = (uint32_t)rv.lo;
+  return true;
+}
+
+template <bool LIST>
+__global__ void __launch_bounds__(128) k_mp_blocks(DevGraph g, RangeView rv, uint32_t span, uint32_t force_ovf) {
+  __shared__ uint32_t s_next;
+  MpCommon mc;
+  if (!mp_begin(rv, span, mc, &s_next)) return;
+  const uint16_t* lut = g.tb.lut;
+  const uint2* ent = g.tb.ent;
+  const uint4 cpb = comp_params(g.tb, Blocks);
+  bool have = false, idle = false;
+  uint32_t t = 0, state = 0, sp = 0, d = 0, dref = 0, b = 0, k = 0, copied = 0, pos = 0, ao = 0, apo = 0, err = 0;
+  bool ovf = false;
+  uint16_t* h16 = nullptr;
+  for (;;) {
+    while (!have && !idle) {  // next node of the span that has copy blocks
+      t = atomicAdd(&s_next, 1u);
+      if (t >= mc.Bn) { idle = true; break; }
+      const uint4 ph = rv.phase1[t];
+      if (ph.z == 0 || ph.w == 0 || rv.outdeg[t] == 0) continue;
+      state = ph.x; sp = ph.y; b = ph.w;
+      d = rv.outdeg[t];
+      const uint32_t r = ph.z;
+      const uint32_t ri = LIST ? ref_index(rv, t, r) : (r <= t ? t - r : NOT_FOUND);
+      err = 0;
+      ovf = false;
+      k = copied = pos = 0;
+      if (ri == NOT_FOUND) err = ERR_RANGE;
+      else {
+        dref = rv.outdeg[ri];
+        if (b > dref && b - dref > 1u) err = ERR_CORRUPT;  // at most dref + 1 blocks
+      }
+      uint32_t* const slot = mc.slot_base + rv.offs[t];
+      h16 = reinterpret_cast<uint16_t*>(slot);
+      const uint32_t hb = (b + 1) >> 1;
+      if (!err && (hb > d || hb > HS_WORDS || b >= MAX_B || dref > 0xFFFFu || force_ovf)) {
+        if (header_to_arena(rv, slot, b, 0, 0, 0, ao, apo)) ovf = true;
+        else err = ERR_WORKSPACE;
+      }
+      if (err) {
+        atomicOr(rv.err, err);
+        rv.cnt[t] = make_uint2(0u, MP_ERR);
+        continue;
+      }
+      have = true;
+    }
+    if (!__any_sync(FULL, have)) break;
+    if (have) {
+      const uint64_t x = ans_decode_cp(cpb, lut, ent, state, sp, g.stream, err);
+      const uint32_t xl = (uint32_t)x, len = xl + (k != 0);
+      if ((x >> 32) || len > dref - pos || len < xl) err |= ERR_CORRUPT;
+      if (!err) {
+        if (ovf) rv.arena[ao + 4 + k] = len; else h16[k] = (uint16_t)len;
+        if ((k & 1) == 0) copied += len;
+        pos += len;
+      }
+      if (err || ++k == b) {
+        if (err) {
+          atomicOr(rv.err, err);
+          rv.cnt[t] = make_uint2(0u, MP_ERR);
+        } else {
+          if ((b & 1) == 0) copied += dref - pos;
+          uint4 ph = rv.phase1[t];
+          ph.x = state; ph.y = sp;
+          rv.phase1[t] = ph;
+          rv.cnt[t] = make_uint2(copied, ovf ? MP_OVF : 0u);
+          if (ovf) rv.ovfrec[t] = make_uint2(ao, apo);
+        }
+        have = false;
+      }
+    }
+  }
+}
+
+// Uniform pass: one lane per node.
+template <bool LIST>
+__global__ void __launch_bounds__(256) k_mp_icount(DevGraph g, RangeView rv, uint32_t force_ovf) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rv.n) return;
+  const uint32_t d = rv.outdeg[t];
+  if (d == 0) { rv.meta[t] = M_DIRECT; rv.cnt[t] = make_uint2(0u, 0u); return; }
+  uint4 ph = rv.phase1[t];
+  const uint32_t r = ph.z, b = ph.w;
+  uint32_t err = 0, copied = 0, fl = 0;
+  if (r) {
+    if (b) {
+      const uint2 c = rv.cnt[t];
+      copied = c.x;
+      fl = c.y & (MP_OVF | MP_ERR);
+    } else {
+      const uint32_t ri = LIST ? ref_index(rv, t, r) : (r <= t ? t - r : NOT_FOUND);
+      if (ri == NOT_FOUND) err = ERR_RANGE; else copied = rv.outdeg[ri];
+    }
+  }
+  if (fl & MP_ERR) { rv.meta[t] = M_DIRECT; return; }  // reported by k_mp_blocks
+  if (!err && copied > d) err = ERR_CORRUPT;
+  uint32_t extras = d - copied, ni = 0;
+  uint2 ov = (fl & MP_OVF) ? rv.ovfrec[t] : make_uint2(0u, 0u);
+  if (!err && extras && g.min_interval) {
+    uint32_t state = ph.x, sp = ph.y;
+    const uint64_t x = ans_decode_cp(comp_params(g.tb, IntervalCount), g.tb.lut, g.tb.ent, state, sp, g.stream, err);
+    if (x > extras) err |= ERR_CORRUPT;
+    ni = (uint32_t)x;
+    ph.x = state; ph.y = sp;
+    if (!err && ni) {
+      const uint32_t hb = (b + 1) >> 1;
+      uint32_t* const slot = node_slot(rv, t);
+      if (fl & MP_OVF) {  // header already in the arena: the pairs get their own piece
+        const unsigned long long o = atomicAdd(rv.cursor, 2ull * ni);
+        if (o + 2ull * ni > rv.arena_cap || o + 2ull * ni >= 0xFFFFFFFFull) err |= ERR_WORKSPACE;
+        else { ov.y = (uint32_t)o; rv.arena[ov.x + 3] = ov.y; }
+      } else if (ni >= MAX_NI || hb + 2ull * ni > d || hb + 2ull * ni > HS_WORDS || force_ovf) {
+        if (header_to_arena(rv, slot, b, b, ni, 0, ov.x, ov.y)) fl |= MP_OVF;
+        else err |= ERR_WORKSPACE;
+      }
+      if (!err && (fl & MP_OVF)) rv.ovfrec[t] = ov;
+    }
+    if (!err) rv.phase1[t] = ph;
+  }
+  if (err) {
+    atomicOr(rv.err, err);
+    rv.meta[t] = M_DIRECT;
+    rv.cnt[t] = make_uint2(0u, MP_ERR);
+    return;
+  }
+  rv.cnt[t] = make_uint2(extras, ni | fl);
+  if (extras == 0) {  // the record is complete: all successors are copied
+    uint64_t m;
+    if (fl & MP_OVF) { rv.arena[ov.x + 1] = 0; rv.arena[ov.x + 2] = 0; m = (uint64_t)r | M_OVF | ((uint64_t)ov.x << 19); }
+    else m = (uint64_t)r | ((uint64_t)b << 19);
+    rv.meta[t] = m;
+  }
+}
+
+// record of a node whose symbols are all decoded
+__device__ __forceinline__ uint64_t mp_meta(const RangeView& rv, uint32_t r, uint32_t b, uint32_t ni, uint32_t nres,
+                                            bool ovf, uint32_t ao) {
+  if (r == 0 && ni == 0) return M_DIRECT;
+  if (ovf) {
+    rv.arena[ao + 1] = ni;
+    rv.arena[ao + 2] = nres;
+    return (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
+  }
+  return (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
+}
+
+template <bool LIST>
+__global__ void __launch_bounds__(128) k_mp_intervals(DevGraph g, RangeView rv, uint32_t span) {
+  __shared__ uint32_t s_next;
+  MpCommon mc;
+  if (!mp_begin(rv, span, mc, &s_next)) return;
+  const uint16_t* lut = g.tb.lut;
+  const uint2* ent = g.tb.ent;
+  const uint4 cps = comp_params(g.tb, IntervalStart), cpl = comp_params(g.tb, IntervalLen);
+  const uint32_t minint = g.min_interval;
+  bool have = false, idle = false;
+  uint32_t t = 0, state = 0, sp = 0, ni = 0, k = 0, extras = 0, prev = 0, v = 0, fl = 0, err = 0;
+  uint32_t* pp = nullptr;
+  for (;;) {
+    while (!have && !idle) {
+      t = atomicAdd(&s_next, 1u);
+      if (t >= mc.Bn) { idle = true; break; }
+      const uint2 c = rv.cnt[t];
+      if ((c.y & MP_ERR) || (c.y & MP_MASK) == 0) continue;
+      const uint4 ph = rv.phase1[t];
+      state = ph.x; sp = ph.y;
+      extras = c.x; ni = c.y & MP_MASK; fl = c.y & MP_OVF;
+      v = LIST ? rv.nodes[t] : mc.lo32 + t;
+      pp = fl ? rv.arena + rv.ovfrec[t].y : mc.slot_base + rv.offs[t] + ((ph.w + 1) >> 1);
+      k = err = 0;
+      have = true;
+    }
+    if (!__any_sync(FULL, have)) break;
+    if (have) {
+      uint64_t x = ans_decode_cp(cps, lut, ent, state, sp, g.stream, err);
+      uint32_t start;
+      bool ok;
+      if (k == 0) ok = add_nat(v, x, start);
+      else { start = prev + 1u + (uint32_t)x; ok = (x >> 32) == 0 && start > prev && start != 0xFFFFFFFFu; }
+      if (!ok) err |= ERR_SYMBOL_WIDTH;
+      uint32_t len = 0;
+      if (!err) {
+        x = ans_decode_cp(cpl, lut, ent, state, sp, g.stream, err);
+        len = (uint32_t)x + minint;
+        if ((x >> 32) || len < (uint32_t)x || len > extras || len == 0) err |= ERR_CORRUPT;
+        prev = start + len;
+        if (prev < start) err |= ERR_SYMBOL_WIDTH;
+      }
+      if (!err) {
+        pp[2 * k] = start;
+        pp[2 * k + 1] = len;
+        extras -= len;
+      }
+      if (err || ++k == ni) {
+        if (err) {
+          atomicOr(rv.err, err);
+          rv.cnt[t] = make_uint2(0u, MP_ERR);
+          rv.meta[t] = M_DIRECT;
+        } else {
+          uint4 ph = rv.phase1[t];
+          ph.x = state; ph.y = sp;
+          rv.phase1[t] = ph;
+          rv.cnt[t] = make_uint2(extras, ni | fl);
+          if (extras == 0) rv.meta[t] = mp_meta(rv, ph.z, ph.w, ni, 0, fl != 0, fl ? rv.ovfrec[t].x : 0u);
+        }
+        have = false;
+      }
+    }
+  }
+}
+
+template <bool LIST>
+__global__ void __launch_bounds__(128) k_mp_residuals(DevGraph g, RangeView rv, uint32_t span) {
+  __shared__ uint32_t s_next;
+  MpCommon mc;
+  if (!mp_begin(rv, span, mc, &s_next)) return;
+  const uint16_t* lut = g.tb.lut;
+  const uint2* ent = g.tb.ent;
+  const uint4 cpf = comp_params(g.tb, FirstResidual), cpr = comp_params(g.tb, Residual);
+  bool have = false, idle = false, first = false;
+  uint32_t t = 0, state = 0, sp = 0, extras = 0, prev = 0, v = 0, err = 0;
+  uint32_t* wp = nullptr;
+  uint64_t m = 0;
+  for (;;) {
+    while (!have && !idle) {
+      t = atomicAdd(&s_next, 1u);
+      if (t >= mc.Bn) { idle = true; break; }
+      const uint2 c = rv.cnt[t];
+      if ((c.y & MP_ERR) || c.x == 0) continue;
+      const uint4 ph = rv.phase1[t];
+      state = ph.x; sp = ph.y;
+      extras = c.x;
+      const uint32_t d = rv.outdeg[t], r = ph.z, b = ph.w, ni = c.y & MP_MASK, nres = extras, hb = (b + 1) >> 1;
+      bool ovf = (c.y & MP_OVF) != 0;
+      uint2 ov = ovf ? rv.ovfrec[t] : make_uint2(0u, 0u);
+      v = LIST ? rv.nodes[t] : mc.lo32 + t;
+      uint32_t* const slot = mc.slot_base + rv.offs[t];
+      err = 0;
+      const bool direct = (r == 0 && ni == 0);
+      if (!direct && !ovf && (nres >= MAX_NRES || hb + 2ull * ni > (uint64_t)(d - nres))) {
+        if (header_to_arena(rv, slot, b, b, ni, ni, ov.x, ov.y)) ovf = true;
+        else err = ERR_WORKSPACE;
+      }
+      if (err) {
+        atomicOr(rv.err, err);
+        rv.meta[t] = M_DIRECT;
+        continue;
+      }
+      m = mp_meta(rv, r, b, ni, nres, ovf, ov.x);
+      wp = slot + (d - nres);
+      first = true;
+      have = true;
+    }
+    if (!__any_sync(FULL, have)) break;
+    if (have) {
+      const uint64_t x = ans_decode_cp(first ? cpf : cpr, lut, ent, state, sp, g.stream, err);
+      uint32_t val;
+      bool ok;
+      if (first) ok = add_nat(v, x, val);
+      else { val = prev + 1u + (uint32_t)x; ok = (x >> 32) == 0 && val > prev && val != 0xFFFFFFFFu; }
+      if (!ok) err |= ERR_SYMBOL_WIDTH;
+      first = false;
+      if (!err) { prev = val; *wp++ = val; }
+      if (err || --extras == 0) {
+        if (err) { atomicOr(rv.err, err); m = M_DIRECT; }
+        rv.meta[t] = m;
+        have = false;
+      }
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------- K2
 // Phase two: copy-block resolution + interval expansion + merge, by reference-chain depth.
 //   k_levels   depth[v] = ref ? depth[v-ref]+1 : 0 for every node that still needs work, and a 12-bit sort
@@ -1211,7 +1514,7 @@ struct Scalars {
 static_assert(sizeof(Scalars) <= 256, "Scalars must fit the cleared line");
 
 struct WorkspacePlan {
-  uint64_t off_outdeg, off_phase1, off_offs, off_meta, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_arena;
+  uint64_t off_outdeg, off_phase1, off_cnt, off_ovfrec, off_offs, off_meta, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_arena;
   uint64_t cub_bytes, halo_cap, fixed_bytes;
 };
 
@@ -1221,6 +1524,8 @@ WorkspacePlan plan_workspace(uint64_t n) {
   o += 256;  // Scalars
   p.off_outdeg = o; o = align_up(o + 4 * (n + 1), 256);
   p.off_phase1 = o; o = align_up(o + 16 * n, 256);
+  p.off_cnt = o; o = align_up(o + 8 * n, 256);
+  p.off_ovfrec = o; o = align_up(o + 8 * n, 256);
   p.off_offs = o; o = align_up(o + 8 * (n + 1), 256);
   p.off_meta = o; o = align_up(o + 8 * n, 256);
   p.off_lev = o; o = align_up(o + 4 * n, 256);
@@ -1331,6 +1636,22 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
     span = std::min<uint32_t>(span, std::max<uint32_t>(128u, (uint32_t)(n / (148 * 32))));
     // long records (one serial chain each, e.g. the hubs of social graphs) are decoded faster by the single-loop
     // kernel: measured 85 vs 116 ms on twitter-2010-shaped, whose longest record dominates K1
+    if (tn.k1_multipass && (tn.k1_multipass > 1 || g->longest_record() < 8192)) {
+      const uint32_t grid = span_count(rv.n, rv.h, span);
+      const bool hasref = g->prelude.compression_window != 0, hasiv = g->prelude.min_interval_length != 0;
+      if (rv.nodes) {
+        if (hasref) k_mp_blocks<true><<<grid, tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
+        k_mp_icount<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g->dev, rv, tn.force_ovf);
+        if (hasiv) k_mp_intervals<true><<<grid, tpb, 0, st>>>(g->dev, rv, span);
+        k_mp_residuals<true><<<grid, tpb, 0, st>>>(g->dev, rv, span);
+      } else {
+        if (hasref) k_mp_blocks<false><<<grid, tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
+        k_mp_icount<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g->dev, rv, tn.force_ovf);
+        if (hasiv) k_mp_intervals<false><<<grid, tpb, 0, st>>>(g->dev, rv, span);
+        k_mp_residuals<false><<<grid, tpb, 0, st>>>(g->dev, rv, span);
+      }
+      count_launch(2 + (hasref ? 1 : 0) + (hasiv ? 1 : 0));
+    } else
     if (tn.k1_phased && (tn.k1_phased > 1 || g->longest_record() < 8192)) {
       static bool attr = false;
       if (!attr) {
@@ -1455,6 +1776,8 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   rv.lo = lo; rv.first = first; rv.n = (uint32_t)n; rv.h = (uint32_t)(first - lo);
   rv.outdeg = (uint32_t*)(w + p.off_outdeg);
   rv.phase1 = (uint4*)(w + p.off_phase1);
+  rv.cnt = (uint2*)(w + p.off_cnt);
+  rv.ovfrec = (uint2*)(w + p.off_ovfrec);
   rv.offs = rv.h ? (uint64_t*)(w + p.off_offs) : d_offsets;
   rv.meta = (uint64_t*)(w + p.off_meta);
   rv.arena = (uint32_t*)(w + p.off_arena);
@@ -1601,6 +1924,8 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   rv.lo = 0; rv.first = 0; rv.n = nU; rv.h = 0; rv.nodes = U;
   rv.outdeg = (uint32_t*)(iw + p.off_outdeg);
   rv.phase1 = (uint4*)(iw + p.off_phase1);
+  rv.cnt = (uint2*)(iw + p.off_cnt);
+  rv.ovfrec = (uint2*)(iw + p.off_ovfrec);
   rv.offs = (uint64_t*)(w + b.off_offsU);
   rv.meta = (uint64_t*)(iw + p.off_meta);
   rv.arena = (uint32_t*)(iw + p.off_arena);
