@@ -174,7 +174,7 @@ int wga_debug_decode_symbols(wga_graph* g, const uint8_t* h_components, uint64_t
 
 /* Kernel tuning knobs of the decode path (process-wide; the parity tests shrink them so that small graphs
  * cross span boundaries, stride the grid and take the overflow paths).  Keys: "k1_span", "k1_tpb",
- * "k1_phased", "k1_carveout", "k2_blocks", "force_ovf", "sort_degree", "e2e_chunk", "reset". */
+ * "k2_blocks", "force_ovf", "sort_degree", "e2e_chunk", "reset". */
 int wga_debug_set_tuning(const char* key, uint64_t value);
 
 /* ---------------------------------------------------------------- model build -------------------- */

@@ -128,15 +128,11 @@ def test_graph_decode_matches_oracle(W, O, gpu, n, deg, params, seed):
 
 
 STRESS_TUNINGS = [
-    dict(k1_span=37, k1_tpb=32, k2_blocks=3),   # many tiny K1 spans, a K2 grid that strides many times
+    dict(k1_span=37, k1_tpb=32, k2_blocks=3),   # many tiny K1 spans, a K2 grid with long chunks per block
     dict(k1_span=5, k2_blocks=1),
     dict(force_ovf=1),                           # every header in the overflow arena
     dict(k1_span=100000, k1_tpb=128, k2_blocks=5000),
-    dict(k1_multipass=0),                        # K1 as one kernel: the single-loop state machine
-    dict(k1_multipass=0, k1_phased=1),           # ... or the phase-structured kernel
-    dict(k1_multipass=2, k1_span=37, k1_tpb=32, force_ovf=1),  # multi-pass K1, tiny spans, arena headers
-    dict(k1_multipass=0, k1_phased=2, k2_blocks=64),  # phased K1 even when the graph has long records
-    dict(k1_multipass=0, k1_phased=1, force_ovf=1, k2_blocks=9),
+    dict(sort_degree=1, k2_blocks=64),           # K2 order by (level, degree) instead of (level, node)
 ]
 
 

@@ -33,12 +33,6 @@ std::atomic<uint64_t> g_kernel_launches{0};
 struct Tuning {
   uint32_t k1_span = 2048;    // nodes per K1 block
   uint32_t k1_tpb = 128;      // threads per K1 block
-  uint32_t k1_carveout = 100; // shared-memory carve-out (percent) requested for k_entropy_phased (swept: more
-                              // resident blocks beat a larger L1)
-  uint32_t k1_multipass = 1;  // 1: K1 as four single-body launches (k_mp_*) unless the graph has long records;
-                              // 2: always; 0: one kernel (see k1_phased)
-  uint32_t k1_phased = 0;     // 0: k_entropy (single loop; 3.12 ms on eu-2015-host-shaped); 1: k_entropy_phased
-                              // (3.22 ms) unless the graph has long records; 2: k_entropy_phased always
   uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
                               // equal chunk of the level, so a partial second wave would double the time
   uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
@@ -52,9 +46,6 @@ int set_tuning(const char* key, uint64_t value) {
   std::string k(key ? key : "");
   if (k == "k1_span") g_tuning.k1_span = (uint32_t)value;
   else if (k == "k1_tpb") g_tuning.k1_tpb = (uint32_t)value;
-  else if (k == "k1_phased") g_tuning.k1_phased = (uint32_t)value;
-  else if (k == "k1_multipass") g_tuning.k1_multipass = (uint32_t)value;
-  else if (k == "k1_carveout") g_tuning.k1_carveout = (uint32_t)value;
   else if (k == "k2_blocks") g_tuning.k2_blocks = (uint32_t)value;
   else if (k == "force_ovf") g_tuning.force_ovf = (uint32_t)value;
   else if (k == "sort_degree") g_tuning.sort_degree = (uint32_t)value;
@@ -78,8 +69,6 @@ struct RangeView {
   const uint32_t* nodes;  // nullptr: node t is lo + t; else a sorted, duplicate-free list of node ids (random access)
   uint32_t h;         // halo nodes: first - lo
   uint32_t* outdeg;   // n+1
-  uint2* cnt;         // n : multi-pass K1: {copied, then extras ; interval count | MP_* flags}
-  uint2* ovfrec;      // n : multi-pass K1: {arena offset of the overflow header, of its pairs} when MP_OVF is set
   uint4* phase1;      // n : from K0: decoder (state, stream index) after the record's head, reference offset, block count
   uint64_t* offs;     // n+1, relative to lo
   uint64_t* meta;     // n : per-node record of K1 (see M_*)
@@ -485,599 +474,6 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
       }
       rv.meta[t] = m;
       c = C_FETCH;
-    }
-  }
-}
-
-// -------------------------------------------------------------------------------------------- K1 (phased)
-// Same result as k_entropy (same parking layout, same per-node record), different schedule.  k_entropy pays,
-// on almost every iteration, for the transition code of all nine components (each runs for one or two
-// lanes).  Here a block takes a batch of PH_NB nodes and walks the record grammar phase by phase, with the
-// per-node decoder contexts in shared memory:
-//   P1  uniform pass   outdegree, reference offset, block count        (1-3 symbols per node)
-//   P2  dynamic loop   copy-block runs          (lanes pull nodes with blocks; one tight body)
-//   P3  uniform pass   copied -> extras, interval count
-//   P4  dynamic loop   interval (start,len) runs
-//   P5  dynamic loop   residual runs; the record of the node is written when its run ends
-//   P6  uniform pass   records of the nodes that had no residuals
-// Every loop body is one symbol decode plus a few instructions, and long runs are started first.
-constexpr int PH_TPB = 128;
-constexpr int PH_NB = 512;
-enum : uint32_t { PF_OVF = 1u, PF_ERR = 2u, PF_DONE = 4u };
-
-struct PhasedShared {
-  uint32_t state[PH_NB], sp[PH_NB], d[PH_NB], dref[PH_NB], aux[PH_NB];  // aux: copied, then extras
-  uint32_t b[PH_NB], ni[PH_NB], ao[PH_NB], apo[PH_NB], so[PH_NB];       // so: slot offset inside the batch
-  uint16_t r[PH_NB], flags[PH_NB];
-  uint16_t big[PH_NB], small[PH_NB];                                     // work list of the current phase
-  uint32_t nbig, nsmall, cur;
-  uint4 cp[WGA_COMPONENTS];
-};
-
-// Pushes node j to the work list of the next dynamic phase; long runs go to the list that is served first.
-__device__ __forceinline__ void ph_push(PhasedShared& S, uint32_t j, bool is_big) {
-  if (is_big) S.big[atomicAdd(&S.nbig, 1u)] = (uint16_t)j;
-  else S.small[atomicAdd(&S.nsmall, 1u)] = (uint16_t)j;
-}
-__device__ __forceinline__ bool ph_pop(PhasedShared& S, uint32_t& j) {
-  const uint32_t i = atomicAdd(&S.cur, 1u);
-  const uint32_t nb = S.nbig;
-  if (i < nb) { j = S.big[i]; return true; }
-  if (i - nb < S.nsmall) { j = S.small[i - nb]; return true; }
-  return false;
-}
-
-template <bool LIST>
-__global__ void __launch_bounds__(PH_TPB) k_entropy_phased(DevGraph g, RangeView rv, uint32_t force_ovf) {
-  extern __shared__ __align__(16) uint8_t ph_raw[];
-  PhasedShared& S = *reinterpret_cast<PhasedShared*>(ph_raw);
-  uint32_t A, Bn;
-  span_range(rv, PH_NB, blockIdx.x, A, Bn);
-  if (span_overflows(rv, A, Bn)) {
-    if (threadIdx.x == 0) atomicOr(rv.err, ERR_WORKSPACE);
-    return;
-  }
-  const uint32_t nb = Bn - A;
-  const uint64_t obase = rv.offs[A];
-  if (rv.offs[Bn] - obase >= 0xFFFFFFFFull) {
-    if (threadIdx.x == 0) atomicOr(rv.err, ERR_SYMBOL_WIDTH);
-    return;
-  }
-  if (threadIdx.x < WGA_COMPONENTS) S.cp[threadIdx.x] = comp_params(g.tb, threadIdx.x);
-  if (threadIdx.x == 0) { S.nbig = S.nsmall = S.cur = 0; }
-  __syncthreads();
-  const uint16_t* lut = g.tb.lut;
-  const uint2* ent = g.tb.ent;
-  const uint32_t minint = g.min_interval, window = g.window;
-  uint32_t* const slot0 = (A < rv.h ? rv.halo_succ : rv.succ - rv.offs[rv.h]) + obase;  // slot of node j: slot0 + so[j]
-  const uint32_t* const states_top = g.states + g.top;
-  const uint64_t* const ptrs_top = g.ptrs + g.top;
-  const uint32_t lo32 = (uint32_t)rv.lo;
-  uint32_t errs = 0;  // error bits seen by this thread (reported once at the end)
-  auto node_id = [&](uint32_t j) -> uint32_t { return LIST ? rv.nodes[A + j] : lo32 + A + j; };
-
-  // ---------------------------------------------------------------- P1: record heads (decoded by K0)
-  for (uint32_t j = threadIdx.x; j < nb; j += PH_TPB) {
-    const uint32_t t = A + j;
-    // K0 left the decoder right after the outdegree symbol
-    const uint4 ph = rv.phase1[t];
-    uint32_t state = ph.x, sp = ph.y, err = 0;
-    uint32_t d = rv.outdeg[t], r = 0, dref = 0, b = 0, ao = 0, apo = 0, fl = 0, copied = 0;
-    S.so[j] = (uint32_t)(rv.offs[t] - obase);
-    r = ph.z;
-    b = ph.w;
-    if (d && r) {
-      const uint32_t ri = LIST ? ref_index(rv, t, r) : (r <= t ? t - r : NOT_FOUND);
-      if (ri == NOT_FOUND) err |= ERR_RANGE;
-      else {
-        dref = rv.outdeg[ri];
-        if (b > dref && b - dref > 1u) err |= ERR_CORRUPT;  // at most dref + 1 blocks
-        else if (b == 0) copied = dref;
-        else {
-          const uint32_t hb = (b + 1) >> 1;
-          if (hb > d || hb > HS_WORDS || b >= MAX_B || dref > 0xFFFFu || force_ovf) {
-            if (header_to_arena(rv, slot0 + S.so[j], b, 0, 0, 0, ao, apo)) fl |= PF_OVF;
-            else err |= ERR_WORKSPACE;
-          }
-          if (!err) ph_push(S, j, b >= 16);
-        }
-      }
-    }
-    if (err) { fl |= PF_ERR; errs |= err; }
-    S.state[j] = state; S.sp[j] = sp; S.d[j] = d; S.dref[j] = dref; S.aux[j] = copied;
-    S.b[j] = b; S.ni[j] = 0; S.ao[j] = ao; S.apo[j] = apo; S.r[j] = (uint16_t)r; S.flags[j] = (uint16_t)fl;
-  }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- P2: copy-block runs
-  {
-    bool have = false;
-    uint32_t j = 0, state = 0, sp = 0, dref = 0, b = 0, k = 0, copied = 0, pos = 0, ao = 0, err = 0;
-    bool ovf = false;
-    uint16_t* h16 = nullptr;
-    for (;;) {
-      if (!have) {
-        have = ph_pop(S, j);
-        if (have) {
-          state = S.state[j]; sp = S.sp[j]; dref = S.dref[j]; b = S.b[j]; ao = S.ao[j];
-          ovf = (S.flags[j] & PF_OVF) != 0;
-          h16 = reinterpret_cast<uint16_t*>(slot0 + S.so[j]);
-          k = copied = pos = err = 0;
-        }
-      }
-      if (!__any_sync(FULL, have)) break;
-      if (have) {
-        const uint64_t x = ans_decode_cp(S.cp[Blocks], lut, ent, state, sp, g.stream, err);
-        const uint32_t xl = (uint32_t)x, len = xl + (k != 0);
-        if ((x >> 32) || len > dref - pos || len < xl) err |= ERR_CORRUPT;
-        if (!err) {
-          if (ovf) rv.arena[ao + 4 + k] = len; else h16[k] = (uint16_t)len;
-          if ((k & 1) == 0) copied += len;
-          pos += len;
-        }
-        if (err || ++k == b) {
-          if (!err && (b & 1) == 0) copied += dref - pos;
-          S.state[j] = state; S.sp[j] = sp; S.aux[j] = copied;
-          if (err) { S.flags[j] |= PF_ERR; errs |= err; }
-          have = false;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) { S.nbig = S.nsmall = S.cur = 0; }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- P3: extras, interval count
-  for (uint32_t j = threadIdx.x; j < nb; j += PH_TPB) {
-    uint32_t fl = S.flags[j];
-    const uint32_t d = S.d[j];
-    if ((fl & PF_ERR) || d == 0) continue;
-    uint32_t err = 0, extras = d, ni = 0;
-    if (S.r[j]) {
-      const uint32_t copied = S.aux[j];
-      if (copied > d) err |= ERR_CORRUPT;
-      extras = d - copied;
-    }
-    if (!err && extras && minint) {
-      uint32_t state = S.state[j], sp = S.sp[j];
-      const uint64_t x = ans_decode_cp(S.cp[IntervalCount], lut, ent, state, sp, g.stream, err);
-      if (x > extras) err |= ERR_CORRUPT;
-      ni = (uint32_t)x;
-      S.state[j] = state; S.sp[j] = sp;
-      if (!err && ni) {
-        const uint32_t b = S.b[j], hb = (b + 1) >> 1;
-        uint32_t ao = S.ao[j], apo = S.apo[j];
-        if (fl & PF_OVF) {  // header already in the arena: the pairs get their own piece
-          const unsigned long long o = atomicAdd(rv.cursor, 2ull * ni);
-          if (o + 2ull * ni > rv.arena_cap || o + 2ull * ni >= 0xFFFFFFFFull) err |= ERR_WORKSPACE;
-          else { apo = (uint32_t)o; rv.arena[ao + 3] = apo; }
-        } else if (ni >= MAX_NI || hb + 2ull * ni > d || hb + 2ull * ni > HS_WORDS || force_ovf) {
-          if (header_to_arena(rv, slot0 + S.so[j], b, b, ni, 0, ao, apo)) fl |= PF_OVF;
-          else err |= ERR_WORKSPACE;
-        }
-        S.ao[j] = ao; S.apo[j] = apo;
-        if (!err) ph_push(S, j, ni >= 8);
-      }
-    }
-    if (err) { fl |= PF_ERR; errs |= err; }
-    S.aux[j] = extras; S.ni[j] = ni; S.flags[j] = (uint16_t)fl;
-  }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- P4: interval runs
-  {
-    bool have = false;
-    uint32_t j = 0, state = 0, sp = 0, ni = 0, k = 0, extras = 0, prev = 0, v = 0, err = 0;
-    uint32_t* pp = nullptr;
-    for (;;) {
-      if (!have) {
-        have = ph_pop(S, j);
-        if (have) {
-          state = S.state[j]; sp = S.sp[j]; ni = S.ni[j]; extras = S.aux[j]; v = node_id(j);
-          pp = (S.flags[j] & PF_OVF) ? rv.arena + S.apo[j] : slot0 + S.so[j] + ((S.b[j] + 1) >> 1);
-          k = err = 0;
-        }
-      }
-      if (!__any_sync(FULL, have)) break;
-      if (have) {
-        uint64_t x = ans_decode_cp(S.cp[IntervalStart], lut, ent, state, sp, g.stream, err);
-        uint32_t start;
-        bool ok;
-        if (k == 0) ok = add_nat(v, x, start);
-        else { start = prev + 1u + (uint32_t)x; ok = (x >> 32) == 0 && start > prev && start != 0xFFFFFFFFu; }
-        if (!ok) err |= ERR_SYMBOL_WIDTH;
-        uint32_t len = 0;
-        if (!err) {
-          x = ans_decode_cp(S.cp[IntervalLen], lut, ent, state, sp, g.stream, err);
-          len = (uint32_t)x + minint;
-          if ((x >> 32) || len < (uint32_t)x || len > extras || len == 0) err |= ERR_CORRUPT;
-          prev = start + len;
-          if (prev < start) err |= ERR_SYMBOL_WIDTH;
-        }
-        if (!err) {
-          pp[2 * k] = start;
-          pp[2 * k + 1] = len;
-          extras -= len;
-        }
-        if (err || ++k == ni) {
-          S.state[j] = state; S.sp[j] = sp; S.aux[j] = extras;
-          if (err) { S.flags[j] |= PF_ERR; errs |= err; }
-          have = false;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) { S.nbig = S.nsmall = S.cur = 0; }
-  __syncthreads();
-  for (uint32_t j = threadIdx.x; j < nb; j += PH_TPB)
-    if (!(S.flags[j] & PF_ERR) && S.d[j] && S.aux[j]) ph_push(S, j, S.aux[j] >= 64);
-  __syncthreads();
-
-  // ---------------------------------------------------------------- P5: residual runs (+ record of the node)
-  {
-    bool have = false, first = false;
-    uint32_t j = 0, state = 0, sp = 0, extras = 0, prev = 0, v = 0, err = 0;
-    uint32_t* wp = nullptr;
-    uint64_t m = 0;
-    for (;;) {
-      if (!have) {
-        have = ph_pop(S, j);
-        if (have) {
-          state = S.state[j]; sp = S.sp[j]; extras = S.aux[j]; v = node_id(j);
-          const uint32_t d = S.d[j], r = S.r[j], b = S.b[j], ni = S.ni[j], nres = extras, hb = (b + 1) >> 1;
-          uint32_t fl = S.flags[j], ao = S.ao[j], apo = S.apo[j];
-          uint32_t* const slot = slot0 + S.so[j];
-          err = 0;
-          const bool direct = (r == 0 && ni == 0);
-          if (!direct && !(fl & PF_OVF) && (nres >= MAX_NRES || hb + 2ull * ni > (uint64_t)(d - nres))) {
-            if (header_to_arena(rv, slot, b, b, ni, ni, ao, apo)) fl |= PF_OVF;
-            else err |= ERR_WORKSPACE;
-          }
-          if (direct) m = M_DIRECT;
-          else if (fl & PF_OVF) {
-            rv.arena[ao + 1] = ni;
-            rv.arena[ao + 2] = nres;
-            m = (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
-          } else m = (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
-          wp = slot + (d - nres);
-          first = true;
-        }
-      }
-      if (!__any_sync(FULL, have)) break;
-      if (have) {
-        const uint64_t x = ans_decode_cp(S.cp[first ? FirstResidual : Residual], lut, ent, state, sp, g.stream, err);
-        uint32_t val;
-        bool ok;
-        if (first) ok = add_nat(v, x, val);
-        else { val = prev + 1u + (uint32_t)x; ok = (x >> 32) == 0 && val > prev && val != 0xFFFFFFFFu; }
-        if (!ok) err |= ERR_SYMBOL_WIDTH;
-        first = false;
-        if (!err) { prev = val; *wp++ = val; }
-        if (err || --extras == 0) {
-          if (err) { errs |= err; m = M_DIRECT; }
-          rv.meta[A + j] = m;
-          S.flags[j] |= PF_DONE;
-          have = false;
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- P6: records of nodes without residuals
-  for (uint32_t j = threadIdx.x; j < nb; j += PH_TPB) {
-    const uint32_t fl = S.flags[j];
-    if (fl & PF_DONE) continue;
-    uint64_t m = M_DIRECT;  // outdegree 0, or a rejected record
-    if (!(fl & PF_ERR) && S.d[j]) {
-      const uint32_t r = S.r[j], b = S.b[j], ni = S.ni[j], ao = S.ao[j];
-      if (fl & PF_OVF) {
-        rv.arena[ao + 1] = ni;
-        rv.arena[ao + 2] = 0;
-        m = (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
-      } else m = (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34);
-    }
-    rv.meta[A + j] = m;
-  }
-  if (errs) atomicOr(rv.err, errs);
-}
-
-// -------------------------------------------------------------------------------------------- K1 (multi-pass)
-// The same result as k_entropy, as four launches with ONE decode body each (uniform single-state passes decode
-// about five times more symbols per second than the mixed state machine: compare K0).  The decoder context of
-// every node travels between the passes in global memory: rv.phase1[t] = {state, stream index, r, b} (written by
-// K0, state/index updated in place) and rv.cnt[t] = {copied -> extras, interval count | MP_* flags}.
-//   k_mp_blocks     run kernel   copy-block lengths of the nodes with b > 0            -> copied
-//   k_mp_icount     uniform      extras = d - copied; interval count; records of nodes that are complete
-//   k_mp_intervals  run kernel   (start, len) pairs of the nodes with intervals        -> extras
-//   k_mp_residuals  run kernel   residual gaps (prefix-summed into the slot tail); record of the node
-// Run kernels: lanes pull nodes of the block's span from a shared counter, skip those without work for this
-// pass, and decode the whole run of a node before pulling the next one; a warp vote ends the loop.
-constexpr uint32_t MP_OVF = 1u << 31, MP_ERR = 1u << 30, MP_MASK = (1u << 30) - 1u;
-
-struct MpCommon {
-  uint32_t A, Bn;
-  uint32_t* slot_base;
-  uint32_t lo32;
-};
-__device__ __forceinline__ bool mp_begin(const RangeView& rv, uint32_t span, MpCommon& mc, uint32_t* s_next) {
-  span_range(rv, span, blockIdx.x, mc.A, mc.Bn);
-  if (span_overflows(rv, mc.A, mc.Bn)) return false;  // reported by K0's caller check / k_mp_icount
-  if (threadIdx.x == 0) *s_next = mc.A;
-  __syncthreads();
-  mc.slot_base = mc.A < rv.h ? rv.halo_succ : rv.succ - rv.offs[rv.h];
-  mc.lo32 = (uint32_t)rv.lo;
-  return true;
-}
-
-template <bool LIST>
-__global__ void __launch_bounds__(128) k_mp_blocks(DevGraph g, RangeView rv, uint32_t span, uint32_t force_ovf) {
-  __shared__ uint32_t s_next;
-  MpCommon mc;
-  if (!mp_begin(rv, span, mc, &s_next)) return;
-  const uint16_t* lut = g.tb.lut;
-  const uint2* ent = g.tb.ent;
-  const uint4 cpb = comp_params(g.tb, Blocks);
-  bool have = false, idle = false;
-  uint32_t t = 0, state = 0, sp = 0, d = 0, dref = 0, b = 0, k = 0, copied = 0, pos = 0, ao = 0, apo = 0, err = 0;
-  bool ovf = false;
-  uint16_t* h16 = nullptr;
-  for (;;) {
-    while (!have && !idle) {  // next node of the span that has copy blocks
-      t = atomicAdd(&s_next, 1u);
-      if (t >= mc.Bn) { idle = true; break; }
-      const uint4 ph = rv.phase1[t];
-      if (ph.z == 0 || ph.w == 0 || rv.outdeg[t] == 0) continue;
-      state = ph.x; sp = ph.y; b = ph.w;
-      d = rv.outdeg[t];
-      const uint32_t r = ph.z;
-      const uint32_t ri = LIST ? ref_index(rv, t, r) : (r <= t ? t - r : NOT_FOUND);
-      err = 0;
-      ovf = false;
-      k = copied = pos = 0;
-      if (ri == NOT_FOUND) err = ERR_RANGE;
-      else {
-        dref = rv.outdeg[ri];
-        if (b > dref && b - dref > 1u) err = ERR_CORRUPT;  // at most dref + 1 blocks
-      }
-      uint32_t* const slot = mc.slot_base + rv.offs[t];
-      h16 = reinterpret_cast<uint16_t*>(slot);
-      const uint32_t hb = (b + 1) >> 1;
-      if (!err && (hb > d || hb > HS_WORDS || b >= MAX_B || dref > 0xFFFFu || force_ovf)) {
-        if (header_to_arena(rv, slot, b, 0, 0, 0, ao, apo)) ovf = true;
-        else err = ERR_WORKSPACE;
-      }
-      if (err) {
-        atomicOr(rv.err, err);
-        rv.cnt[t] = make_uint2(0u, MP_ERR);
-        continue;
-      }
-      have = true;
-    }
-    if (!__any_sync(FULL, have)) break;
-    if (have) {
-      const uint64_t x = ans_decode_cp(cpb, lut, ent, state, sp, g.stream, err);
-      const uint32_t xl = (uint32_t)x, len = xl + (k != 0);
-      if ((x >> 32) || len > dref - pos || len < xl) err |= ERR_CORRUPT;
-      if (!err) {
-        if (ovf) rv.arena[ao + 4 + k] = len; else h16[k] = (uint16_t)len;
-        if ((k & 1) == 0) copied += len;
-        pos += len;
-      }
-      if (err || ++k == b) {
-        if (err) {
-          atomicOr(rv.err, err);
-          rv.cnt[t] = make_uint2(0u, MP_ERR);
-        } else {
-          if ((b & 1) == 0) copied += dref - pos;
-          uint4 ph = rv.phase1[t];
-          ph.x = state; ph.y = sp;
-          rv.phase1[t] = ph;
-          rv.cnt[t] = make_uint2(copied, ovf ? MP_OVF : 0u);
-          if (ovf) rv.ovfrec[t] = make_uint2(ao, apo);
-        }
-        have = false;
-      }
-    }
-  }
-}
-
-// Uniform pass: one lane per node.
-template <bool LIST>
-__global__ void __launch_bounds__(256) k_mp_icount(DevGraph g, RangeView rv, uint32_t force_ovf) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= rv.n) return;
-  const uint32_t d = rv.outdeg[t];
-  if (d == 0) { rv.meta[t] = M_DIRECT; rv.cnt[t] = make_uint2(0u, 0u); return; }
-  uint4 ph = rv.phase1[t];
-  const uint32_t r = ph.z, b = ph.w;
-  uint32_t err = 0, copied = 0, fl = 0;
-  if (r) {
-    if (b) {
-      const uint2 c = rv.cnt[t];
-      copied = c.x;
-      fl = c.y & (MP_OVF | MP_ERR);
-    } else {
-      const uint32_t ri = LIST ? ref_index(rv, t, r) : (r <= t ? t - r : NOT_FOUND);
-      if (ri == NOT_FOUND) err = ERR_RANGE; else copied = rv.outdeg[ri];
-    }
-  }
-  if (fl & MP_ERR) { rv.meta[t] = M_DIRECT; return; }  // reported by k_mp_blocks
-  if (!err && copied > d) err = ERR_CORRUPT;
-  uint32_t extras = d - copied, ni = 0;
-  uint2 ov = (fl & MP_OVF) ? rv.ovfrec[t] : make_uint2(0u, 0u);
-  if (!err && extras && g.min_interval) {
-    uint32_t state = ph.x, sp = ph.y;
-    const uint64_t x = ans_decode_cp(comp_params(g.tb, IntervalCount), g.tb.lut, g.tb.ent, state, sp, g.stream, err);
-    if (x > extras) err |= ERR_CORRUPT;
-    ni = (uint32_t)x;
-    ph.x = state; ph.y = sp;
-    if (!err && ni) {
-      const uint32_t hb = (b + 1) >> 1;
-      uint32_t* const slot = node_slot(rv, t);
-      if (fl & MP_OVF) {  // header already in the arena: the pairs get their own piece
-        const unsigned long long o = atomicAdd(rv.cursor, 2ull * ni);
-        if (o + 2ull * ni > rv.arena_cap || o + 2ull * ni >= 0xFFFFFFFFull) err |= ERR_WORKSPACE;
-        else { ov.y = (uint32_t)o; rv.arena[ov.x + 3] = ov.y; }
-      } else if (ni >= MAX_NI || hb + 2ull * ni > d || hb + 2ull * ni > HS_WORDS || force_ovf) {
-        if (header_to_arena(rv, slot, b, b, ni, 0, ov.x, ov.y)) fl |= MP_OVF;
-        else err |= ERR_WORKSPACE;
-      }
-      if (!err && (fl & MP_OVF)) rv.ovfrec[t] = ov;
-    }
-    if (!err) rv.phase1[t] = ph;
-  }
-  if (err) {
-    atomicOr(rv.err, err);
-    rv.meta[t] = M_DIRECT;
-    rv.cnt[t] = make_uint2(0u, MP_ERR);
-    return;
-  }
-  rv.cnt[t] = make_uint2(extras, ni | fl);
-  if (extras == 0) {  // the record is complete: all successors are copied
-    uint64_t m;
-    if (fl & MP_OVF) { rv.arena[ov.x + 1] = 0; rv.arena[ov.x + 2] = 0; m = (uint64_t)r | M_OVF | ((uint64_t)ov.x << 19); }
-    else m = (uint64_t)r | ((uint64_t)b << 19);
-    rv.meta[t] = m;
-  }
-}
-
-// record of a node whose symbols are all decoded
-__device__ __forceinline__ uint64_t mp_meta(const RangeView& rv, uint32_t r, uint32_t b, uint32_t ni, uint32_t nres,
-                                            bool ovf, uint32_t ao) {
-  if (r == 0 && ni == 0) return M_DIRECT;
-  if (ovf) {
-    rv.arena[ao + 1] = ni;
-    rv.arena[ao + 2] = nres;
-    return (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
-  }
-  return (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
-}
-
-template <bool LIST>
-__global__ void __launch_bounds__(128) k_mp_intervals(DevGraph g, RangeView rv, uint32_t span) {
-  __shared__ uint32_t s_next;
-  MpCommon mc;
-  if (!mp_begin(rv, span, mc, &s_next)) return;
-  const uint16_t* lut = g.tb.lut;
-  const uint2* ent = g.tb.ent;
-  const uint4 cps = comp_params(g.tb, IntervalStart), cpl = comp_params(g.tb, IntervalLen);
-  const uint32_t minint = g.min_interval;
-  bool have = false, idle = false;
-  uint32_t t = 0, state = 0, sp = 0, ni = 0, k = 0, extras = 0, prev = 0, v = 0, fl = 0, err = 0;
-  uint32_t* pp = nullptr;
-  for (;;) {
-    while (!have && !idle) {
-      t = atomicAdd(&s_next, 1u);
-      if (t >= mc.Bn) { idle = true; break; }
-      const uint2 c = rv.cnt[t];
-      if ((c.y & MP_ERR) || (c.y & MP_MASK) == 0) continue;
-      const uint4 ph = rv.phase1[t];
-      state = ph.x; sp = ph.y;
-      extras = c.x; ni = c.y & MP_MASK; fl = c.y & MP_OVF;
-      v = LIST ? rv.nodes[t] : mc.lo32 + t;
-      pp = fl ? rv.arena + rv.ovfrec[t].y : mc.slot_base + rv.offs[t] + ((ph.w + 1) >> 1);
-      k = err = 0;
-      have = true;
-    }
-    if (!__any_sync(FULL, have)) break;
-    if (have) {
-      uint64_t x = ans_decode_cp(cps, lut, ent, state, sp, g.stream, err);
-      uint32_t start;
-      bool ok;
-      if (k == 0) ok = add_nat(v, x, start);
-      else { start = prev + 1u + (uint32_t)x; ok = (x >> 32) == 0 && start > prev && start != 0xFFFFFFFFu; }
-      if (!ok) err |= ERR_SYMBOL_WIDTH;
-      uint32_t len = 0;
-      if (!err) {
-        x = ans_decode_cp(cpl, lut, ent, state, sp, g.stream, err);
-        len = (uint32_t)x + minint;
-        if ((x >> 32) || len < (uint32_t)x || len > extras || len == 0) err |= ERR_CORRUPT;
-        prev = start + len;
-        if (prev < start) err |= ERR_SYMBOL_WIDTH;
-      }
-      if (!err) {
-        pp[2 * k] = start;
-        pp[2 * k + 1] = len;
-        extras -= len;
-      }
-      if (err || ++k == ni) {
-        if (err) {
-          atomicOr(rv.err, err);
-          rv.cnt[t] = make_uint2(0u, MP_ERR);
-          rv.meta[t] = M_DIRECT;
-        } else {
-          uint4 ph = rv.phase1[t];
-          ph.x = state; ph.y = sp;
-          rv.phase1[t] = ph;
-          rv.cnt[t] = make_uint2(extras, ni | fl);
-          if (extras == 0) rv.meta[t] = mp_meta(rv, ph.z, ph.w, ni, 0, fl != 0, fl ? rv.ovfrec[t].x : 0u);
-        }
-        have = false;
-      }
-    }
-  }
-}
-
-template <bool LIST>
-__global__ void __launch_bounds__(128) k_mp_residuals(DevGraph g, RangeView rv, uint32_t span) {
-  __shared__ uint32_t s_next;
-  MpCommon mc;
-  if (!mp_begin(rv, span, mc, &s_next)) return;
-  const uint16_t* lut = g.tb.lut;
-  const uint2* ent = g.tb.ent;
-  const uint4 cpf = comp_params(g.tb, FirstResidual), cpr = comp_params(g.tb, Residual);
-  bool have = false, idle = false, first = false;
-  uint32_t t = 0, state = 0, sp = 0, extras = 0, prev = 0, v = 0, err = 0;
-  uint32_t* wp = nullptr;
-  uint64_t m = 0;
-  for (;;) {
-    while (!have && !idle) {
-      t = atomicAdd(&s_next, 1u);
-      if (t >= mc.Bn) { idle = true; break; }
-      const uint2 c = rv.cnt[t];
-      if ((c.y & MP_ERR) || c.x == 0) continue;
-      const uint4 ph = rv.phase1[t];
-      state = ph.x; sp = ph.y;
-      extras = c.x;
-      const uint32_t d = rv.outdeg[t], r = ph.z, b = ph.w, ni = c.y & MP_MASK, nres = extras, hb = (b + 1) >> 1;
-      bool ovf = (c.y & MP_OVF) != 0;
-      uint2 ov = ovf ? rv.ovfrec[t] : make_uint2(0u, 0u);
-      v = LIST ? rv.nodes[t] : mc.lo32 + t;
-      uint32_t* const slot = mc.slot_base + rv.offs[t];
-      err = 0;
-      const bool direct = (r == 0 && ni == 0);
-      if (!direct && !ovf && (nres >= MAX_NRES || hb + 2ull * ni > (uint64_t)(d - nres))) {
-        if (header_to_arena(rv, slot, b, b, ni, ni, ov.x, ov.y)) ovf = true;
-        else err = ERR_WORKSPACE;
-      }
-      if (err) {
-        atomicOr(rv.err, err);
-        rv.meta[t] = M_DIRECT;
-        continue;
-      }
-      m = mp_meta(rv, r, b, ni, nres, ovf, ov.x);
-      wp = slot + (d - nres);
-      first = true;
-      have = true;
-    }
-    if (!__any_sync(FULL, have)) break;
-    if (have) {
-      const uint64_t x = ans_decode_cp(first ? cpf : cpr, lut, ent, state, sp, g.stream, err);
-      uint32_t val;
-      bool ok;
-      if (first) ok = add_nat(v, x, val);
-      else { val = prev + 1u + (uint32_t)x; ok = (x >> 32) == 0 && val > prev && val != 0xFFFFFFFFu; }
-      if (!ok) err |= ERR_SYMBOL_WIDTH;
-      first = false;
-      if (!err) { prev = val; *wp++ = val; }
-      if (err || --extras == 0) {
-        if (err) { atomicOr(rv.err, err); m = M_DIRECT; }
-        rv.meta[t] = m;
-        have = false;
-      }
     }
   }
 }
@@ -1514,7 +910,7 @@ struct Scalars {
 static_assert(sizeof(Scalars) <= 256, "Scalars must fit the cleared line");
 
 struct WorkspacePlan {
-  uint64_t off_outdeg, off_phase1, off_cnt, off_ovfrec, off_offs, off_meta, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_arena;
+  uint64_t off_outdeg, off_phase1, off_offs, off_meta, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_arena;
   uint64_t cub_bytes, halo_cap, fixed_bytes;
 };
 
@@ -1524,8 +920,6 @@ WorkspacePlan plan_workspace(uint64_t n) {
   o += 256;  // Scalars
   p.off_outdeg = o; o = align_up(o + 4 * (n + 1), 256);
   p.off_phase1 = o; o = align_up(o + 16 * n, 256);
-  p.off_cnt = o; o = align_up(o + 8 * n, 256);
-  p.off_ovfrec = o; o = align_up(o + 8 * n, 256);
   p.off_offs = o; o = align_up(o + 8 * (n + 1), 256);
   p.off_meta = o; o = align_up(o + 8 * n, 256);
   p.off_lev = o; o = align_up(o + 4 * n, 256);
@@ -1634,39 +1028,7 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
     uint32_t span = tn.k1_span ? tn.k1_span : 1;
     // small ranges: shrink the spans so that the grid still fills the machine (148 SMs x 32 blocks)
     span = std::min<uint32_t>(span, std::max<uint32_t>(128u, (uint32_t)(n / (148 * 32))));
-    // long records (one serial chain each, e.g. the hubs of social graphs) are decoded faster by the single-loop
-    // kernel: measured 85 vs 116 ms on twitter-2010-shaped, whose longest record dominates K1
-    if (tn.k1_multipass && (tn.k1_multipass > 1 || g->longest_record() < 8192)) {
-      const uint32_t grid = span_count(rv.n, rv.h, span);
-      const bool hasref = g->prelude.compression_window != 0, hasiv = g->prelude.min_interval_length != 0;
-      if (rv.nodes) {
-        if (hasref) k_mp_blocks<true><<<grid, tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
-        k_mp_icount<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g->dev, rv, tn.force_ovf);
-        if (hasiv) k_mp_intervals<true><<<grid, tpb, 0, st>>>(g->dev, rv, span);
-        k_mp_residuals<true><<<grid, tpb, 0, st>>>(g->dev, rv, span);
-      } else {
-        if (hasref) k_mp_blocks<false><<<grid, tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
-        k_mp_icount<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g->dev, rv, tn.force_ovf);
-        if (hasiv) k_mp_intervals<false><<<grid, tpb, 0, st>>>(g->dev, rv, span);
-        k_mp_residuals<false><<<grid, tpb, 0, st>>>(g->dev, rv, span);
-      }
-      count_launch(2 + (hasref ? 1 : 0) + (hasiv ? 1 : 0));
-    } else
-    if (tn.k1_phased && (tn.k1_phased > 1 || g->longest_record() < 8192)) {
-      static bool attr = false;
-      if (!attr) {
-        WGA_CUDA(cudaFuncSetAttribute(k_entropy_phased<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PhasedShared)));
-        WGA_CUDA(cudaFuncSetAttribute(k_entropy_phased<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PhasedShared)));
-        // leave a good part of the SM's 228 KB to L1: the decoder tables (lut + entries, ~100 KB) live there
-        const int carve = (int)tn.k1_carveout;
-        WGA_CUDA(cudaFuncSetAttribute(k_entropy_phased<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-        WGA_CUDA(cudaFuncSetAttribute(k_entropy_phased<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-        attr = true;
-      }
-      const uint32_t grid = span_count(rv.n, rv.h, PH_NB);
-      if (rv.nodes) k_entropy_phased<true><<<grid, PH_TPB, sizeof(PhasedShared), st>>>(g->dev, rv, tn.force_ovf);
-      else k_entropy_phased<false><<<grid, PH_TPB, sizeof(PhasedShared), st>>>(g->dev, rv, tn.force_ovf);
-    } else if (rv.nodes) k_entropy<true><<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
+    if (rv.nodes) k_entropy<true><<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
     else k_entropy<false><<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
     count_launch();
   }
@@ -1776,8 +1138,6 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   rv.lo = lo; rv.first = first; rv.n = (uint32_t)n; rv.h = (uint32_t)(first - lo);
   rv.outdeg = (uint32_t*)(w + p.off_outdeg);
   rv.phase1 = (uint4*)(w + p.off_phase1);
-  rv.cnt = (uint2*)(w + p.off_cnt);
-  rv.ovfrec = (uint2*)(w + p.off_ovfrec);
   rv.offs = rv.h ? (uint64_t*)(w + p.off_offs) : d_offsets;
   rv.meta = (uint64_t*)(w + p.off_meta);
   rv.arena = (uint32_t*)(w + p.off_arena);
@@ -1924,8 +1284,6 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   rv.lo = 0; rv.first = 0; rv.n = nU; rv.h = 0; rv.nodes = U;
   rv.outdeg = (uint32_t*)(iw + p.off_outdeg);
   rv.phase1 = (uint4*)(iw + p.off_phase1);
-  rv.cnt = (uint2*)(iw + p.off_cnt);
-  rv.ovfrec = (uint2*)(iw + p.off_ovfrec);
   rv.offs = (uint64_t*)(w + b.off_offsU);
   rv.meta = (uint64_t*)(iw + p.off_meta);
   rv.arena = (uint32_t*)(iw + p.off_arena);
