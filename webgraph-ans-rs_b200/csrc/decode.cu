@@ -7,19 +7,24 @@
 //      -> ANSBVGraphDecoderFactory::new_decoder(v)   src/bvgraph/factories/bvgraph_decoder_factory.rs:46-58
 //      -> ANSDecoder::decode(component)              src/ans/decoder.rs:58-100
 //  Pipeline (all launches on the caller's stream):
-//    K0  k_outdegree   first symbol of every record from (states[N-1-v], pointers[N-1-v]) -> outdegree
-//        cub scan      -> CSR offsets
-//    K1  k_entropy     phase one: entropy decode of every component of every node.  One node per LANE,
-//                      lanes pull nodes from a per-block counter and run a uniform per-symbol state
-//                      machine (which component next / how many left), so the instruction stream stays
-//                      convergent although records differ.  Decoded values are PARKED inside the node's
-//                      own final CSR slot: residuals (already prefix-summed) at the tail, copy-block
-//                      lengths (u16) and interval (start,len) pairs at the head.  Nodes that are pure
-//                      residual lists are final after K1.
-//    K2  k_levels      phase two, by reference-chain depth: depth of every node that still needs work and a
-//        cub sort      sort key (level, degree bucket) -> one segment per level, similar degrees adjacent
-//        k_resolve     per level, one node per lane: tight three-way merge (copied elements of the finished
+//    K0  k_outdegree   one lane per node, every lane at the same symbol (the cheapest way to decode): the
+//                      fixed-shape head of every record from (states[N-1-v], pointers[N-1-v]) -- outdegree,
+//                      reference offset, block count -- and the decoder state after it for K1
+//        cub scan      outdegrees -> CSR offsets
+//    K1  k_entropy     phase one: entropy decode of the rest of every record.  One node per LANE: lanes pull
+//                      nodes from a per-block counter and run a per-symbol state machine (which component
+//                      next / how many left); a warp vote per iteration is the reconvergence point, so the
+//                      symbol decode runs with all busy lanes although records differ.  Decoded values are
+//                      PARKED inside the node's own final CSR slot: residuals (already prefix-summed) at the
+//                      tail, copy-block lengths (u16) and interval (start,len) pairs at the head.  Nodes that
+//                      are pure residual lists are final after K1.
+//    K2  k_levels      phase two, by reference-chain depth: depth of every node that still needs work
+//        cub sort      stable sort by level -> one segment per level, node order kept inside a level
+//        k_resolve_big0  long reference-free records with intervals: one block per node
+//        k_resolve     per level, one node per lane: three-way merge (copied elements of the finished
 //                      referenced list, expanded intervals, residuals) in place into the node's CSR slot
+//    Random access (wga_successors_batch) runs the same kernels on the sorted reference closure of the
+//    query nodes (node-list mode) and gathers the query lists.
 // =============================================================================
 #include <cub/cub.cuh>
 
@@ -29,7 +34,7 @@ namespace wga {
 
 std::atomic<uint64_t> g_kernel_launches{0};
 
-// run-time tuning (tests shrink these to exercise span boundaries, ring wrap and the overflow paths)
+// run-time tuning (tests change these to exercise span boundaries, grid striding and the overflow paths)
 struct Tuning {
   uint32_t k1_span = 2048;    // nodes per K1 block
   uint32_t k1_tpb = 128;      // threads per K1 block
