@@ -1006,7 +1006,10 @@ static uint32_t resolve_grid(const Tuning& tn) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resolve, RES_TPB, 0);
-    cached = (uint32_t)(sms * (per_sm > 0 ? per_sm : 1));
+    // swept on eu-2015-host-shaped: 10 resident blocks per SM (40 warps) beat 12 -- the lane-private streams of
+    // more warps no longer fit L1 -- and anything that is not a whole wave loses to the partial second wave
+    per_sm = per_sm > 10 ? 10 : (per_sm > 0 ? per_sm : 1);
+    cached = (uint32_t)(sms * per_sm);
   }
   return cached;
 }
