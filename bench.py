@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                       "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                       stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -291,7 +291,6 @@ def main():
     torch.cuda.synchronize()
     barrier()
     launches = W.kernel_launches() - k0
-    clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms, float(arcs), float(b_alg)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -397,6 +396,7 @@ def main():
     e2e_value = arcs_all / te.item() / 1e9
     e2e = {"value": e2e_value, "unit": "Garcs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": te.item() * 1e3}
+    clocks = sampler.stop()  # sampled over the timed decode steps, the stage timing and the end-to-end steps
 
     # ---- verification against the oracle (bit-exact CSR) and CPU baseline, rank 0 only
     cpu_baseline = None
