@@ -79,6 +79,8 @@ class ClockSampler:
                                       stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            import atexit
+            atexit.register(lambda: self.p.poll() is None and self.p.kill())  # never leave nvidia-smi -lms behind
         except Exception:
             self.p = None
 
