@@ -74,8 +74,7 @@ struct RangeView {
   const uint32_t* nodes;  // nullptr: node t is lo + t; else a sorted, duplicate-free list of node ids (random access)
   uint32_t h;         // halo nodes: first - lo
   uint32_t* outdeg;   // n+1
-  uint4* phase1;      // 2n : from K0: [2t] = {state, stream index, r, b} after the record's head (incl. the first
-                      //      min(b, PRE_BLOCKS) block lengths), [2t+1] = those block lengths
+  uint4* phase1;      // n : from K0: decoder (state, stream index) after the record's head, reference offset, block count
   uint64_t* offs;     // n+1, relative to lo
   uint64_t* meta;     // n : per-node record of K1 (see M_*)
   uint32_t* arena;    // overflow headers (K1) and pass-2 temporaries
@@ -99,7 +98,6 @@ constexpr uint32_t MAX_B = 1u << 15, MAX_NI = 1u << 14, MAX_NRES = 1u << 16;
 constexpr uint32_t HS_WORDS = 16;  // in-slot headers are at most this many words (k_resolve caches them per lane)
 
 constexpr uint32_t NOT_FOUND = 0xFFFFFFFFu;
-constexpr uint32_t PRE_BLOCKS = 4;  // copy-block lengths K0 decodes per record (records with a reference have ~3 on average)
 // Index of the node referenced by node t with reference offset r (r != 0).  In a sorted duplicate-free
 // list the node (id - r) sits at most r positions before t.
 __device__ __forceinline__ uint32_t ref_index(const RangeView& rv, uint32_t t, uint32_t r) {
@@ -155,8 +153,7 @@ __device__ __forceinline__ void load_phase(const DevGraph& g, uint64_t v, uint32
 // One lane per node, every lane at the same symbol: the cheapest way to decode (about 110 G symbols/s on a B200,
 // against 45 G in the general state machine of K1).  So K0 decodes not only the outdegree but the whole
 // fixed-shape head of a record -- outdegree, reference offset, block count -- and hands K1 the decoder state
-// and the first PRE_BLOCKS copy-block lengths -- and hands K1 the decoder state after it (phase1).  Block count
-// and lengths are validated by K1, which knows the outdegree of the referenced node.
+// after it (phase1).  The block count is validated by K1, which knows the outdegree of the referenced node.
 __global__ void __launch_bounds__(TPB) k_outdegree(DevGraph g, uint64_t lo, const uint32_t* nodes, uint32_t n,
                                                    uint32_t* outdeg, uint4* phase1, uint32_t* err_out) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,19 +178,7 @@ __global__ void __launch_bounds__(TPB) k_outdegree(DevGraph g, uint64_t lo, cons
         b = (uint32_t)y;
       }
     }
-    // the first PRE_BLOCKS copy-block lengths: still one symbol per lane and step, lanes with fewer blocks idle
-    uint32_t bl[PRE_BLOCKS] = {0, 0, 0, 0};
-#pragma unroll
-    for (uint32_t k = 0; k < PRE_BLOCKS; ++k) {
-      if (k < b && !err) {
-        const uint64_t x = ans_decode(g.tb, g.tb.lut, g.tb.ent, Blocks, state, ptr, g.stream, err);
-        const uint64_t len = k == 0 ? x : x + 1;  // later blocks are stored minus one
-        if (len > 0xFFFFFFFFull) err |= ERR_CORRUPT;
-        bl[k] = (uint32_t)len;
-      }
-    }
-    phase1[2 * (size_t)t] = make_uint4(state, (uint32_t)ptr, r, b);
-    phase1[2 * (size_t)t + 1] = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+    phase1[t] = make_uint4(state, (uint32_t)ptr, r, b);
   }
   if (err) atomicOr(err_out, err);
 }
@@ -333,7 +318,7 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
       if (t >= Bn) c = C_IDLE;
       else {
         v = LIST ? rv.nodes[t] : lo32 + t;
-        const uint4 ph = rv.phase1[2 * (size_t)t];  // K0 left the decoder after the head of the record
+        const uint4 ph = rv.phase1[t];  // K0 left the decoder after the head: outdegree, reference offset, block count
         state = ph.x;
         sp = ph.y;  // the resident span has < 2^32 words (checked at upload)
         r = ph.z;
@@ -360,21 +345,7 @@ __global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint3
                   if (header_to_arena(rv, slot, b, 0, 0, 0, ao, apo)) ovf = true;
                   else err |= ERR_WORKSPACE;
                 }
-                // the block lengths K0 already decoded: validate against the referenced list and park them
-                const uint4 pb = rv.phase1[2 * (size_t)t + 1];
-                const uint32_t npre = min(b, PRE_BLOCKS);
-                for (; k < npre && !err; ++k) {
-                  const uint32_t len = k == 0 ? pb.x : k == 1 ? pb.y : k == 2 ? pb.z : pb.w;
-                  if (len > dref - pos) { err |= ERR_CORRUPT; break; }
-                  if (ovf) rv.arena[ao + 4 + k] = len;
-                  else reinterpret_cast<uint16_t*>(slot)[k] = (uint16_t)len;
-                  if ((k & 1) == 0) copied += len;
-                  pos += len;
-                }
-                if (k == b) {
-                  if ((b & 1) == 0) copied += dref - pos;
-                  c = C_AFTER_BLOCKS;
-                } else c = Blocks;
+                c = Blocks;
               }
             }
           }
@@ -953,7 +924,7 @@ WorkspacePlan plan_workspace(uint64_t n) {
   uint64_t o = 0;
   o += 256;  // Scalars
   p.off_outdeg = o; o = align_up(o + 4 * (n + 1), 256);
-  p.off_phase1 = o; o = align_up(o + 32 * n, 256);
+  p.off_phase1 = o; o = align_up(o + 16 * n, 256);
   p.off_offs = o; o = align_up(o + 8 * (n + 1), 256);
   p.off_meta = o; o = align_up(o + 8 * n, 256);
   p.off_lev = o; o = align_up(o + 4 * n, 256);
