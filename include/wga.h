@@ -25,7 +25,9 @@
  *  pointers, h_ are HOST pointers.  `stream` is a cudaStream_t passed as void*
  *  (NULL = default stream).  Every function returns 0 on success or a negative
  *  WGA_E_* code; wga_last_error() returns a thread-local message.  Successor ids
- *  are u32 (graphs with < 2^32 nodes), CSR offsets u64.  There is NO CPU fallback:
+ *  are u32 (graphs with < 2^32 nodes), CSR offsets u64.  A handle is read-only after open, but it owns the
+ *  small pinned block through which the kernels publish scalars to the host, so run ONE decode / random-access
+ *  call at a time per handle (open a second handle, or a shard per rank, for concurrency).  There is NO CPU fallback:
  *  calls that need the GPU fail with WGA_E_CUDA when no device is usable.
  * ============================================================================= */
 #ifndef WGA_H
