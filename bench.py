@@ -318,8 +318,8 @@ def main():
         acc += stages
     W.lib().wga_set_profiling(g._h, 0)
     acc /= reps
-    stage_names = ["outdegree+scan(k_outdegree,cub)", "entropy_decode(k_entropy)", "levels+sort(k_levels,cub)",
-                   "resolve(k_resolve x levels)"]
+    stage_names = ["heads+scan(k_heads,cub)", "entropy_decode(k_entropy)", "tiles(k_tile)",
+                   "global_pass(k_hard_*)"]
     kernels = {stage_names[i]: float(acc[i]) for i in range(min(4, max(0, nev - 1)))}
     peak, peak_src = measured_peak_gbs()
     step_kernel_ms = float(sum(kernels.values())) or ms

@@ -175,8 +175,8 @@ int wga_debug_decode_symbols(wga_graph* g, const uint8_t* h_components, uint64_t
                              uint64_t* h_out, uint64_t* h_end_ptr, uint32_t* h_end_state);
 
 /* Kernel tuning knobs of the decode path (process-wide; the parity tests shrink them so that small graphs
- * cross span boundaries, stride the grid and take the overflow paths).  Keys: "k1_span", "k1_tpb",
- * "k2_blocks", "force_ovf", "sort_degree", "e2e_chunk", "reset". */
+ * cross tile boundaries, force sub-tiling and take the global-memory pass).  Keys: "tile", "slotcap", "rowcap",
+ * "dbig", "k1_blocks", "refill", "e2e_chunk", "reset". */
 int wga_debug_set_tuning(const char* key, uint64_t value);
 
 /* ---------------------------------------------------------------- model build -------------------- */

@@ -128,19 +128,19 @@ def test_graph_decode_matches_oracle(W, O, gpu, n, deg, params, seed):
 
 
 STRESS_TUNINGS = [
-    dict(k1_span=37, k1_tpb=32, k2_blocks=3),   # many tiny K1 spans, a K2 grid with long chunks per block
-    dict(k1_span=5, k2_blocks=1),
-    dict(force_ovf=1),                           # every header in the overflow arena
-    dict(k1_span=100000, k1_tpb=128, k2_blocks=5000),
-    dict(sort_degree=1, k2_blocks=64),           # K2 order by (level, degree) instead of (level, node)
+    dict(tile=37, k1_blocks=1, refill=1),        # many tiny tiles / K1 units, one K1 block
+    dict(tile=5, refill=32),                      # tiles smaller than the look-back window
+    dict(slotcap=96, rowcap=6),                   # tiles that do not fit shared memory: sub-tiling, nodes left to the global pass
+    dict(dbig=8),                                 # most nodes resolved by the global pass (k_hard_*)
+    dict(tile=192, slotcap=700, rowcap=24, k1_blocks=3),
 ]
 
 
 @pytest.mark.parametrize("tuning", range(len(STRESS_TUNINGS)))
 @pytest.mark.parametrize("n,deg,params,seed", [GRAPH_CASES[2], GRAPH_CASES[4], GRAPH_CASES[6], GRAPH_CASES[8]])
 def test_graph_decode_under_stress_tunings(W, O, gpu, n, deg, params, seed, tuning):
-    """Same parity check with the kernel knobs changed so that small graphs exercise span boundaries,
-    grid striding and the overflow-arena headers."""
+    """Same parity check with the kernel knobs changed so that small graphs exercise tile boundaries,
+    sub-tiling, look-back records read from global memory and the global pass for nodes a tile cannot hold."""
     off, succ = make_case(n, deg, seed)
     og = O.OracleGraph.store_csr(off, succ, *params)
     g = open_oracle_graph(W, og)
@@ -158,8 +158,8 @@ def test_graph_decode_under_stress_tunings(W, O, gpu, n, deg, params, seed, tuni
 
 
 def test_long_records_take_the_cooperative_path(W, O, gpu):
-    """Records with thousands of successors (power-law hubs): reference-free ones with intervals are merged by
-    a whole block (k_resolve_big0), the others by one lane; both must equal the oracle."""
+    """Records with thousands of successors (power-law hubs): their residual runs are parked in the node's own
+    slot and the lists are resolved by the global pass (k_hard_*); all must equal the oracle."""
     rng = np.random.default_rng(11)
     n = 60000
     off, succ = make_case(n, 6, 77)

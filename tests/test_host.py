@@ -65,6 +65,19 @@ def test_golden_head_files_load(W, head):
     assert p["pointers"][-1] == p["stream"].size and (np.diff(p["pointers"].astype(np.int64)) >= 0).all()
 
 
+def test_packed_tables_equal_reference_decoder_tables_on_host(W, O, head):
+    """K3 parity without a GPU: the bucket + popcount lookup on the packed tables of a host-only handle gives, per
+    slot, the (freq, cumul_freq, quasi_folded) of ANSModel4Decoder::new (model4decoder.rs:18-68)."""
+    g = W.ANSBvGraph.load(head["base"], host_only=True)
+    og = O.OracleGraph.load(head["base"])
+    for c in range(9):
+        ours = g.debug_expand_table(c)
+        ref = og.decoder_table(c)
+        assert ours.size == ref.size
+        for f in ("freq", "cumul_freq", "quasi_folded"):
+            assert (ours[f] == ref[f]).all(), (c, f)
+
+
 def test_files_roundtrip_through_oracle_reader(W, O, tmp_path):
     """What the product writes, the oracle's independent epserde/Elias-Fano reader reads back."""
     rng = np.random.default_rng(3)

@@ -66,26 +66,31 @@ enum Component : int {
 // The reference expands every component to 2^frame 16-byte entries (model4decoder.rs:18-54; up to 1 MiB
 // per component, L2-resident at best).  Slots are uniformly distributed, so that table cannot be cached.
 // We keep instead, per component:
-//   lut[2^min(L,LUT_BITS)] : u16 index of the non-zero symbol that owns the first slot of the bucket
-//   ent[nnz+1]             : {cumul | freq<<16 , base | folds<<16}; last entry is a sentinel
-// A lookup is lut -> ent (+ a short forward walk for rare symbols sharing a bucket): ~45 KB + 8 B per
-// symbol, which fits in shared memory for typical graphs.
-constexpr int LUT_BITS = 11;
-
+//   bkt[max(1, 2^L / 32)] : per bucket of 32 slots {mask, j0}: j0 = index of the non-zero symbol that owns the
+//                           first slot of the bucket, bit s of mask (s >= 1) set iff a symbol's slot range starts
+//                           at slot 32*bucket + s.  Owner of a slot = j0 + popc(mask & ((2 << s) - 1)): exact, no walk.
+//   ent[nnz+1]            : {cumul | freq<<16 , base | folds<<16}; last entry is a sentinel that owns the unused
+//                           slots beyond the sum of frequencies (folds == 0xFFFF)
+// <= 16 KB of buckets per component + 8 B per symbol: shared-memory resident in the entropy kernel.
 struct Ent {
   uint32_t cf;  // cumul_freq | freq << 16
   uint32_t bf;  // base (symbol - offset*folds) | folds << 16 ; folds == 0xFFFF marks the sentinel
 };
+struct Bkt {
+  uint32_t mask;
+  uint32_t j0;
+};
 
 struct PackedTablesData {
-  std::vector<uint16_t> lut;
+  std::vector<Bkt> bkt;
   std::vector<Ent> ent;
-  uint32_t lut_off[WGA_COMPONENTS];
+  uint32_t bkt_off[WGA_COMPONENTS];
   uint32_t ent_off[WGA_COMPONENTS];
+  uint32_t nb[WGA_COMPONENTS];
+  uint32_t nent[WGA_COMPONENTS];  // including the sentinel
   uint32_t nnz[WGA_COMPONENTS];
   uint8_t L[WGA_COMPONENTS];
   uint8_t R[WGA_COMPONENTS];
-  uint8_t shift[WGA_COMPONENTS];
 };
 PackedTablesData pack_tables(const ComponentModel tables[WGA_COMPONENTS]);
 

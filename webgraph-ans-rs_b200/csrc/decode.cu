@@ -7,26 +7,33 @@
 //      -> ANSBVGraphDecoderFactory::new_decoder(v)   src/bvgraph/factories/bvgraph_decoder_factory.rs:46-58
 //      -> ANSDecoder::decode(component)              src/ans/decoder.rs:58-100
 //  Pipeline (all launches on the caller's stream):
-//    K0  k_outdegree   one lane per node, every lane at the same symbol (the cheapest way to decode): the
-//                      fixed-shape head of every record from (states[N-1-v], pointers[N-1-v]) -- outdegree,
-//                      reference offset, block count -- and the decoder state after it for K1
+//    K0  k_heads       one lane per node, every lane at the same symbol: the fixed-shape head of every record from
+//                      (states[N-1-v], pointers[N-1-v]) -- outdegree, reference offset, block count -- and the
+//                      decoder state after it
 //        cub scan      outdegrees -> CSR offsets
-//    K1  k_entropy     phase one: entropy decode of the rest of every record.  One node per LANE: lanes pull
-//                      nodes from a per-block counter and run a per-symbol state machine (which component
-//                      next / how many left); a warp vote per iteration is the reconvergence point, so the
-//                      symbol decode runs with all busy lanes although records differ.  Decoded values are
-//                      PARKED inside the node's own final CSR slot: residuals (already prefix-summed) at the
-//                      tail, copy-block lengths (u16) and interval (start,len) pairs at the head.  Nodes that
-//                      are pure residual lists are final after K1.
-//    K2  k_levels      phase two, by reference-chain depth: depth of every node that still needs work
-//        cub sort      stable sort by level -> one segment per level, node order kept inside a level
-//        k_resolve_big0  long reference-free records with intervals: one block per node
-//        k_resolve     per level, one node per lane: three-way merge (copied elements of the finished
-//                      referenced list, expanded intervals, residuals) in place into the node's CSR slot
+//    K1  k_entropy     phase one: entropy decode of the rest of every record.  Persistent kernel, one 1024-thread
+//                      block per SM with the decoder tables of the six components in SHARED memory (bucket +
+//                      popcount lookup, no search).  Warps are independent: each pulls units of consecutive nodes
+//                      from a global counter, its lanes take the nodes one by one (ballot-ranked, no atomics) and
+//                      run a per-symbol state machine; every busy lane decodes ONE symbol per iteration and the
+//                      32 produced words (cumulative copy-block ends, interval count, interval starts / lengths,
+//                      prefix-summed residuals) go out as ONE coalesced 128-byte row.  A record is therefore a
+//                      column segment (row0, lane, length) of the warp's row stream.
+//    K2  k_tile        phase two: one block per tile of consecutive nodes, everything in SHARED memory.  The tile's
+//                      rows arrive as one bulk copy; the few predecessor nodes referenced from outside the tile
+//                      (found by walking the reference chains of the tile's own nodes) are re-resolved locally, so
+//                      tiles are independent.  Nodes are bucketed by (reference-chain depth, outdegree class); per
+//                      depth, every lane merges one node -- copied elements of the already finished referenced
+//                      list (block mask), expanded intervals, residuals -- from / into shared memory, and the
+//                      finished tile leaves as one coalesced copy.
+//        k_hard_*      nodes a tile cannot hold (outdegree >= 1024, chains deeper than 8, chains leaving the
+//                      look-back window) are resolved afterwards from global memory, one launch per depth.
 //    Random access (wga_successors_batch) runs the same kernels on the sorted reference closure of the
 //    query nodes (node-list mode) and gathers the query lists.
 // =============================================================================
 #include <cub/cub.cuh>
+
+#include <mutex>
 
 #include "graph.hpp"
 
@@ -34,26 +41,26 @@ namespace wga {
 
 std::atomic<uint64_t> g_kernel_launches{0};
 
-// run-time tuning (tests change these to exercise span boundaries, grid striding and the overflow paths)
+// run-time tuning (tests change these to exercise tile boundaries, sub-tiling and the hard-node path)
 struct Tuning {
-  uint32_t k1_span = 2048;    // nodes per K1 block
-  uint32_t k1_tpb = 128;      // threads per K1 block
-  uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
-                              // equal chunk of the level, so a partial second wave would double the time
-  uint32_t force_ovf = 0;     // K1: put every header in the overflow arena
-  uint32_t e2e_chunk = 1u << 19;  // nodes per chunk of the pipelined host entry point (swept: 31.6 ms at 2^19)
-  uint32_t sort_degree = 0;   // K2: 1 = sort key includes the degree bucket; 0 = level only, node order kept
-                              // (measured: locality of neighbouring nodes beats equal loop lengths, 2.9 vs 6.6 ms)
+  uint32_t tile = 192;        // nodes per K2 tile = nodes per K1 unit (<= K2_NT - look-back window)
+  uint32_t slotcap = 10240;   // K2: successors a tile keeps in shared memory (words)
+  uint32_t rowcap = 128;      // K2: rows of K1 output a tile keeps in shared memory
+  uint32_t dbig = 1024;       // outdegree from which a node is resolved from global memory
+  uint32_t k1_blocks = 0;     // K1 grid; 0 = one block per SM
+  uint32_t refill = 6;        // K1: lanes that must be free before the warp fetches new nodes
+  uint32_t e2e_chunk = 1u << 19;  // nodes per chunk of the pipelined host entry point
 };
 static Tuning g_tuning;
 
 int set_tuning(const char* key, uint64_t value) {
   std::string k(key ? key : "");
-  if (k == "k1_span") g_tuning.k1_span = (uint32_t)value;
-  else if (k == "k1_tpb") g_tuning.k1_tpb = (uint32_t)value;
-  else if (k == "k2_blocks") g_tuning.k2_blocks = (uint32_t)value;
-  else if (k == "force_ovf") g_tuning.force_ovf = (uint32_t)value;
-  else if (k == "sort_degree") g_tuning.sort_degree = (uint32_t)value;
+  if (k == "tile") g_tuning.tile = (uint32_t)value;
+  else if (k == "slotcap") g_tuning.slotcap = (uint32_t)value;
+  else if (k == "rowcap") g_tuning.rowcap = (uint32_t)value;
+  else if (k == "dbig") g_tuning.dbig = (uint32_t)value;
+  else if (k == "k1_blocks") g_tuning.k1_blocks = (uint32_t)value;
+  else if (k == "refill") g_tuning.refill = (uint32_t)value;
   else if (k == "e2e_chunk") g_tuning.e2e_chunk = (uint32_t)value;
   else if (k == "reset") g_tuning = Tuning();
   else return WGA_E_ARG;
@@ -66,119 +73,126 @@ namespace {
 constexpr int TPB = 128;
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr uint32_t INF = 0xffffffffu;  // "stream exhausted"; successor ids are <= 0xfffffffe
+constexpr uint32_t NOT_FOUND = 0xFFFFFFFFu;
+
+// ---- K1 output: rows ------------------------------------------------------------------------------------
+constexpr uint32_t CH_SHIFT = 7, CH = 1u << CH_SHIFT;  // rows per chunk (16 KB)
+constexpr uint32_t MAXC = 512;                         // chunks per row stream (one stream per K1 warp)
+constexpr int K1_THREADS = 1024;
+constexpr uint32_t K1_WARPS = K1_THREADS / 32;
+constexpr uint32_t MAX_STREAMS = 8192;
+// record word of node t (uint2): x = first row of the record in its stream
+//                                y = words (24 bits) | lane << 24 | flags << 29
+constexpr uint32_t MF_ERR = 1u, MF_INSLOT = 2u, MF_FINAL = 4u;
+constexpr uint32_t NSYM_MAX = (1u << 24) - 1;
+// head word of node t (K0): reference offset in node-list positions (12 bits) | block count << 12
+constexpr uint32_t RT_BITS = 12, RT_MASK = (1u << RT_BITS) - 1, B_MAX = (1u << (32 - RT_BITS)) - 1;
+constexpr uint32_t DSOLO = 1024;  // residual runs at least this long are parked in the node's own slot, not in rows
 
 struct RangeView {
   uint64_t lo;        // first decoded node (halo start)
-  uint64_t first;     // first node the caller asked for
   uint32_t n;         // nodes decoded: last - lo
   const uint32_t* nodes;  // nullptr: node t is lo + t; else a sorted, duplicate-free list of node ids (random access)
   uint32_t h;         // halo nodes: first - lo
   uint32_t* outdeg;   // n+1
-  uint4* phase1;      // n : from K0: decoder (state, stream index) after the record's head, reference offset, block count
+  uint2* ph;          // n : decoder (state, stream index) after the record's head
+  uint32_t* rb;       // n : head word
   uint64_t* offs;     // n+1, relative to lo
-  uint64_t* meta;     // n : per-node record of K1 (see M_*)
-  uint32_t* arena;    // overflow headers (K1) and pass-2 temporaries
-  uint64_t arena_cap;
-  unsigned long long* cursor;
-  uint32_t* maxlevel; // deepest reference chain seen by k_levels (only tracked from LCAP up)
+  uint2* meta;        // n : record word of K1
+  uint8_t* hardflag;  // n : 0 resolved by its tile, 1 needs the global pass, 2 final without it
+  uint32_t* hard_list;  // nodes with hardflag 1
+  uint32_t* hard_lev;
+  uint32_t* hard_count;
+  uint32_t* maxlevel;   // deepest chain among the hard nodes
+  uint32_t* rows;       // row storage: chunk c = rows[c*CH*32 ...]
+  uint32_t rows_cap;    // chunks
+  uint32_t* chunk_ctr;
+  uint32_t* stream_chunks;  // [streams][MAXC]
+  uint32_t* unit_stream;    // [units]
+  uint32_t* unit_ctr;
+  uint32_t unit;        // nodes per unit (= K2 tile)
+  uint32_t n_units;
   uint32_t* halo_succ;  // successors of halo nodes
   uint64_t halo_cap;
   uint32_t* succ;       // caller's array: successors of nodes >= first
   uint64_t succ_cap;
   uint32_t* err;
-  unsigned long long* stats;  // optional debug counters (16 x u64), nullptr when disabled
 };
 
-// meta word written by K1:
-//   bits 0-15 reference offset r | bit 16 header in the overflow arena | bit 17 node is final after K1
-//   in-slot header: bits 19-33 block count b | 34-47 interval count | 48-63 residual count
-//   overflow header: bits 19-63 arena offset of {b, ni, nres, pairs offset, blocks...}
-constexpr uint64_t M_OVF = 1ull << 16, M_DIRECT = 1ull << 17;
-constexpr uint32_t MAX_B = 1u << 15, MAX_NI = 1u << 14, MAX_NRES = 1u << 16;
-constexpr uint32_t HS_WORDS = 16;  // in-slot headers are at most this many words (k_resolve caches them per lane)
-
-constexpr uint32_t NOT_FOUND = 0xFFFFFFFFu;
 // Index of the node referenced by node t with reference offset r (r != 0).  In a sorted duplicate-free
 // list the node (id - r) sits at most r positions before t.
-__device__ __forceinline__ uint32_t ref_index(const RangeView& rv, uint32_t t, uint32_t r) {
-  if (!rv.nodes) return r <= t ? t - r : NOT_FOUND;
-  const uint32_t id = rv.nodes[t];
+__device__ __forceinline__ uint32_t ref_index(const uint32_t* nodes, uint32_t t, uint32_t r) {
+  if (!nodes) return r <= t ? t - r : NOT_FOUND;
+  const uint32_t id = nodes[t];
   if (r > id) return NOT_FOUND;
   const uint32_t target = id - r;
   uint32_t lo = t >= r ? t - r : 0u, hi = t;
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
-    if (rv.nodes[mid] < target) lo = mid + 1; else hi = mid;
+    if (nodes[mid] < target) lo = mid + 1; else hi = mid;
   }
-  return (lo < t && rv.nodes[lo] == target) ? lo : NOT_FOUND;
+  return (lo < t && nodes[lo] == target) ? lo : NOT_FOUND;
 }
 
+// Final list of node t, or nullptr when it would not fit the destination (error set by the caller).
 __device__ __forceinline__ uint32_t* node_slot(const RangeView& rv, uint32_t t) {
-  uint64_t o = rv.offs[t];
-  if (t < rv.h) return rv.halo_succ + o;
-  return rv.succ + (o - rv.offs[rv.h]);
+  const uint64_t o = rv.offs[t], e = rv.offs[t + 1];
+  if (t < rv.h) return e <= rv.halo_cap ? rv.halo_succ + o : nullptr;
+  const uint64_t b = rv.offs[rv.h];
+  return e - b <= rv.succ_cap ? rv.succ + (o - b) : nullptr;
 }
 
-// Block -> node span [A,B) (indices relative to rv.lo).  Spans never straddle the halo boundary rv.h, so
-// that a span's successors are one contiguous piece of either halo_succ or succ.
-__host__ __device__ inline uint32_t span_count(uint32_t n, uint32_t h, uint32_t span) {
-  return (h + span - 1) / span + (n - h + span - 1) / span;
-}
-__device__ __forceinline__ void span_range(const RangeView& rv, uint32_t span, uint32_t blk, uint32_t& A, uint32_t& B) {
-  const uint32_t nbh = (rv.h + span - 1) / span;
-  if (blk < nbh) {
-    A = blk * span;
-    B = min(A + span, rv.h);
-  } else {
-    A = rv.h + (blk - nbh) * span;
-    B = (rv.n - A > span) ? A + span : rv.n;
-  }
-}
-// true (and error set) when the span's successors would not fit the destination
-__device__ __forceinline__ bool span_overflows(const RangeView& rv, uint32_t A, uint32_t B) {
-  if (A < rv.h) return rv.offs[B] > rv.halo_cap;
-  return rv.offs[B] - rv.offs[rv.h] > rv.succ_cap;
+// word k of a record that starts at (row0, lane) of row stream s
+__device__ __forceinline__ const uint32_t* row_word(const RangeView& rv, uint32_t s, uint32_t row, uint32_t lane) {
+  const uint32_t c = rv.stream_chunks[s * MAXC + (row >> CH_SHIFT)];
+  return rv.rows + ((size_t)c * CH + (row & (CH - 1))) * 32 + lane;
 }
 
 // (state, pointer) of node v: ANSBVGraphDecoderFactory::new_decoder (bvgraph_decoder_factory.rs:46-58)
-__device__ __forceinline__ void load_phase(const DevGraph& g, uint64_t v, uint32_t& state, int64_t& ptr,
-                                           uint32_t& err) {
-  state = g.states[g.top - v];
+__device__ __forceinline__ void load_phase(const DevGraph& g, uint64_t v, Dec& d, uint32_t& err) {
+  d.state = g.states[g.top - v];
   uint64_t p = g.ptrs[g.top - v] - g.stream_base;
   if (p > g.stream_words) { err |= ERR_CORRUPT; p = 0; }
-  ptr = (int64_t)p;
+  d.sp = (uint32_t)p;  // the resident span has < 2^32 words (checked at upload)
+  dec_prime(d, g.stream);
 }
 
 // -------------------------------------------------------------------------------------------- K0
-// One lane per node, every lane at the same symbol: the cheapest way to decode (about 110 G symbols/s on a B200,
-// against 45 G in the general state machine of K1).  So K0 decodes not only the outdegree but the whole
-// fixed-shape head of a record -- outdegree, reference offset, block count -- and hands K1 the decoder state
-// after it (phase1).  The block count is validated by K1, which knows the outdegree of the referenced node.
-__global__ void __launch_bounds__(TPB) k_outdegree(DevGraph g, uint64_t lo, const uint32_t* nodes, uint32_t n,
-                                                   uint32_t* outdeg, uint4* phase1, uint32_t* err_out) {
+// One lane per node, every lane at the same symbol: the fixed-shape head of a record -- outdegree, reference
+// offset, block count -- and the decoder state after it.  The block count is validated by K1, which knows the
+// outdegree of the referenced node.
+__global__ void __launch_bounds__(TPB) k_heads(DevGraph g, uint64_t lo, const uint32_t* nodes, uint32_t n,
+                                               uint32_t* outdeg, uint2* ph, uint32_t* rb, uint32_t* err_out) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n) return;
   if (t == n) { outdeg[n] = 0; return; }
+  const GlobalTables tab{g.tb.bkt, g.tb.ent};
   uint64_t v = nodes ? (uint64_t)nodes[t] : lo + t;
-  uint32_t state, err = 0;
-  int64_t ptr;
-  load_phase(g, v, state, ptr, err);
-  uint64_t d = ans_decode(g.tb, g.tb.lut, g.tb.ent, Outdegree, state, ptr, g.stream, err);
-  if (d > 0xFFFFFFFFull) err |= ERR_SYMBOL_WIDTH;
+  uint32_t err = 0;
+  Dec dc;
+  load_phase(g, v, dc, err);
+  uint64_t d = ans_decode(g.tb, tab, Outdegree, dc, g.stream, err);
+  if (d > 0xFFFFFFFEull) { err |= ERR_SYMBOL_WIDTH; d = 0; }
+  if (err) d = 0;
   outdeg[t] = (uint32_t)d;
-  if (phase1) {
-    uint32_t r = 0, b = 0;
-    if (d != 0 && g.window != 0 && !err) {
-      const uint64_t x = ans_decode(g.tb, g.tb.lut, g.tb.ent, ReferenceOffset, state, ptr, g.stream, err);
+  if (ph) {
+    uint32_t rt = 0, b = 0;
+    if (d != 0 && g.window != 0) {
+      const uint64_t x = ans_decode(g.tb, tab, ReferenceOffset, dc, g.stream, err);
       if (x > g.window) err |= ERR_CORRUPT;
-      r = (uint32_t)x;
-      if (r != 0 && !err) {
-        const uint64_t y = ans_decode(g.tb, g.tb.lut, g.tb.ent, BlockCount, state, ptr, g.stream, err);
-        if (y > 0xFFFFFFFFull) err |= ERR_CORRUPT;
-        b = (uint32_t)y;
+      else if (x != 0 && !err) {
+        const uint32_t ri = ref_index(nodes, t, (uint32_t)x);
+        if (ri == NOT_FOUND) err |= ERR_RANGE;  // the referenced node is not part of this decode
+        else {
+          const uint64_t y = ans_decode(g.tb, tab, BlockCount, dc, g.stream, err);
+          if (y > B_MAX) err |= (y > 0xFFFFFFFFull) ? ERR_CORRUPT : ERR_LIMIT;
+          else if (!err) { rt = t - ri; b = (uint32_t)y; }
+        }
       }
     }
-    phase1[t] = make_uint4(state, (uint32_t)ptr, r, b);
+    if (err) { rt = 0; b = 0; }
+    ph[t] = make_uint2(dc.state, dc.sp);
+    rb[t] = rt | (b << RT_BITS);
   }
   if (err) atomicOr(err_out, err);
 }
@@ -193,6 +207,7 @@ struct U32ToU64 {
 // reference offset) of up to 32 not-yet-inspected nodes.
 __global__ void k_halo(DevGraph g, uint64_t first, uint64_t last, uint64_t* lo_out, uint32_t* err_out) {
   const uint32_t lane = threadIdx.x;
+  const GlobalTables tab{g.tb.bkt, g.tb.ent};
   uint64_t lo = first;
   uint64_t chk_lo = first;
   uint64_t chk_hi = first + g.window < last ? first + g.window : last;
@@ -203,12 +218,11 @@ __global__ void k_halo(DevGraph g, uint64_t first, uint64_t last, uint64_t* lo_o
       uint64_t v = base + lane;
       uint64_t mine = lo;
       if (v < chk_hi) {
-        uint32_t state;
-        int64_t ptr;
-        load_phase(g, v, state, ptr, err);
-        uint64_t d = ans_decode(g.tb, g.tb.lut, g.tb.ent, Outdegree, state, ptr, g.stream, err);
-        if (d != 0 && g.window != 0) {
-          uint64_t r = ans_decode(g.tb, g.tb.lut, g.tb.ent, ReferenceOffset, state, ptr, g.stream, err);
+        Dec dc;
+        load_phase(g, v, dc, err);
+        uint64_t d = ans_decode(g.tb, tab, Outdegree, dc, g.stream, err);
+        if (d != 0 && g.window != 0 && !err) {
+          uint64_t r = ans_decode(g.tb, tab, ReferenceOffset, dc, g.stream, err);
           if (r > v) err |= ERR_CORRUPT;
           else if (v - r < mine) mine = v - r;
         }
@@ -231,41 +245,32 @@ __global__ void k_halo(DevGraph g, uint64_t first, uint64_t last, uint64_t* lo_o
 }
 
 // -------------------------------------------------------------------------------------------- K1
-// Pseudo components of the per-lane state machine (0..8 are the BVGraphComponent values, mod.rs:46-61).
-enum : uint32_t { C_AFTER_BLOCKS = 9, C_FINISH = 10, C_FETCH = 11, C_IDLE = 12 };
+// Shared-memory tables of the entropy kernel: all buckets of the six components it decodes, and as many
+// entries per component as fit (the first ones: small symbols are the frequent ones); the rest is read from
+// global memory through the same generic load.
+struct K1Tables {
+  uint4 cp[WGA_COMPONENTS];       // x = mask | L << 16 | R << 21, y = smem bucket offset, z = smem entry offset, w = hot entries
+  uint32_t gent_off[WGA_COMPONENTS];  // global entry offset
+  uint32_t bkt_words;             // uint2 elements
+  uint32_t ent_words;
+};
 
-// Moves the header of a node (kb block lengths, kp interval pairs already parked in the slot) to a
-// record in the overflow arena.  Returns false when the arena is full.
-__device__ __noinline__ bool header_to_arena_impl(uint32_t* arena, uint64_t arena_cap, unsigned long long* cursor,
-                                                  const uint32_t* slot, uint32_t b, uint32_t kb, uint32_t ni,
-                                                  uint32_t kp, uint32_t* ao_out) {
-  const unsigned long long need = 4ull + b + 2ull * ni;
-  const unsigned long long o = atomicAdd(cursor, need);
-  if (o + need > arena_cap || o + need >= 0xFFFFFFFFull) return false;
-  const uint32_t ao = (uint32_t)o;
-  const uint32_t apo = ao + 4 + b;
-  *ao_out = ao;
-  uint32_t* rec = arena + ao;
-  rec[0] = b;
-  rec[1] = ni;
-  rec[2] = 0;
-  rec[3] = apo;
-  const uint16_t* s16 = reinterpret_cast<const uint16_t*>(slot);
-  for (uint32_t i = 0; i < kb; ++i) rec[4 + i] = s16[i];
-  const uint32_t hb = (b + 1) >> 1;
-  for (uint32_t i = 0; i < 2 * kp; ++i) arena[apo + i] = slot[hb + i];
-  return true;
-}
-__device__ __forceinline__ bool header_to_arena(const RangeView& rv, const uint32_t* slot, uint32_t b, uint32_t kb,
-                                                uint32_t ni, uint32_t kp, uint32_t& ao, uint32_t& apo) {
-  uint32_t a = 0;
-  const bool ok = header_to_arena_impl(rv.arena, rv.arena_cap, rv.cursor, slot, b, kb, ni, kp, &a);
-  ao = a;
-  apo = a + 4 + b;
-  return ok;
-}
+struct SmemTables {
+  const uint2* bkt;   // shared
+  const uint2* ent;   // shared (hot prefix of every component)
+  const uint2* gent;  // global
+  const uint32_t* gent_off;  // shared copy
+  const uint32_t* recip_tab;  // shared: floor(65536/R)+1
+  __device__ __forceinline__ uint2 bucket(uint32_t i) const { return bkt[i]; }
+  __device__ __forceinline__ uint2 entry(const uint4& cp, uint32_t off, uint32_t j) const {
+    if (j < cp.w) return ent[off + j];
+    return __ldg(gent + gent_off[(cp.x >> 26)] + j);
+  }
+  __device__ __forceinline__ uint32_t recip(const uint4& cp) const { return recip_tab[(cp.x >> 21) & 31u]; }
+};
 
-constexpr uint32_t SOLO_RUN = 2048;  // residual runs at least this long are finished in a tight loop of their own
+// per-lane machine states: the component being decoded (3..8 = BVGraphComponent, mod.rs:46-61) or one of
+enum : uint32_t { C_FETCH = 9, C_IDLE = 10 };
 
 // node + nat2int(x) in 32-bit arithmetic (ids are < 2^32, so a valid x is < 2^33); false on leaving [0, 2^32-2]
 __device__ __forceinline__ bool add_nat(uint32_t v, uint64_t x, uint32_t& out) {
@@ -277,494 +282,551 @@ __device__ __forceinline__ bool add_nat(uint32_t v, uint64_t x, uint32_t& out) {
 
 // LIST: node t is rv.nodes[t] (random access) instead of rv.lo + t.
 template <bool LIST>
-__global__ void __launch_bounds__(128) k_entropy(DevGraph g, RangeView rv, uint32_t span, uint32_t force_ovf) {
-  __shared__ uint32_t s_next;
-  __shared__ uint4 s_cp[WGA_COMPONENTS];
-  uint32_t A, Bn;
-  span_range(rv, span, blockIdx.x, A, Bn);
-  if (span_overflows(rv, A, Bn)) {
-    if (threadIdx.x == 0) atomicOr(rv.err, ERR_WORKSPACE);
-    return;
+__global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView rv, K1Tables kt, uint32_t refill_min) {
+  extern __shared__ __align__(16) unsigned char k1_smem[];
+  uint4* s_cp = reinterpret_cast<uint4*>(k1_smem);                        // 9 x 16 B
+  uint32_t* s_goff = reinterpret_cast<uint32_t*>(k1_smem + 9 * 16);       // 9 (+ pad to 12)
+  uint32_t* s_recip = s_goff + 12;                                         // 32
+  uint2* s_bkt = reinterpret_cast<uint2*>(s_recip + 32);
+  uint2* s_ent = s_bkt + kt.bkt_words;
+  {
+    if (threadIdx.x < WGA_COMPONENTS) {
+      uint4 c = kt.cp[threadIdx.x];
+      c.x |= threadIdx.x << 26;  // component index for the cold-entry path
+      s_cp[threadIdx.x] = c;
+      s_goff[threadIdx.x] = kt.gent_off[threadIdx.x];
+    }
+    if (threadIdx.x < 32) s_recip[threadIdx.x] = 65536u / (threadIdx.x ? threadIdx.x : 1u) + 1u;
+    // buckets and hot entries of components 3..8, laid out as kt.cp says
+    for (int c = Blocks; c <= Residual; ++c) {
+      const uint4 cp = kt.cp[c];
+      const uint32_t nb = g.tb.nb[c];
+      for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) s_bkt[cp.y + i] = g.tb.bkt[g.tb.bkt_off[c] + i];
+      for (uint32_t i = threadIdx.x; i < cp.w; i += blockDim.x) s_ent[cp.z + i] = g.tb.ent[g.tb.ent_off[c] + i];
+    }
   }
-  if (threadIdx.x == 0) s_next = A;
-  if (threadIdx.x < WGA_COMPONENTS) s_cp[threadIdx.x] = comp_params(g.tb, threadIdx.x);
   __syncthreads();
-  const uint16_t* lut = g.tb.lut;
-  const uint2* ent = g.tb.ent;
-  const uint32_t c_extras = g.min_interval ? (uint32_t)IntervalCount : (uint32_t)FirstResidual;
+  const SmemTables tab{s_bkt, s_ent, g.tb.ent, s_goff, s_recip};
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t stream_id = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
   const uint32_t minint = g.min_interval;
-  const uint32_t window = g.window;
-  // slot of node t = base + offs[t] (spans never straddle the halo boundary)
-  uint32_t* const slot_base = A < rv.h ? rv.halo_succ : rv.succ - rv.offs[rv.h];
-  // phases of node v: states[top - v], ptrs[top - v] (file order is reversed, bvgraph_decoder_factory.rs:49-50)
-  const uint32_t* const states_top = g.states + g.top;
-  const uint64_t* const ptrs_top = g.ptrs + g.top;
+  const uint32_t c_extras = minint ? (uint32_t)IntervalCount : (uint32_t)FirstResidual;
   const uint32_t lo32 = (uint32_t)rv.lo;
 
-  // per-lane record state
-  uint32_t c = C_FETCH, t = 0, state = 0, sp = 0, v = 0, prev = 0, d = 0, r = 0, dref = 0, b = 0, k = 0, copied = 0,
-           pos = 0, extras = 0, ni = 0, hb = 0, nres = 0, ao = 0, apo = 0;
-  uint32_t* slot = nullptr;
-  uint32_t* wp = nullptr;
-  bool ovf = false, direct = false;
+  // warp-uniform
+  uint32_t nx = 0, ne = 0;      // nodes [nx, ne) of the current unit are not yet handed out
+  bool exhausted = false;
+  uint32_t row = 0;             // rows written so far by this warp
+  uint32_t* rowp = nullptr;     // row `row` of the stream, this lane's word
+  bool rows_ok = true;
 
-  // Every lane stays in the loop until the whole warp has run out of nodes: the vote at the top is the
-  // per-iteration reconvergence point, so that the symbol decode below runs with all busy lanes together.
-  // Each case computes an error flag instead of leaving early, which keeps the cases short and single-exit.
+  // per-lane record state
+  uint32_t c = C_FETCH, t = 0, v = 0, prev = 0, d = 0, dref = 0, k = 0, b = 0, copied = 0, pos = 0, extras = 0, ni = 0,
+           row0 = 0, ns = 0, flags = 0;
+  uint32_t* wp = nullptr;  // residuals parked in the node's own slot (MF_INSLOT)
+  Dec dc{0, 0, 0};
+
   for (;;) {
     uint32_t err = 0;
-    if (c == C_FETCH) {
-      t = atomicAdd(&s_next, 1u);
-      if (t >= Bn) c = C_IDLE;
-      else {
-        v = LIST ? rv.nodes[t] : lo32 + t;
-        const uint4 ph = rv.phase1[t];  // K0 left the decoder after the head: outdegree, reference offset, block count
-        state = ph.x;
-        sp = ph.y;  // the resident span has < 2^32 words (checked at upload)
-        r = ph.z;
-        b = ph.w;
-        d = rv.outdeg[t];
-        extras = d;
-        ni = copied = nres = pos = k = 0;
-        hb = (b + 1) >> 1;
-        ovf = false;
-        direct = d == 0;
-        if (d == 0) c = C_FINISH;
-        else {
-          slot = slot_base + rv.offs[t];
-          if (r == 0) c = c_extras;
+    bool finish = false;
+    // ---------------------------------------------------------------- hand out nodes
+    {
+      const uint32_t nf = __ballot_sync(FULL, c == C_FETCH);
+      const uint32_t busy = __ballot_sync(FULL, c < C_FETCH);
+      if (nf && (busy == 0 || (uint32_t)__popc(nf) >= refill_min)) {
+        if (nx >= ne && !exhausted) {
+          uint32_t u = 0;
+          if (lane == 0) u = atomicAdd(rv.unit_ctr, 1u);
+          u = __shfl_sync(FULL, u, 0);
+          if (u >= rv.n_units) exhausted = true;
           else {
-            const uint32_t ri = LIST ? ref_index(rv, t, r) : (r <= t ? t - r : NOT_FOUND);
-            if (ri == NOT_FOUND) err |= ERR_RANGE;  // the referenced node is not part of this decode
+            nx = u * rv.unit;
+            ne = min(nx + rv.unit, rv.n);
+            if (lane == 0) rv.unit_stream[u] = stream_id;
+          }
+        }
+        if (c == C_FETCH) {
+          const uint32_t my = nx + (uint32_t)__popc(nf & lt_mask);
+          if (exhausted) c = C_IDLE;
+          else if (my < ne) {
+            t = my;
+            const uint2 p = rv.ph[t];
+            const uint32_t rbw = rv.rb[t];
+            d = rv.outdeg[t];
+            v = LIST ? rv.nodes[t] : lo32 + t;
+            dc.state = p.x;
+            dc.sp = p.y;
+            row0 = row;
+            ns = 0;
+            flags = 0;
+            ni = 0;
+            wp = nullptr;
+            if (d == 0) finish = true;
             else {
-              dref = rv.outdeg[ri];
-              if (b > dref && b - dref > 1u) err |= ERR_CORRUPT;  // at most dref + 1 blocks
-              else if (b == 0) { copied = dref; c = C_AFTER_BLOCKS; }
+              dec_prime(dc, g.stream);
+              const uint32_t rt = rbw & RT_MASK;
+              b = rbw >> RT_BITS;
+              if (rt == 0) { extras = d; c = c_extras; }
               else {
-                if (hb > d || hb > HS_WORDS || b >= MAX_B || dref > 0xFFFFu || force_ovf) {
-                  if (header_to_arena(rv, slot, b, 0, 0, 0, ao, apo)) ovf = true;
-                  else err |= ERR_WORKSPACE;
-                }
-                c = Blocks;
+                dref = rv.outdeg[t - rt];
+                if (b > dref && b - dref > 1u) err |= ERR_CORRUPT;  // at most dref + 1 blocks
+                else if (b == 0) {
+                  if (dref > d) err |= ERR_CORRUPT;
+                  else { extras = d - dref; if (extras) c = c_extras; else finish = true; }
+                } else { k = b; pos = 0; copied = 0; c = Blocks; }
               }
+              if (rt) flags |= 8u;  // (internal) the node has a reference
             }
           }
         }
+        nx = min(ne, nx + (uint32_t)__popc(nf));
       }
     }
     if (__all_sync(FULL, c == C_IDLE)) break;
-    if (c <= Residual) {
-      const uint64_t x = ans_decode_cp(s_cp[c], lut, ent, state, sp, g.stream, err);
+    // ---------------------------------------------------------------- one symbol per busy lane
+    const bool decoding = c < C_FETCH && !err && !finish;
+    uint32_t val = 0;
+    if (decoding) {
+      const uint64_t x = ans_decode_cp(s_cp[c], tab, dc, g.stream, err);
       const uint32_t xl = (uint32_t)x;
       const bool wide = (x >> 32) != 0;  // only nat2int arguments (first residual / interval start) may need 33 bits
-      if (c >= FirstResidual) {
-        // ---- residuals: value = node + nat2int(x) | previous + 1 + x   (most frequent symbols)
-        uint32_t val;
-        bool ok;
-        if (c == FirstResidual) {
-          nres = extras;
-          direct = (r == 0 && ni == 0);
-          if (!direct && !ovf && (nres >= MAX_NRES || hb + 2ull * ni > (uint64_t)(d - nres))) {
-            if (header_to_arena(rv, slot, b, b, ni, ni, ao, apo)) ovf = true;
-            else err |= ERR_WORKSPACE;
-          }
-          wp = slot + (d - nres);
-          ok = add_nat(v, x, val);
-        } else {
-          val = prev + 1u + xl;
-          ok = !wide && val > prev && val != 0xFFFFFFFFu;
-        }
-        if (!ok) err |= ERR_SYMBOL_WIDTH;
-        if (!err) {
-          prev = val;
-          *wp++ = val;
-          c = --extras ? (uint32_t)Residual : (uint32_t)C_FINISH;
-        }
-        // A long residual run is one serial chain and ends up as the last thing the kernel waits for (hubs
-        // of social graphs: 10^5 gaps): finish it in a loop of its own, whose body is only the symbol decode
-        // and the prefix sum, instead of one pass through the whole state machine per gap.
-        if (!err && c == Residual && extras >= SOLO_RUN) {
-          const uint4 cpr = s_cp[Residual];
-          while (extras) {
-            uint32_t e2 = 0;
-            const uint64_t y = ans_decode_cp(cpr, lut, ent, state, sp, g.stream, e2);
-            const uint32_t nv = prev + 1u + (uint32_t)y;
-            if (e2 || (y >> 32) || nv <= prev || nv == 0xFFFFFFFFu) { err |= e2 ? e2 : ERR_SYMBOL_WIDTH; break; }
-            prev = nv;
-            *wp++ = nv;
-            --extras;
-          }
-          if (!err) c = C_FINISH;
-        }
-      } else if (c == Blocks) {
-        const uint32_t len = xl + (k != 0);
-        if (wide || len > dref - pos || len < xl) err |= ERR_CORRUPT;
-        if (!err) {
-          if (ovf) rv.arena[ao + 4 + k] = len;
-          else reinterpret_cast<uint16_t*>(slot)[k] = (uint16_t)len;
-          if ((k & 1) == 0) copied += len;
+      switch (c) {
+        case Blocks: {
+          const uint32_t len = xl + ((k != b) ? 1u : 0u);  // first block literal, later ones minus 1
+          if (wide || len < xl || len > dref - pos) { err |= ERR_CORRUPT; break; }
+          const uint32_t done = b - k;  // blocks before this one: even = copy block
+          if ((done & 1u) == 0) copied += len;
           pos += len;
-          if (++k == b) {
-            if ((b & 1) == 0) copied += dref - pos;
-            c = C_AFTER_BLOCKS;
+          val = pos;  // cumulative end
+          if (--k == 0) {
+            if ((b & 1u) == 0) copied += dref - pos;  // even count: the tail is copied too
+            if (copied > d) { err |= ERR_CORRUPT; break; }
+            extras = d - copied;
+            if (extras) c = c_extras; else finish = true;
           }
+          break;
         }
-      } else if (c >= IntervalStart) {
-        if (c == IntervalStart) {
-          uint32_t val;
+        case IntervalCount: {
+          if (wide || xl > extras || (uint64_t)xl * minint > extras) { err |= ERR_CORRUPT; break; }
+          ni = xl;
+          val = xl;
+          k = 0;
+          c = ni ? (uint32_t)IntervalStart : (uint32_t)FirstResidual;
+          break;
+        }
+        case IntervalStart: {
           bool ok;
           if (k == 0) ok = add_nat(v, x, val);
           else { val = prev + 1u + xl; ok = !wide && val > prev && val != 0xFFFFFFFFu; }  // prev: end of the last one
-          if (!ok) err |= ERR_SYMBOL_WIDTH;
-          if (!err) {
-            prev = val;  // start of this interval
-            if (ovf) rv.arena[apo + 2 * k] = val;
-            else slot[hb + 2 * k] = val;
-            c = IntervalLen;
-          }
-        } else {
+          if (!ok) { err |= ERR_SYMBOL_WIDTH; break; }
+          prev = val;
+          c = IntervalLen;
+          break;
+        }
+        case IntervalLen: {
           const uint32_t len = xl + minint;
-          if (wide || len < xl || len > extras || len == 0) err |= ERR_CORRUPT;
           const uint32_t end = prev + len;  // one past the end of this interval
-          if (end < prev) err |= ERR_SYMBOL_WIDTH;
-          if (!err) {
-            prev = end;
-            if (ovf) rv.arena[apo + 2 * k + 1] = len;
-            else slot[hb + 2 * k + 1] = len;
-            extras -= len;
-            if (++k == ni) c = extras ? (uint32_t)FirstResidual : (uint32_t)C_FINISH;
-            else c = IntervalStart;
-          }
+          if (wide || len < xl || len > extras || len == 0) { err |= ERR_CORRUPT; break; }
+          if (end < prev) { err |= ERR_SYMBOL_WIDTH; break; }
+          val = len;
+          prev = end;
+          extras -= len;
+          if (++k == ni) { if (extras) c = FirstResidual; else finish = true; }
+          else c = IntervalStart;
+          break;
         }
-      } else {  // IntervalCount
-        if (wide || xl > extras) err |= ERR_CORRUPT;
-        if (!err) {
-          ni = xl;
-          k = 0;
-          if (ni == 0) c = FirstResidual;
-          else {
-            if (ovf) {  // header already in the arena: the pairs get their own piece
-              const unsigned long long o = atomicAdd(rv.cursor, 2ull * ni);
-              if (o + 2ull * ni > rv.arena_cap || o + 2ull * ni >= 0xFFFFFFFFull) err |= ERR_WORKSPACE;
-              else { apo = (uint32_t)o; rv.arena[ao + 3] = apo; }
-            } else if (ni >= MAX_NI || hb + 2ull * ni > d || hb + 2ull * ni > HS_WORDS || force_ovf) {
-              if (header_to_arena(rv, slot, b, b, ni, 0, ao, apo)) ovf = true;
-              else err |= ERR_WORKSPACE;
-            }
-            c = IntervalStart;
+        case FirstResidual: {
+          if (!add_nat(v, x, val)) { err |= ERR_SYMBOL_WIDTH; break; }
+          prev = val;
+          if (extras >= DSOLO) {  // long run: park it at the tail of the node's own slot
+            uint32_t* slot = node_slot(rv, t);
+            if (!slot) { err |= ERR_WORKSPACE; break; }
+            wp = slot + (d - extras);
+            flags |= MF_INSLOT;
+            if (!(flags & 8u) && ni == 0) flags |= MF_FINAL;  // no reference, no interval: the slot is the final list
           }
+          if (--extras) c = Residual; else finish = true;
+          break;
+        }
+        default: {  // Residual
+          val = prev + 1u + xl;
+          if (wide || val <= prev || val == 0xFFFFFFFFu) { err |= ERR_SYMBOL_WIDTH; break; }
+          prev = val;
+          if (--extras == 0) finish = true;
+          break;
         }
       }
     }
-    if (c == C_AFTER_BLOCKS && !err) {
-      if (copied > d) err |= ERR_CORRUPT;
-      else {
-        extras = d - copied;
-        c = extras ? c_extras : (uint32_t)C_FINISH;
+    // ---------------------------------------------------------------- one coalesced row
+    const bool have = decoding && !err;
+    const bool to_row = have && wp == nullptr;
+    if (have && wp != nullptr) *wp++ = val;
+    if (__any_sync(FULL, to_row)) {
+      if ((row & (CH - 1)) == 0) {  // new chunk
+        uint32_t cid = 0;
+        if (lane == 0) {
+          cid = atomicAdd(rv.chunk_ctr, 1u);
+          if (cid < rv.rows_cap && (row >> CH_SHIFT) < MAXC) rv.stream_chunks[stream_id * MAXC + (row >> CH_SHIFT)] = cid;
+          else { cid = 0xFFFFFFFFu; atomicOr(rv.err, ERR_WORKSPACE); }
+        }
+        cid = __shfl_sync(FULL, cid, 0);
+        rows_ok = cid != 0xFFFFFFFFu;
+        rowp = rv.rows + (size_t)(rows_ok ? cid : 0u) * CH * 32 + lane;
       }
+      if (to_row && rows_ok) *rowp = val;
+      if (to_row) ++ns;
+      rowp += 32;
+      ++row;
     }
-    if (err) {  // the record is inconsistent: leave the node out of phase two and report
+    // ---------------------------------------------------------------- end of a record
+    if (err) {
       atomicOr(rv.err, err);
-      rv.meta[t] = M_DIRECT;
+      rv.meta[t] = make_uint2(0u, (lane << 24) | (MF_ERR << 29));
       c = C_FETCH;
-    } else if (c == C_FINISH) {
-      uint64_t m;
-      if (direct) m = M_DIRECT;
-      else if (ovf) {
-        rv.arena[ao + 1] = ni;
-        rv.arena[ao + 2] = nres;
-        m = (uint64_t)r | M_OVF | ((uint64_t)ao << 19);
-      } else {
-        m = (uint64_t)r | ((uint64_t)b << 19) | ((uint64_t)ni << 34) | ((uint64_t)nres << 48);
-      }
-      rv.meta[t] = m;
+    } else if (finish) {
+      if (ns > NSYM_MAX) { atomicOr(rv.err, ERR_LIMIT); flags |= MF_ERR; }
+      rv.meta[t] = make_uint2(row0, (ns & NSYM_MAX) | (lane << 24) | ((flags & 7u) << 29));
       c = C_FETCH;
     }
   }
 }
 
-// -------------------------------------------------------------------------------------------- K2
-// Phase two: copy-block resolution + interval expansion + merge, by reference-chain depth.
-//   k_levels   depth[v] = ref ? depth[v-ref]+1 : 0 for every node that still needs work, and a 12-bit sort
-//              key (level bucket, degree bucket descending)
-//   cub sort   nodes ordered by key: one contiguous segment per level, inside it nodes of similar degree
-//              next to each other, so that the 32 lanes of a warp run merge loops of similar length
-//   k_resolve  one launch per level; one node per lane: a tight three-way merge of (copied elements of the
-//              finished referenced list, expanded intervals, residuals) written in place into the node's
-//              CSR slot.  The parked residuals sit at the tail of the slot and are consumed before the write
-//              pointer reaches them; the parked header is first copied to shared memory.
-constexpr uint32_t HS = 16;       // in-slot header words (u16 block lengths + interval pairs) a lane caches
-constexpr uint32_t LCAP = 6;      // levels 0..LCAP-1 have their own segment; deeper nodes share segment LCAP
-constexpr uint32_t KEY_SKIP = 15; // level bucket of nodes that are final after K1
-constexpr uint32_t KEY_BIG0 = 13; // level bucket of long reference-free records with intervals (k_resolve_big0)
-constexpr uint32_t BIG0_DEGREE = 4096;   // outdegree from which a level-0 record takes the cooperative path
-constexpr uint32_t BIG0_MAX_NI = 3072;   // intervals the cooperative path keeps in shared memory (3 x 12 KB static)
-constexpr int RES_TPB = 128;
+// -------------------------------------------------------------------------------------------- K2: tile kernel
+constexpr int K2_NT = 256;
+constexpr uint32_t HMAX = 64;    // look-back window of a tile (nodes before it that it may have to re-resolve)
+constexpr uint32_t LMAXT = 8;    // deepest reference chain a tile resolves
+constexpr uint32_t NCLS = 8, NBINS = (LMAXT + 1) * NCLS;
+constexpr uint32_t HRECCAP = 1536;  // words of look-back records staged in shared memory
 
-__device__ __forceinline__ uint32_t degree_bucket(uint32_t d) {  // monotone, 0..227
-  if (d < 128) return d;
-  const uint32_t lg = 31u - (uint32_t)__clz((int)d);
-  return 128u + (lg - 7u) * 4u + ((d >> (lg - 2u)) & 3u);
+__device__ __forceinline__ uint32_t d_class(uint32_t d) {  // 0 = largest
+  return d > 96 ? 0u : d > 64 ? 1u : d > 48 ? 2u : d > 32 ? 3u : d > 16 ? 4u : d > 8 ? 5u : d > 4 ? 6u : 7u;
 }
 
-__global__ void __launch_bounds__(256) k_levels(RangeView rv, uint16_t* keys, uint32_t* vals, uint32_t* lev_out,
-                                                uint32_t* hist, uint32_t sort_degree) {
-  __shared__ uint32_t s_hist[16];
-  if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t lev = 0;
-  if (t < rv.n) {
-    const uint64_t m = rv.meta[t];
-    uint32_t lb = KEY_SKIP;
-    if (!(m & M_DIRECT)) {
-      uint32_t u = t, r = (uint32_t)(m & 0xFFFFu);
-      while (r) {  // chain of referenced nodes (a node that is final after K1 has no reference)
-        u = ref_index(rv, u, r);
-        ++lev;
-        r = (uint32_t)(rv.meta[u] & 0xFFFFu);
-      }
-      lb = min(lev, LCAP);
-      lev_out[t] = lev;
-      if (lev == 0 && rv.outdeg[t] >= BIG0_DEGREE) {  // one lane would merge this list element by element
-        const uint32_t ni = (m & M_OVF) ? rv.arena[(uint32_t)(m >> 19) + 1] : (uint32_t)(m >> 34) & (MAX_NI - 1);
-        if (ni <= BIG0_MAX_NI) lb = KEY_BIG0;
+struct TileCfg {
+  uint32_t tile, slotcap, rowcap, dbig;
+};
+
+// word k of a record in shared memory (the tile's rows: stride 32; staged look-back records: stride 1)
+struct SmemRec {
+  const uint32_t* p;
+  uint32_t stride;
+  __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return p[k * stride]; }
+};
+// word k of a record in global memory (chunks are not contiguous)
+struct GlobalRec {
+  const RangeView* rv;
+  uint32_t s, r0, ln;
+  __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return *row_word(*rv, s, r0 + k, ln); }
+};
+
+// One successor list: merge of (copied elements of the finished referenced list, expanded intervals, residuals).
+//   rec(k) = word k of the node's K1 record: [cumulative copy-block ends x b][interval count][start,len x ni][residuals]
+// inslot: the residuals are not in the record but parked at the tail of `out` (MF_INSLOT); they are consumed before
+// the write position reaches them (written <= copied + interval elements + residuals consumed).
+template <class Rec>
+__device__ __forceinline__ void merge_list(uint32_t* __restrict__ out, uint32_t d, const uint32_t* __restrict__ ref,
+                                           uint32_t dref, uint32_t b, uint32_t ns, uint32_t minint, const Rec rec,
+                                           bool inslot) {
+  // ---- layout of the record
+  uint32_t idx = b, ni = 0;
+  if (ns > b && minint) ni = rec(idx++);
+  uint32_t ip = idx, iend = idx + 2 * ni;  // interval pairs
+  uint32_t rp = iend, rend = ns;           // residuals
+  if (ns < b || 2 * (uint64_t)ni > (uint64_t)(ns - idx)) { ni = 0; ip = iend = rp = rend = 0; b = 0; }  // inconsistent record
+  const uint32_t* tail = nullptr;
+  if (inslot) {  // parked residuals: d - copied - interval elements of them
+    uint64_t used = 0;
+    for (uint32_t q = 0; q < ni; ++q) used += rec(ip + 2 * q + 1);
+    if (ref) {
+      if (b == 0) used += dref;
+      else {
+        uint32_t prev = 0;
+        for (uint32_t q = 0; q < b; ++q) { const uint32_t e = rec(q); if ((q & 1u) == 0) used += e - prev; prev = e; }
+        if ((b & 1u) == 0) used += dref - prev;
       }
     }
-    keys[t] = (uint16_t)((lb << 8) | (sort_degree ? 255u - degree_bucket(rv.outdeg[t]) : 0u));
-    vals[t] = t;
-    atomicAdd(&s_hist[lb], 1u);
+    if (used > d) return;  // K1 checked this
+    rend = d;
+    rp = (uint32_t)used;  // index into out
+    tail = out;
+  }
+  // ---- heads of the three runs
+  uint32_t ci = 0, cend = 0, kb = 0, cval = INF;
+  auto next_copy_block = [&]() {  // after copy block kb (even): skip block kb+1, copy block kb+2
+    for (;;) {
+      kb += 2;
+      if (kb - 1 < b) { ci = rec(kb - 1); cend = kb < b ? rec(kb) : dref; }
+      else { ci = cend = dref; cval = INF; return; }
+      if (cend > dref) cend = dref;
+      if (ci < cend) { cval = ref[ci]; return; }
+    }
+  };
+  if (ref) {
+    cend = b ? min(rec(0), dref) : dref;
+    if (ci < cend) cval = ref[0]; else next_copy_block();
+  }
+  uint32_t ival = INF, ilim = 0;
+  if (ni) { ival = rec(ip); ilim = ival + rec(ip + 1); ip += 2; }
+  uint32_t rval = INF;
+  if (rp < rend) rval = tail ? tail[rp] : rec(rp);
+  // ---- merge
+  for (uint32_t p = 0; p < d; ++p) {
+    const uint32_t mn = min(cval, min(ival, rval));
+    if (mn == cval) {
+      if (++ci < cend) cval = ref[ci]; else next_copy_block();
+    } else if (mn == rval) {
+      rval = ++rp < rend ? (tail ? tail[rp] : rec(rp)) : INF;
+    } else {
+      if (++ival == ilim) {
+        if (ip < iend) { ival = rec(ip); ilim = ival + rec(ip + 1); ip += 2; } else ival = INF;
+      }
+    }
+    out[p] = mn;  // after the heads moved on: out[p] may be the parked residual that was just read
+  }
+}
+
+__global__ void __launch_bounds__(K2_NT) k_tile(RangeView rv, TileCfg cfg, uint32_t minint, uint32_t lookback) {
+  extern __shared__ __align__(16) uint32_t k2_smem[];
+  uint32_t* const s_slots = k2_smem;                             // slotcap + 8
+  uint32_t* const s_rows = s_slots + cfg.slotcap + 8;            // rowcap * 32
+  uint32_t* const s_hrec = s_rows + cfg.rowcap * 32;             // HRECCAP
+  uint32_t* const s_d = s_hrec + HRECCAP;                        // per candidate: outdegree
+  uint32_t* const s_so = s_d + K2_NT;                            //   slot offset
+  uint32_t* const s_rb = s_so + K2_NT;                           //   head word
+  uint32_t* const s_row0 = s_rb + K2_NT;                         //   record: first row
+  uint32_t* const s_my = s_row0 + K2_NT;                         //   record: words | lane << 24 | flags << 29
+  uint32_t* const s_hro = s_my + K2_NT;                          //   look-back record: offset in s_hrec, or INF = global
+  uint32_t* const s_st = s_hro + K2_NT;                          //   bit 0 big, 1 hard, 2 part, 3 need ; level << 8
+  uint32_t* const s_order = s_st + K2_NT;                        // tasks by (level, outdegree class)
+  uint32_t* const s_bin = s_order + K2_NT;                       // NBINS + 1
+  uint32_t* const s_binbase = s_bin + NBINS + 8;                 // NBINS + 1
+  __shared__ uint32_t s_scal[8];  // 0 total slots, 1 rmin, 2 rmax, 3 hrec used, 4 maxlev, 5 holes, 6 limit, 7 retry
+  typedef cub::BlockScan<uint32_t, K2_NT> BlockScan;
+  __shared__ typename BlockScan::TempStorage s_scan;
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t A = blockIdx.x * cfg.tile, B = min(A + cfg.tile, rv.n);
+  const uint32_t my_stream = rv.unit_stream[blockIdx.x];
+
+  for (uint32_t a = A; a < B;) {
+    const uint32_t C0 = a > lookback ? a - lookback : 0u;
+    const uint32_t own0 = a - C0;
+    uint32_t limit = B;  // owned nodes of this round: [a, limit)
+    uint32_t M, total_slots;
+    bool fits;
+    // -------------------------------------------------------------- descriptors (one candidate per thread)
+    uint32_t d = 0, rbw = 0, big = 0, lev = 0, hard = 0;
+    uint2 m = make_uint2(0, 0);
+    const uint32_t t = C0 + tid;
+    if (t < B) {
+      d = rv.outdeg[t];
+      rbw = rv.rb[t];
+      m = rv.meta[t];
+      const uint32_t fl = m.y >> 29;
+      big = (d >= cfg.dbig || 2u * (m.y & NSYM_MAX) > cfg.rowcap || fl != 0) ? 1u : 0u;
+      s_d[tid] = d;
+      s_rb[tid] = rbw;
+      s_row0[tid] = m.x;
+      s_my[tid] = m.y;
+    }
+    s_st[tid] = big;
+    if (tid < 8) s_scal[tid] = 0;
+    __syncthreads();
+    // -------------------------------------------------------------- reference chains: depth, hardness, needed look-back nodes
+    if (t < B) {
+      hard = big;
+      uint32_t j = tid;
+      while (!hard) {
+        const uint32_t rt = s_rb[j] & RT_MASK;
+        if (rt == 0) break;
+        if (rt > j) { hard = 1; break; }  // the chain leaves the look-back window
+        j -= rt;
+        if (s_st[j] & 1u) hard = 1;
+        else if (++lev > LMAXT) hard = 1;
+        else if (tid >= own0) atomicOr(&s_st[j], 8u);
+      }
+    }
+    __syncthreads();
+    for (;;) {  // shrink the round until it fits shared memory
+      M = limit - C0;
+      const bool owned = tid >= own0 && tid < M;
+      const bool part = tid < M && !hard && (owned || (s_st[tid] & 8u));
+      uint32_t so = 0;
+      BlockScan(s_scan).ExclusiveSum(part ? d : 0u, so, total_slots);
+      const uint32_t nsym = m.y & NSYM_MAX;
+      if (tid == 0) { s_scal[1] = INF; s_scal[2] = 0; s_scal[6] = INF; }
+      __syncthreads();
+      if (owned && part && nsym) {
+        atomicMin(&s_scal[1], m.x);
+        atomicMax(&s_scal[2], m.x + nsym);
+      }
+      // first candidate whose slot would not fit
+      if (part && so + d > cfg.slotcap) atomicMin(&s_scal[6], tid);
+      __syncthreads();
+      const uint32_t rmin = s_scal[1], rmax = s_scal[2], over = s_scal[6];
+      fits = over == INF && (rmax <= rmin || rmax - rmin <= cfg.rowcap);
+      if (fits || limit == a + 1) {
+        s_so[tid] = so;
+        uint32_t st = (s_st[tid] & 9u) | (hard << 1) | (part && fits ? 4u : 0u) | (lev << 8);
+        __syncthreads();
+        s_st[tid] = st;
+        break;
+      }
+      // halve the owned range (or cut it at the first slot overflow, whichever is smaller)
+      uint32_t nl = a + max(1u, (limit - a) / 2);
+      if (over != INF && over > own0 && C0 + over < nl) nl = C0 + over;
+      limit = nl;
+      __syncthreads();
+    }
+    __syncthreads();
+    // a single node that does not fit with its ancestors: the global pass takes it
+    if (!fits) {
+      if (tid >= own0 && tid < M) hard = 1;
+    }
+    const uint32_t st_mine = s_st[tid];
+    const bool part = (st_mine & 4u) != 0;
+    const bool owned = tid >= own0 && tid < M;
+    const uint32_t rmin = s_scal[1], rmax = s_scal[2];
+    // -------------------------------------------------------------- owned nodes: hard list, flags
+    if (owned) {
+      const uint32_t fl = m.y >> 29;
+      uint32_t hf = 0;
+      if (!part) hf = (d == 0 || (fl & (MF_ERR | MF_FINAL))) ? 2u : 1u;
+      if (!part && d == 0) hf = 2u;
+      rv.hardflag[t] = (uint8_t)hf;
+      if (hf == 1u) {
+        const uint32_t pos = atomicAdd(rv.hard_count, 1u);
+        rv.hard_list[pos] = t;
+      }
+      if (!part && d != 0) s_scal[5] = 1;  // hole in the owned slots: no bulk copy-out
+    }
+    // -------------------------------------------------------------- stage in: the tile's rows, look-back records
+    if (fits && rmax > rmin) {
+      for (uint32_t r = rmin + warp; r < rmax; r += K2_NT / 32)
+        s_rows[(r - rmin) * 32 + lane] = *row_word(rv, my_stream, r, lane);
+    }
+    s_hro[tid] = INF;
+    if (part && !owned) {
+      const uint32_t nsym = m.y & NSYM_MAX;
+      if (nsym) {
+        const uint32_t o = atomicAdd(&s_scal[3], nsym);
+        if (o + nsym <= HRECCAP) s_hro[tid] = o;
+      }
+    }
+    if (part) atomicMax(&s_scal[4], lev);
+    __syncthreads();
+    for (uint32_t i = warp; i < own0; i += K2_NT / 32) {  // one warp per look-back node
+      const uint32_t o = s_hro[i];
+      if (o == INF) continue;
+      const uint32_t my = s_my[i], nsym = my & NSYM_MAX, ln = (my >> 24) & 31u, r0 = s_row0[i];
+      const uint32_t s = rv.unit_stream[(C0 + i) / rv.unit];
+      for (uint32_t k = lane; k < nsym; k += 32) s_hrec[o + k] = *row_word(rv, s, r0 + k, ln);
+    }
+    // -------------------------------------------------------------- tasks by (level, outdegree class)
+    for (uint32_t i = tid; i <= NBINS; i += K2_NT) s_bin[i] = 0;
+    __syncthreads();
+    uint32_t bin = 0, rank = 0;
+    const bool task = part && d != 0;
+    if (task) {
+      bin = lev * NCLS + d_class(d);
+      rank = atomicAdd(&s_bin[bin], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t acc = 0;
+      for (uint32_t i = 0; i < NBINS; ++i) { s_binbase[i] = acc; acc += s_bin[i]; }
+      s_binbase[NBINS] = acc;
+    }
+    __syncthreads();
+    if (task) s_order[s_binbase[bin] + rank] = tid;
+    __syncthreads();
+    // -------------------------------------------------------------- resolve, one level after the other
+    const uint32_t maxlev = s_scal[4];
+    for (uint32_t l = 0; l <= maxlev; ++l) {
+      const uint32_t beg = s_binbase[l * NCLS], end = s_binbase[(l + 1) * NCLS];
+      for (uint32_t q = beg + tid; q < end; q += K2_NT) {
+        const uint32_t i = s_order[q];
+        const uint32_t di = s_d[i], rbi = s_rb[i], my = s_my[i];
+        const uint32_t rt = rbi & RT_MASK, bi = rbi >> RT_BITS, nsym = my & NSYM_MAX;
+        const uint32_t* ref = rt ? s_slots + s_so[i - rt] : nullptr;
+        const uint32_t dref = rt ? s_d[i - rt] : 0u;
+        uint32_t* out = s_slots + s_so[i];
+        if (i >= own0) merge_list(out, di, ref, dref, bi, nsym, minint, SmemRec{s_rows + (s_row0[i] - rmin) * 32 + ((my >> 24) & 31u), 32u}, false);
+        else if (s_hro[i] != INF) merge_list(out, di, ref, dref, bi, nsym, minint, SmemRec{s_hrec + s_hro[i], 1u}, false);
+        else  // a look-back record that did not fit the staging area: read it from global memory
+          merge_list(out, di, ref, dref, bi, nsym, minint,
+                     GlobalRec{&rv, rv.unit_stream[(C0 + i) / rv.unit], s_row0[i], (my >> 24) & 31u}, false);
+      }
+      __syncthreads();
+    }
+    // -------------------------------------------------------------- copy out the owned lists
+    if (fits) {
+      const uint32_t s_beg = s_so[own0];
+      const uint32_t s_end = total_slots;  // owned nodes are the last candidates
+      const bool straddle = a < rv.h && limit > rv.h;
+      if (!s_scal[5] && !straddle && s_end > s_beg) {
+        const uint64_t o0 = rv.offs[a], o1 = rv.offs[limit];
+        uint32_t* dst = nullptr;
+        if (a < rv.h) { if (o1 <= rv.halo_cap) dst = rv.halo_succ + o0; }
+        else { const uint64_t bs = rv.offs[rv.h]; if (o1 - bs <= rv.succ_cap) dst = rv.succ + (o0 - bs); }
+        if (!dst) { if (tid == 0) atomicOr(rv.err, ERR_WORKSPACE); }
+        else for (uint32_t e = s_beg + tid; e < s_end; e += K2_NT) dst[e - s_beg] = s_slots[e];
+      } else {
+        for (uint32_t i = own0 + warp; i < M; i += K2_NT / 32) {
+          if (!(s_st[i] & 4u) || s_d[i] == 0) continue;
+          uint32_t* dst = node_slot(rv, C0 + i);
+          if (!dst) { if (lane == 0) atomicOr(rv.err, ERR_WORKSPACE); continue; }
+          const uint32_t* srcp = s_slots + s_so[i];
+          for (uint32_t e = lane; e < s_d[i]; e += 32) dst[e] = srcp[e];
+        }
+      }
+    }
+    __syncthreads();
+    a = limit;
+  }
+}
+
+// -------------------------------------------------------------------------------------------- K2: global pass
+// Nodes the tiles left out (hardflag 1).  Depth among themselves: ancestors that are already final count 0.
+__global__ void __launch_bounds__(256) k_hard_levels(RangeView rv) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nh = *rv.hard_count;
+  uint32_t lev = 0;
+  if (i < nh) {
+    uint32_t j = rv.hard_list[i];
+    for (;;) {
+      const uint32_t rt = rv.rb[j] & RT_MASK;
+      if (rt == 0) break;
+      j -= rt;
+      if (rv.hardflag[j] != 1) break;
+      ++lev;
+    }
+    rv.hard_lev[i] = lev;
   }
   for (int o = 16; o; o >>= 1) lev = max(lev, __shfl_xor_sync(FULL, lev, o));
-  if ((threadIdx.x & 31) == 0 && lev >= LCAP) atomicMax(rv.maxlevel, lev);
-  __syncthreads();
-  if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
+  if ((threadIdx.x & 31) == 0 && lev) atomicMax(rv.maxlevel, lev);
 }
 
-// hist[16] -> seg[17] (exclusive prefix): nodes of level bucket l are order[seg[l] .. seg[l+1])
-__global__ void k_segments(const uint32_t* hist, uint32_t* seg) {
-  if (threadIdx.x == 0) {
-    uint32_t acc = 0;
-    for (int l = 0; l < 16; ++l) { seg[l] = acc; acc += hist[l]; }
-    seg[16] = acc;
+// One lane per hard node of the given depth: the same merge, from global memory.
+__global__ void __launch_bounds__(128) k_hard_resolve(RangeView rv, uint32_t level, uint32_t minint) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *rv.hard_count || rv.hard_lev[i] != level) return;
+  const uint32_t t = rv.hard_list[i];
+  const uint32_t d = rv.outdeg[t], rbw = rv.rb[t];
+  const uint2 m = rv.meta[t];
+  const uint32_t rt = rbw & RT_MASK, b = rbw >> RT_BITS, nsym = m.y & NSYM_MAX, fl = m.y >> 29;
+  uint32_t* out = node_slot(rv, t);
+  if (!out) { atomicOr(rv.err, ERR_WORKSPACE); return; }
+  const uint32_t* ref = nullptr;
+  uint32_t dref = 0;
+  if (rt) {
+    ref = node_slot(rv, t - rt);
+    dref = rv.outdeg[t - rt];
+    if (!ref) { atomicOr(rv.err, ERR_WORKSPACE); return; }
   }
-}
-
-// One level of phase two.  Lane-per-node state machine (same shape as K1): every lane holds one node and
-// emits ONE successor per iteration -- the minimum of the three stream heads (copied element, interval
-// element, residual) -- so that all lanes of a warp run the same short merge step regardless of how their
-// lists are composed.  Lanes that finish a node wait until SETUP_BATCH lanes are free and then fetch + set up
-// their next nodes together (the set-up is several dependent HBM loads and ~100 instructions).
-// Each block owns a contiguous chunk of the level's segment and hands its nodes out in order, so that the
-// lanes of a warp work on neighbouring nodes (their records, offsets and referenced lists share sectors).
-__global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_t* order, const uint32_t* seg,
-                                                     uint32_t lb, uint32_t exact_level, const uint32_t* lev) {
-  __shared__ uint32_t s_hdr[RES_TPB * (HS + 1)];
-  __shared__ uint32_t s_next;
-  uint32_t* const hdr = s_hdr + threadIdx.x * (HS + 1);  // odd stride: conflict-free
-  const uint32_t beg = seg[lb], end = seg[lb + 1];
-  const uint32_t len = end - beg;
-  const uint32_t chunk = (len + gridDim.x - 1) / gridDim.x;
-  const uint32_t cb = beg + min(len, blockIdx.x * chunk), ce = beg + min(len, (blockIdx.x + 1) * chunk);
-  if (cb >= ce) return;
-  if (threadIdx.x == 0) s_next = cb;
-  __syncthreads();
-  constexpr uint32_t SETUP_BATCH = 8;
-  constexpr int STEPS_PER_VOTE = 2;  // merge steps between two scheduling votes
-  enum { S_FETCH, S_MERGE, S_IDLE };
-  int st = S_FETCH;
-  // streams of the current node: 32-bit indices against three base pointers
-  uint32_t* out = nullptr;          // the node's slot; p = successors written, d = outdegree
-  const uint32_t* ref = nullptr;    // the referenced list; [ci, cend) = current copy block
-  const uint32_t* res = nullptr;    // the parked residuals (tail of the slot); rj = next one, nres = count
-  const uint32_t* blk32 = nullptr;  // block lengths in the overflow arena (else u16 in hdr)
-  const uint32_t* pp = nullptr;     // interval pairs (hdr or arena)
-  uint32_t p = 0, d = 0, ci = 0, cend = 0, dref = 0, rj = 0, nres = 0;
-  uint32_t cval = INF, ival = INF, iend = 0, rval = INF, b = 0, bk = 0, ni = 0, ik = 0;
-  uint32_t bw0 = 0, bw1 = 0;        // first four in-slot block lengths (u16 each), kept in registers
-  auto block_len = [&](uint32_t k) -> uint32_t {
-    if (blk32) return blk32[k];
-    if (k < 4) return ((k < 2 ? bw0 : bw1) >> ((k & 1u) * 16u)) & 0xFFFFu;
-    return reinterpret_cast<const uint16_t*>(hdr)[k];
-  };
-  // the current copy block is exhausted: skip block bk, then copy block bk+1 (or the implicit tail)
-  auto next_copy_block = [&]() {
-    cval = INF;
-    if (bk < b) {
-      ci += block_len(bk);
-      ++bk;
-      if (bk < b) { cend = ci + block_len(bk); ++bk; } else cend = dref;
-      if (ci < cend) cval = ref[ci];
-    }
-  };
-  for (;;) {
-    const uint32_t fetchers = __ballot_sync(FULL, st == S_FETCH);
-    const uint32_t mergers = __ballot_sync(FULL, st == S_MERGE);
-    if ((fetchers | mergers) == 0) break;
-    if (fetchers && (mergers == 0 || __popc(fetchers) >= SETUP_BATCH)) {
-      if (st == S_FETCH) {
-        uint32_t i = atomicAdd(&s_next, 1u);
-        uint32_t t = 0;
-        bool have = false;
-        while (i < ce) {  // (levels deeper than LCAP share a segment: skip nodes of other levels)
-          t = order[i];
-          if (!exact_level || lev[t] == exact_level) { have = true; break; }
-          i = atomicAdd(&s_next, 1u);
-        }
-        if (!have) st = S_IDLE;
-        else {
-          const uint64_t m = rv.meta[t];
-          const uint32_t r = (uint32_t)(m & 0xFFFFu);
-          out = node_slot(rv, t);
-          d = (uint32_t)(rv.offs[t + 1] - rv.offs[t]);
-          if (m & M_OVF) {
-            const uint32_t* rec = rv.arena + (uint32_t)(m >> 19);
-            b = rec[0]; ni = rec[1]; nres = rec[2];
-            blk32 = rec + 4;
-            pp = rv.arena + rec[3];
-          } else {
-            b = (uint32_t)(m >> 19) & (MAX_B - 1);
-            ni = (uint32_t)(m >> 34) & (MAX_NI - 1);
-            nres = (uint32_t)(m >> 48);
-            const uint32_t hb = (b + 1) >> 1, H = hb + 2 * ni;  // K1 guarantees H <= HS for in-slot headers
-            for (uint32_t w = 0; w < H; ++w) hdr[w] = out[w];
-            bw0 = hdr[0];
-            bw1 = hdr[1];
-            blk32 = nullptr;
-            pp = hdr + hb;
-          }
-          p = 0;
-          res = out + (d - nres);
-          rj = 0;
-          rval = nres ? res[0] : INF;
-          ik = 0;
-          ival = INF;
-          if (ni) { ival = pp[0]; iend = ival + pp[1]; }
-          cval = INF;
-          if (r) {
-            const uint32_t tr = ref_index(rv, t, r);  // exists: K1 rejected the record otherwise
-            ref = node_slot(rv, tr);
-            dref = (uint32_t)(rv.offs[tr + 1] - rv.offs[tr]);
-            ci = 0;
-            bk = 0;
-            cend = dref;
-            if (b) { cend = block_len(0); bk = 1; }
-            if (ci < cend) cval = ref[ci];
-            else next_copy_block();  // empty first copy block
-          }
-          st = (d != 0) ? S_MERGE : S_FETCH;
-        }
-      }
-    }
-#pragma unroll
-    for (int step = 0; step < STEPS_PER_VOTE; ++step) {
-      if (st == S_MERGE) {
-        const uint32_t mn = min(cval, min(ival, rval));
-        out[p] = mn;  // (buffering 4 successors for 16-byte stores was measured: no gain, the kernel is issue-bound)
-        if (mn == cval) {
-          if (++ci == cend) next_copy_block();
-          else cval = ref[ci];
-        } else if (mn == rval) {
-          rval = ++rj < nres ? res[rj] : INF;
-        } else {
-          if (++ival == iend) {
-            if (++ik < ni) { ival = pp[2 * ik]; iend = ival + pp[2 * ik + 1]; } else ival = INF;
-          }
-        }
-        if (++p == d) st = S_FETCH;
-      }
-    }
-  }
-}
-
-// Long reference-free records (outdegree >= BIG0_DEGREE, with intervals): one BLOCK per node instead of one
-// lane.  The list is the residuals with the expanded intervals inserted, so every element's final position
-// is its index in its own run plus the number of elements of the other run below it:
-//   residual j   -> j + (total length of the intervals that start below it)
-//   interval k,e -> (lengths of the intervals before k) + e + (number of residuals below its start)
-// In place: the residuals sit at the tail of the slot and only move towards the front, so they are moved in
-// ascending chunks (a chunk is read completely before it is written); the interval elements are filled in
-// afterwards.  Social graphs have such records (power-law degrees); one lane would need ~0.2 us per element.
-__global__ void __launch_bounds__(256) k_resolve_big0(RangeView rv, const uint32_t* order, const uint32_t* seg) {
-  __shared__ uint32_t s_start[BIG0_MAX_NI], s_pl[BIG0_MAX_NI + 1], s_below[BIG0_MAX_NI];
-  __shared__ uint32_t s_scan[256];
-  const uint32_t beg = seg[KEY_BIG0], end = seg[KEY_BIG0 + 1];
-  for (uint32_t i = beg + blockIdx.x; i < end; i += gridDim.x) {
-    const uint32_t t = order[i];
-    const uint64_t m = rv.meta[t];
-    uint32_t* const out = node_slot(rv, t);
-    const uint32_t d = (uint32_t)(rv.offs[t + 1] - rv.offs[t]);
-    uint32_t ni, nres;
-    const uint32_t* pp;
-    if (m & M_OVF) {
-      const uint32_t* rec = rv.arena + (uint32_t)(m >> 19);
-      ni = rec[1]; nres = rec[2];
-      pp = rv.arena + rec[3];
-    } else {
-      ni = (uint32_t)(m >> 34) & (MAX_NI - 1);
-      nres = (uint32_t)(m >> 48);
-      pp = out;  // reference-free: no block lengths before the pairs
-    }
-    const uint32_t* const res = out + (d - nres);
-    __syncthreads();  // shared arrays of the previous node are no longer read
-    // ---- interval starts, exclusive prefix of their lengths, residuals below each start
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < ni; base += 256) {
-      const uint32_t k = base + threadIdx.x;
-      uint32_t len = 0;
-      if (k < ni) {
-        const uint32_t st = pp[2 * k];
-        len = pp[2 * k + 1];
-        s_start[k] = st;
-        uint32_t lo = 0, hi = nres;  // residuals < st
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (res[mid] < st) lo = mid + 1; else hi = mid;
-        }
-        s_below[k] = lo;
-      }
-      s_scan[threadIdx.x] = len;
-      __syncthreads();
-      for (uint32_t o = 1; o < 256; o <<= 1) {
-        const uint32_t y = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0u;
-        __syncthreads();
-        s_scan[threadIdx.x] += y;
-        __syncthreads();
-      }
-      if (k < ni) s_pl[k] = carry + s_scan[threadIdx.x] - len;
-      carry += s_scan[255];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) s_pl[ni] = carry;
-    __syncthreads();
-    const uint32_t total_iv = carry;
-    // ---- residuals, in ascending chunks
-    for (uint32_t base = 0; base < nres; base += 256) {
-      const uint32_t j = base + threadIdx.x;
-      uint32_t x = 0, shift = 0;
-      if (j < nres) {
-        x = res[j];
-        uint32_t lo = 0, hi = ni;  // intervals that start below x
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (s_start[mid] < x) lo = mid + 1; else hi = mid;
-        }
-        shift = s_pl[lo];
-      }
-      __syncthreads();  // the whole chunk is read before any of it is overwritten
-      if (j < nres) out[j + shift] = x;
-    }
-    __syncthreads();
-    // ---- interval elements
-    for (uint32_t e = threadIdx.x; e < total_iv; e += 256) {
-      uint32_t lo = 0, hi = ni;  // last interval whose prefix is <= e
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (s_pl[mid + 1] <= e) lo = mid + 1; else hi = mid;
-      }
-      out[e + s_below[lo]] = s_start[lo] + (e - s_pl[lo]);
-    }
-  }
+  merge_list(out, d, ref, dref, b, nsym, minint, GlobalRec{&rv, rv.unit_stream[t / rv.unit], m.x, (m.y >> 24) & 31u},
+             (fl & MF_INSLOT) != 0);
 }
 
 // -------------------------------------------------------------------------------------------- random access
@@ -786,15 +848,15 @@ __global__ void __launch_bounds__(256) k_query_ids(const uint64_t* q, uint64_t n
 __global__ void __launch_bounds__(TPB) k_closure_step(DevGraph g, const uint32_t* in, uint32_t n_in, uint32_t* out,
                                                       uint32_t* count, uint32_t cap, uint64_t res_first, uint32_t* err_out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const GlobalTables tab{g.tb.bkt, g.tb.ent};
   uint32_t target = NOT_FOUND, err = 0;
   if (i < n_in && g.window != 0) {
     const uint64_t v = in[i];
-    uint32_t state;
-    int64_t ptr;
-    load_phase(g, v, state, ptr, err);
-    const uint64_t d = ans_decode(g.tb, g.tb.lut, g.tb.ent, Outdegree, state, ptr, g.stream, err);
+    Dec dc;
+    load_phase(g, v, dc, err);
+    const uint64_t d = ans_decode(g.tb, tab, Outdegree, dc, g.stream, err);
     if (d != 0 && !err) {
-      const uint64_t r = ans_decode(g.tb, g.tb.lut, g.tb.ent, ReferenceOffset, state, ptr, g.stream, err);
+      const uint64_t r = ans_decode(g.tb, tab, ReferenceOffset, dc, g.stream, err);
       if (r > g.window) err |= ERR_CORRUPT;
       else if (r != 0 && !err) {
         if (r > v || v - r < res_first) err |= ERR_RANGE;
@@ -849,12 +911,9 @@ __global__ void __launch_bounds__(256) k_query_gather(const uint32_t* qidx, uint
 __global__ void k_expand_table(DevTables tb, int c, uint32_t n_slots, uint4* out) {
   uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_slots) return;
-  uint32_t j = tb.lut[tb.lut_off[c] + (slot >> tb.shift[c])];
-  uint2 e = tb.ent[tb.ent_off[c] + j];
-  while (slot - (e.x & 0xFFFFu) >= (e.x >> 16)) {
-    ++j;
-    e = tb.ent[tb.ent_off[c] + j];
-  }
+  const uint2 bk = tb.bkt[tb.bkt_off[c] + (slot >> 5)];
+  const uint32_t j = bk.y + (uint32_t)__popc(bk.x & ((2u << (slot & 31u)) - 1u));
+  const uint2 e = tb.ent[tb.ent_off[c] + j];
   uint32_t folds = e.y >> 16;
   uint4 o;
   if (folds == 0xFFFFu) {  // unused slot: DecoderModelEntry::default()
@@ -869,14 +928,16 @@ __global__ void k_expand_table(DevTables tb, int c, uint32_t n_slots, uint4* out
   out[slot] = o;
 }
 
-__global__ void k_decode_symbols(DevGraph g, const uint8_t* comps, uint64_t n, int64_t ptr, uint32_t state,
+__global__ void k_decode_symbols(DevGraph g, const uint8_t* comps, uint64_t n, uint64_t ptr, uint32_t state,
                                  uint64_t* out, uint64_t* end) {
   if (threadIdx.x || blockIdx.x) return;
+  const GlobalTables tab{g.tb.bkt, g.tb.ent};
   uint32_t err = 0;
-  for (uint64_t i = 0; i < n; ++i)
-    out[i] = ans_decode(g.tb, g.tb.lut, g.tb.ent, comps[i], state, ptr, g.stream, err);
-  end[0] = (uint64_t)ptr;
-  end[1] = state;
+  Dec dc{state, (uint32_t)ptr, 0};
+  dec_prime(dc, g.stream);
+  for (uint64_t i = 0; i < n; ++i) out[i] = ans_decode(g.tb, tab, comps[i], dc, g.stream, err);
+  end[0] = (uint64_t)dc.sp;
+  end[1] = dc.state;
   end[2] = err;
 }
 
@@ -886,13 +947,14 @@ __global__ void k_offsets_rebase(const uint64_t* src, uint64_t base, uint64_t* d
 }
 
 // scalars the host needs after a decode -> mapped host memory (no DMA copy: see wga_graph::h_pub)
-__global__ void k_publish(const uint64_t* tot0, const uint64_t* tot1, const uint32_t* maxlevel, const uint32_t* err,
-                          uint64_t* pub) {
+__global__ void k_publish(const uint64_t* tot0, const uint64_t* tot1, const uint32_t* maxlevel, const uint32_t* hard_count,
+                          const uint32_t* err, uint64_t* pub) {
   if (threadIdx.x == 0) {
     pub[1] = *tot0;
     pub[2] = *tot1;
     pub[3] = *maxlevel;
     pub[4] = *err;
+    pub[5] = *hard_count;
   }
 }
 
@@ -905,56 +967,67 @@ inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 // Scalars at the head of the workspace (one 256-byte line, cleared per call).
 struct Scalars {
-  unsigned long long cursor;  // arena bump pointer
   uint64_t lo;                // k_halo result
+  uint32_t unit_ctr;
+  uint32_t chunk_ctr;
+  uint32_t hard_count;
   uint32_t maxlevel;
-  uint32_t pad;
-  uint32_t hist[16];          // nodes per level bucket
-  uint32_t seg[17];           // exclusive prefix of hist
 };
 static_assert(sizeof(Scalars) <= 256, "Scalars must fit the cleared line");
 
 struct WorkspacePlan {
-  uint64_t off_outdeg, off_phase1, off_offs, off_meta, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_arena;
+  uint64_t off_outdeg, off_ph, off_rb, off_offs, off_meta, off_hflag, off_hlist, off_hlev, off_ustream, off_schunks, off_cub,
+      off_halo, off_rows;
   uint64_t cub_bytes, halo_cap, fixed_bytes;
 };
 
-WorkspacePlan plan_workspace(uint64_t n) {
+WorkspacePlan plan_workspace(uint64_t n, uint32_t unit) {
   WorkspacePlan p{};
   uint64_t o = 0;
   o += 256;  // Scalars
   p.off_outdeg = o; o = align_up(o + 4 * (n + 1), 256);
-  p.off_phase1 = o; o = align_up(o + 16 * n, 256);
+  p.off_ph = o; o = align_up(o + 8 * n, 256);
+  p.off_rb = o; o = align_up(o + 4 * n, 256);
   p.off_offs = o; o = align_up(o + 8 * (n + 1), 256);
   p.off_meta = o; o = align_up(o + 8 * n, 256);
-  p.off_lev = o; o = align_up(o + 4 * n, 256);
-  for (int i = 0; i < 2; ++i) { p.off_keys[i] = o; o = align_up(o + 2 * n, 256); }
-  for (int i = 0; i < 2; ++i) { p.off_vals[i] = o; o = align_up(o + 4 * n, 256); }
-  size_t scan_bytes = 0, sort_bytes = 0;
+  p.off_hflag = o; o = align_up(o + n, 256);
+  p.off_hlist = o; o = align_up(o + 4 * n, 256);
+  p.off_hlev = o; o = align_up(o + 4 * n, 256);
+  p.off_ustream = o; o = align_up(o + 4 * ((n + unit - 1) / unit + 1), 256);
+  p.off_schunks = o; o = align_up(o + 4ull * MAX_STREAMS * MAXC, 256);
+  size_t scan_bytes = 0;
   cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(nullptr, U32ToU64());
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, it, (uint64_t*)nullptr, (int64_t)(n + 1));
-  cub::DoubleBuffer<uint16_t> dk(nullptr, nullptr);
-  cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
-  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int64_t)n, 0, 12);
-  p.cub_bytes = std::max(scan_bytes, sort_bytes);
+  p.cub_bytes = scan_bytes;
   p.off_cub = o; o = align_up(o + p.cub_bytes, 256);
   p.halo_cap = 1u << 20;  // successors of halo nodes (u32 each)
   p.off_halo = o; o = align_up(o + 4 * p.halo_cap, 256);
-  p.off_arena = o;
-  p.fixed_bytes = o;
+  p.off_rows = align_up(o, 16384);
+  p.fixed_bytes = p.off_rows;
   return p;
+}
+
+uint32_t effective_tile(const Tuning& tn, uint32_t window) {
+  const uint32_t lookback = std::min<uint32_t>(HMAX, window * LMAXT);
+  uint32_t tile = tn.tile ? tn.tile : 1;
+  if (tile > K2_NT - lookback) tile = K2_NT - lookback;
+  return tile;
 }
 
 }  // namespace
 
 uint64_t decode_workspace_size(const wga_graph* g, uint64_t first, uint64_t last) {
   uint64_t n = last - first + 4096;  // room for a halo
-  WorkspacePlan p = plan_workspace(n);
+  WorkspacePlan p = plan_workspace(n, effective_tile(g_tuning, (uint32_t)g->prelude.compression_window));
   double frac = g->prelude.number_of_nodes ? (double)(last - first) / (double)g->prelude.number_of_nodes : 1.0;
   uint64_t arcs_est = (uint64_t)((double)g->prelude.number_of_arcs * frac) + (1u << 20);
-  // arena: headers that do not fit their node's slot (rare)
-  uint64_t arena_cap = n + arcs_est / 8 + (1u << 20);
-  return p.fixed_bytes + 4 * arena_cap;
+  // rows: one 4-byte word per decoded symbol, 32 lanes per row of which about three quarters are busy; a record has
+  // at most (blocks + 1 + outdegree) words
+  uint64_t rows_bytes = 8 * arcs_est + 48 * n + (32ull << 20);
+  // every K1 warp that gets work owns at least one chunk
+  const uint32_t tile = effective_tile(g_tuning, (uint32_t)g->prelude.compression_window);
+  rows_bytes += std::min<uint64_t>((n + tile - 1) / tile, MAX_STREAMS) * (4ull * CH * 32);
+  return p.fixed_bytes + rows_bytes;
 }
 
 static void check_device_error(wga_graph* g, uint32_t herr, cudaStream_t st) {
@@ -963,6 +1036,7 @@ static void check_device_error(wga_graph* g, uint32_t herr, cudaStream_t st) {
     if (herr & ERR_WORKSPACE) throw Error(WGA_E_WORKSPACE, "decode: workspace or output buffer too small; pass larger buffers");
     if (herr & ERR_RANGE) throw Error(WGA_E_CORRUPT, "decode: a reference leaves the decoded range");
     if (herr & ERR_SYMBOL_WIDTH) throw Error(WGA_E_UNSUPPORTED, "decode: a decoded value does not fit 32 bits");
+    if (herr & ERR_LIMIT) throw Error(WGA_E_UNSUPPORTED, "decode: a record exceeds an implementation limit (2^20 copy blocks / 2^24 words)");
     throw Error(WGA_E_CORRUPT, "decode: inconsistent stream or tables");
   }
 }
@@ -979,15 +1053,17 @@ void outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets
   if (!g->on_device) throw Error(WGA_E_CUDA, "graph was opened host-only");
   if (first > last || last > g->res_last || first < g->res_first) throw Error(WGA_E_ARG, "range outside the resident nodes");
   uint64_t n = last - first;
-  WorkspacePlan p = plan_workspace(n);
-  if (ws_bytes < p.fixed_bytes) throw Error(WGA_E_WORKSPACE, "workspace too small");
+  WorkspacePlan p = plan_workspace(n, 192);
+  if (ws_bytes < p.off_ph) throw Error(WGA_E_WORKSPACE, "workspace too small");
   uint8_t* w = (uint8_t*)ws;
   uint32_t* outdeg = (uint32_t*)(w + p.off_outdeg);
-  k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, first, nullptr, (uint32_t)n, outdeg, nullptr, g->d_err);
+  k_heads<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, first, nullptr, (uint32_t)n, outdeg, nullptr, nullptr, g->d_err);
   count_launch();
+  // the scan's temporary storage lives behind the outdegrees (the other arrays of the plan are not used here)
   size_t cb = p.cub_bytes;
+  if (ws_bytes < p.off_ph + cb) throw Error(WGA_E_WORKSPACE, "workspace too small");
   cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(outdeg, U32ToU64());
-  WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_cub, cb, it, d_offsets, (int64_t)(n + 1), st));
+  WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_ph, cb, it, d_offsets, (int64_t)(n + 1), st));
   count_launch(2);
   WGA_CUDA(cudaGetLastError());
 }
@@ -998,30 +1074,75 @@ static void mark(wga_graph* g, cudaStream_t st) {
   cudaEventRecord(g->ev[g->n_ev++], st);
 }
 
-static uint32_t resolve_grid(const Tuning& tn) {
-  if (tn.k2_blocks) return tn.k2_blocks;
-  static uint32_t cached = 0;
-  if (!cached) {
-    int dev = 0, sms = 148, per_sm = 8;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resolve, RES_TPB, 0);
-    // swept on eu-2015-host-shaped: 10 resident blocks per SM (40 warps) beat 12 -- the lane-private streams of
-    // more warps no longer fit L1 -- and anything that is not a whole wave loses to the partial second wave
-    per_sm = per_sm > 10 ? 10 : (per_sm > 0 ? per_sm : 1);
-    cached = (uint32_t)(sms * per_sm);
+namespace {
+
+struct DeviceInfo {
+  int sms = 148;
+  int smem_optin = 227 * 1024;
+};
+const DeviceInfo& device_info(int dev) {
+  static DeviceInfo info[64];
+  static bool have[64] = {};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!have[dev]) {
+    cudaDeviceGetAttribute(&info[dev].sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&info[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    have[dev] = true;
   }
-  return cached;
+  return info[dev];
 }
 
+// Shared-memory layout of the entropy kernel's tables.
+uint64_t plan_k1_tables(const wga_graph* g, K1Tables& kt, int smem_limit) {
+  const PackedTablesData& p = g->packed;
+  const uint64_t head = 9 * 16 + 12 * 4 + 32 * 4;
+  uint32_t bo = 0;
+  for (int c = 0; c < WGA_COMPONENTS; ++c) {
+    const uint32_t L = p.L[c], R = p.R[c] ? p.R[c] : 1u;
+    kt.cp[c] = make_uint4(((1u << L) - 1u) | (L << 16) | (R << 21), 0u, 0u, 0u);
+    kt.gent_off[c] = p.ent_off[c];
+    if (c >= Blocks) { kt.cp[c].y = bo; bo += p.nb[c]; }
+  }
+  kt.bkt_words = bo;
+  // entries: water-filling of what is left
+  int64_t budget = ((int64_t)smem_limit - 1024 - (int64_t)head - 8ll * bo) / 8;
+  if (budget < 0) throw Error(WGA_E_UNSUPPORTED, "decoder tables do not fit shared memory");
+  uint32_t hot[WGA_COMPONENTS] = {};
+  uint32_t left = (uint32_t)budget;
+  for (int round = 0; round < 8; ++round) {
+    int open = 0;
+    for (int c = Blocks; c <= Residual; ++c) if (hot[c] < p.nent[c]) ++open;
+    if (!open || !left) break;
+    const uint32_t share = std::max<uint32_t>(1, left / open);
+    for (int c = Blocks; c <= Residual; ++c) {
+      const uint32_t want = std::min<uint32_t>(p.nent[c] - hot[c], std::min(share, left));
+      hot[c] += want;
+      left -= want;
+    }
+  }
+  uint32_t eo = 0;
+  for (int c = Blocks; c <= Residual; ++c) { kt.cp[c].z = eo; kt.cp[c].w = hot[c]; eo += hot[c]; }
+  kt.ent_words = eo;
+  return head + 8ull * bo + 8ull * eo;
+}
+
+uint64_t tile_smem_bytes(const TileCfg& c) {
+  return 4ull * ((uint64_t)c.slotcap + 8 + 32ull * c.rowcap + HRECCAP + 8ull * K2_NT + 2 * (NBINS + 8));
+}
+
+}  // namespace
+
 // K0 .. K2 on the nodes described by rv (a contiguous range, or a sorted node list), then one host
-// synchronisation that reads back the totals (tot[0] = halo arcs, tot[1] = all arcs), the deepest level and
+// synchronisation that reads back the totals (tot[0] = halo arcs, tot[1] = all arcs), the hard-node count and
 // the error word.
-static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const WorkspacePlan& p, Scalars* sc,
+static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const WorkspacePlan& p, Scalars* sc,
                          const Tuning& tn, cudaStream_t st, uint64_t tot[2]) {
   const uint64_t n = rv.n;
+  const DeviceInfo& di = device_info(g->device);
   // ---- K0 + scan
-  k_outdegree<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, rv.lo, rv.nodes, (uint32_t)n, rv.outdeg, rv.phase1, g->d_err);
+  k_heads<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, rv.lo, rv.nodes, (uint32_t)n, rv.outdeg, rv.ph, rv.rb, g->d_err);
   count_launch();
   {
     size_t cb = p.cub_bytes;
@@ -1029,54 +1150,51 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
     WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_cub, cb, it, rv.offs, (int64_t)(n + 1), st));
     count_launch(2);
   }
-  mark(g, st);  // 1: outdegrees + scan done
-  // ---- K1: entropy decode (spans that would overflow the output are skipped and reported)
+  mark(g, st);  // 1: heads + scan done
+  // ---- K1: entropy decode into rows
   {
-    uint32_t tpb = tn.k1_tpb < 32 ? 32 : (tn.k1_tpb > 128 ? 128 : tn.k1_tpb / 32 * 32);
-    uint32_t span = tn.k1_span ? tn.k1_span : 1;
-    // small ranges: shrink the spans so that the grid still fills the machine (148 SMs x 32 blocks)
-    span = std::min<uint32_t>(span, std::max<uint32_t>(128u, (uint32_t)(n / (148 * 32))));
-    if (rv.nodes) k_entropy<true><<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
-    else k_entropy<false><<<span_count(rv.n, rv.h, span), tpb, 0, st>>>(g->dev, rv, span, tn.force_ovf);
+    K1Tables kt{};
+    const uint64_t smem = plan_k1_tables(g, kt, di.smem_optin);
+    uint32_t blocks = tn.k1_blocks ? tn.k1_blocks : (uint32_t)di.sms;
+    blocks = std::min<uint32_t>(blocks, (rv.n_units + K1_WARPS - 1) / K1_WARPS);
+    blocks = std::max<uint32_t>(1u, std::min<uint32_t>(blocks, MAX_STREAMS / K1_WARPS));
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[0]) {
+      WGA_CUDA(cudaFuncSetAttribute(k_entropy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin - 1024));
+      WGA_CUDA(cudaFuncSetAttribute(k_entropy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin - 1024));
+      attr_done[0] = true;
+    }
+    const uint32_t refill = std::max<uint32_t>(1u, std::min<uint32_t>(32u, tn.refill));
+    if (rv.nodes) k_entropy<true><<<blocks, K1_THREADS, smem, st>>>(g->dev, rv, kt, refill);
+    else k_entropy<false><<<blocks, K1_THREADS, smem, st>>>(g->dev, rv, kt, refill);
     count_launch();
   }
   mark(g, st);  // 2: entropy decode done
-  // ---- K2: levels, sort by (level, degree), one resolve launch per level
-  uint32_t* lev = (uint32_t*)(w + p.off_lev);
-  cub::DoubleBuffer<uint16_t> dkeys((uint16_t*)(w + p.off_keys[0]), (uint16_t*)(w + p.off_keys[1]));
-  cub::DoubleBuffer<uint32_t> dvals((uint32_t*)(w + p.off_vals[0]), (uint32_t*)(w + p.off_vals[1]));
-  const bool have_refs = g->prelude.compression_window != 0 || g->prelude.min_interval_length != 0;
-  if (have_refs) {
-    k_levels<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rv, dkeys.Current(), dvals.Current(), lev, sc->hist, tn.sort_degree);
-    count_launch();
-    size_t cb = p.cub_bytes;
-    WGA_CUDA(cub::DeviceRadixSort::SortPairs(w + p.off_cub, cb, dkeys, dvals, (int64_t)n, tn.sort_degree ? 0 : 8, 12, st));
-    count_launch(3);
-    k_segments<<<1, 32, 0, st>>>(sc->hist, sc->seg);
-    count_launch();
-    mark(g, st);  // 3: levels + sort done
-    k_resolve_big0<<<296, 256, 0, st>>>(rv, dvals.Current(), sc->seg);  // (empty on graphs without long records)
-    count_launch();
-    const uint32_t grid = resolve_grid(tn);
-    const uint32_t nlev = g->prelude.compression_window ? LCAP : 1;  // without references everything is level 0
-    for (uint32_t l = 0; l < nlev; ++l) {
-      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, l, 0, lev);
-      count_launch();
+  // ---- K2: tiles
+  const uint32_t window = (uint32_t)g->prelude.compression_window;
+  const uint32_t lookback = std::min<uint32_t>(HMAX, window * LMAXT);
+  {
+    TileCfg cfg{rv.unit, std::max<uint32_t>(64u, tn.slotcap), std::max<uint32_t>(1u, tn.rowcap), std::max<uint32_t>(2u, tn.dbig)};
+    const uint64_t smem = tile_smem_bytes(cfg);
+    if ((int64_t)smem > (int64_t)di.smem_optin - 2048) throw Error(WGA_E_ARG, "tile tuning exceeds shared memory");
+    static uint64_t attr_bytes = 0;
+    if (attr_bytes < smem) {
+      WGA_CUDA(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_bytes = smem;
     }
-  } else {
-    mark(g, st);
+    k_tile<<<rv.n_units, K2_NT, smem, st>>>(rv, cfg, g->dev.min_interval, lookback);
+    count_launch();
   }
-  mark(g, st);  // 4: resolve done
-  // ---- totals, deepest level, error word
-  uint32_t maxlevel = 0, herr = 0;
-  k_publish<<<1, 32, 0, st>>>(rv.offs + rv.h, rv.offs + n, &sc->maxlevel, g->d_err, g->d_pub);
+  mark(g, st);  // 3: tiles done
+  // ---- totals, hard nodes, error word
+  k_publish<<<1, 32, 0, st>>>(rv.offs + rv.h, rv.offs + n, &sc->maxlevel, &sc->hard_count, g->d_err, g->d_pub);
   count_launch();
   WGA_CUDA(cudaStreamSynchronize(st));
   WGA_CUDA(cudaGetLastError());
   tot[0] = g->h_pub[1];
   tot[1] = g->h_pub[2];
-  maxlevel = (uint32_t)g->h_pub[3];
-  herr = (uint32_t)g->h_pub[4];
+  uint32_t herr = (uint32_t)g->h_pub[4];
+  const uint32_t nhard = (uint32_t)g->h_pub[5];
   if (tot[0] > rv.halo_cap) {
     if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
     throw Error(WGA_E_WORKSPACE, "halo successors exceed the workspace");
@@ -1086,16 +1204,60 @@ static void run_pipeline(wga_graph* g, const RangeView& rv, uint8_t* w, const Wo
     throw Error(WGA_E_WORKSPACE, "d_succ too small: need " + std::to_string(tot[1] - tot[0]) + " elements");
   }
   check_device_error(g, herr, st);
-  // ---- reference chains deeper than LCAP (e.g. graphs compressed with an unbounded max_ref_count): one
-  //      launch per extra level over the shared deep segment
-  if (have_refs && maxlevel >= LCAP) {
-    const uint32_t grid = resolve_grid(tn);
-    for (uint32_t l = LCAP; l <= maxlevel; ++l) {
-      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, LCAP, l, lev);
+  // ---- nodes the tiles left to the global pass, one launch per depth
+  if (nhard) {
+    k_hard_levels<<<(nhard + 255) / 256, 256, 0, st>>>(rv);
+    k_publish<<<1, 32, 0, st>>>(rv.offs + rv.h, rv.offs + n, &sc->maxlevel, &sc->hard_count, g->d_err, g->d_pub);
+    count_launch(2);
+    WGA_CUDA(cudaStreamSynchronize(st));
+    const uint32_t maxlevel = (uint32_t)g->h_pub[3];
+    for (uint32_t l = 0; l <= maxlevel; ++l) {
+      k_hard_resolve<<<(nhard + 127) / 128, 128, 0, st>>>(rv, l, g->dev.min_interval);
       count_launch();
     }
     check_device_error(g, read_device_error(g, st), st);
   }
+  mark(g, st);  // 4: global pass done
+}
+
+static void apply_env_tuning() {
+  static std::once_flag once;
+  std::call_once(once, [] {  // WGA_TUNING="key=value,key=value": same knobs as wga_debug_set_tuning (profiling runs)
+    if (const char* e = getenv("WGA_TUNING")) {
+      std::string str(e);
+      size_t i = 0;
+      while (i < str.size()) {
+        size_t j = str.find(',', i);
+        if (j == std::string::npos) j = str.size();
+        size_t q = str.find('=', i);
+        if (q != std::string::npos && q < j) set_tuning(str.substr(i, q - i).c_str(), strtoull(str.c_str() + q + 1, nullptr, 10));
+        i = j + 1;
+      }
+    }
+  });
+}
+
+static void bind_views(RangeView& rv, uint8_t* w, const WorkspacePlan& p, Scalars* sc, uint64_t ws_bytes, uint32_t unit) {
+  rv.outdeg = (uint32_t*)(w + p.off_outdeg);
+  rv.ph = (uint2*)(w + p.off_ph);
+  rv.rb = (uint32_t*)(w + p.off_rb);
+  rv.meta = (uint2*)(w + p.off_meta);
+  rv.hardflag = (uint8_t*)(w + p.off_hflag);
+  rv.hard_list = (uint32_t*)(w + p.off_hlist);
+  rv.hard_lev = (uint32_t*)(w + p.off_hlev);
+  rv.hard_count = &sc->hard_count;
+  rv.maxlevel = &sc->maxlevel;
+  rv.rows = (uint32_t*)(w + p.off_rows);
+  const uint64_t chunks = (ws_bytes - p.off_rows) / (4ull * CH * 32);
+  rv.rows_cap = (uint32_t)std::min<uint64_t>(chunks, 0xFFFFFFF0ull);
+  rv.chunk_ctr = &sc->chunk_ctr;
+  rv.stream_chunks = (uint32_t*)(w + p.off_schunks);
+  rv.unit_stream = (uint32_t*)(w + p.off_ustream);
+  rv.unit_ctr = &sc->unit_ctr;
+  rv.unit = unit;
+  rv.n_units = (rv.n + unit - 1) / unit;
+  rv.halo_succ = (uint32_t*)(w + p.off_halo);
+  rv.halo_cap = p.halo_cap;
 }
 
 void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets, uint32_t* d_succ,
@@ -1108,21 +1270,7 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     if (h_arcs) *h_arcs = 0;
     return;
   }
-  static bool env_done = false;
-  if (!env_done) {  // WGA_TUNING="key=value,key=value": same knobs as wga_debug_set_tuning (profiling runs)
-    env_done = true;
-    if (const char* e = getenv("WGA_TUNING")) {
-      std::string str(e);
-      size_t i = 0;
-      while (i < str.size()) {
-        size_t j = str.find(',', i);
-        if (j == std::string::npos) j = str.size();
-        size_t q = str.find('=', i);
-        if (q != std::string::npos && q < j) set_tuning(str.substr(i, q - i).c_str(), strtoull(str.c_str() + q + 1, nullptr, 10));
-        i = j + 1;
-      }
-    }
-  }
+  apply_env_tuning();
   const Tuning tn = g_tuning;
   uint8_t* w = (uint8_t*)ws;
   if (ws_bytes < 256) throw Error(WGA_E_WORKSPACE, "workspace too small");
@@ -1140,21 +1288,14 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     if (lo < g->res_first) throw Error(WGA_E_ARG, "reference chain leaves the resident shard");
   }
   const uint64_t n = last - lo;
-  WorkspacePlan p = plan_workspace(n);
-  if (ws_bytes < p.fixed_bytes + 4096) throw Error(WGA_E_WORKSPACE, "workspace too small");
+  const uint32_t unit = effective_tile(tn, (uint32_t)g->prelude.compression_window);
+  WorkspacePlan p = plan_workspace(n, unit);
+  if (ws_bytes < p.fixed_bytes + 4ull * CH * 32) throw Error(WGA_E_WORKSPACE, "workspace too small");
   RangeView rv{};
-  rv.lo = lo; rv.first = first; rv.n = (uint32_t)n; rv.h = (uint32_t)(first - lo);
-  rv.outdeg = (uint32_t*)(w + p.off_outdeg);
-  rv.phase1 = (uint4*)(w + p.off_phase1);
+  rv.lo = lo; rv.n = (uint32_t)n; rv.h = (uint32_t)(first - lo);
+  bind_views(rv, w, p, sc, ws_bytes, unit);
   rv.offs = rv.h ? (uint64_t*)(w + p.off_offs) : d_offsets;
-  rv.meta = (uint64_t*)(w + p.off_meta);
-  rv.arena = (uint32_t*)(w + p.off_arena);
-  rv.arena_cap = (ws_bytes - p.off_arena) / 4;
-  rv.cursor = &sc->cursor;
-  rv.maxlevel = &sc->maxlevel;
-  rv.halo_succ = (uint32_t*)(w + p.off_halo);
-  rv.halo_cap = p.halo_cap;
-  rv.succ = d_succ; rv.succ_cap = succ_capacity;
+  rv.succ = d_succ; rv.succ_cap = d_succ ? succ_capacity : 0;
   rv.err = g->d_err;
   uint64_t tot[2] = {0, 0};
   run_pipeline(g, rv, w, p, sc, tn, st, tot);
@@ -1179,7 +1320,7 @@ struct BatchPlan {
   uint64_t off_scal, off_qid, off_all[2], off_U, off_qidx, off_cub, off_offsU, off_succU, off_inner;
   uint64_t cub_bytes, inner_bytes, total;
 };
-BatchPlan plan_batch(uint64_t nq, uint64_t max_total_arcs) {
+BatchPlan plan_batch(uint64_t nq, uint64_t max_total_arcs, uint32_t unit) {
   BatchPlan b{};
   b.cap_nodes = 8 * nq + 4096;       // queries + every node on their reference chains
   if (b.cap_nodes > 0xFFFFFFF0ull) b.cap_nodes = 0xFFFFFFF0ull;
@@ -1199,16 +1340,17 @@ BatchPlan plan_batch(uint64_t nq, uint64_t max_total_arcs) {
   b.off_cub = o; o = align_up(o + b.cub_bytes, 256);
   b.off_offsU = o; o = align_up(o + 8 * (b.cap_nodes + 1), 256);
   b.off_succU = o; o = align_up(o + 4 * b.cap_arcs, 256);
-  WorkspacePlan p = plan_workspace(b.cap_nodes);
-  b.inner_bytes = p.fixed_bytes + 4 * (b.cap_nodes / 4 + b.cap_arcs / 8 + (1u << 20));
-  b.off_inner = o; o += b.inner_bytes;
+  WorkspacePlan p = plan_workspace(b.cap_nodes, unit);
+  b.inner_bytes = p.fixed_bytes + 8 * b.cap_arcs + 48 * b.cap_nodes + (16ull << 20) +
+                  std::min<uint64_t>((b.cap_nodes + unit - 1) / unit, MAX_STREAMS) * (4ull * CH * 32);
+  b.off_inner = align_up(o, 16384); o = b.off_inner + b.inner_bytes;
   b.total = o;
   return b;
 }
 }  // namespace
 
-uint64_t successors_workspace_size(const wga_graph*, uint64_t n_queries, uint64_t max_total_arcs) {
-  return plan_batch(n_queries, max_total_arcs).total;
+uint64_t successors_workspace_size(const wga_graph* g, uint64_t n_queries, uint64_t max_total_arcs) {
+  return plan_batch(n_queries, max_total_arcs, effective_tile(g_tuning, (uint32_t)g->prelude.compression_window)).total;
 }
 
 void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64_t* d_offsets, uint32_t* d_succ,
@@ -1220,16 +1362,18 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
     if (h_arcs) *h_arcs = 0;
     return;
   }
+  apply_env_tuning();
+  const Tuning tn = g_tuning;
+  const uint32_t unit = effective_tile(tn, (uint32_t)g->prelude.compression_window);
   // the caller sizes the workspace with an upper bound of the arcs it expects; recover it from the size
-  BatchPlan b = plan_batch(nq, 0);
+  BatchPlan b = plan_batch(nq, 0, unit);
   if (ws_bytes < b.total) throw Error(WGA_E_WORKSPACE, "workspace too small");
-  {  // largest arc bound whose plan fits this workspace (the plan grows by ~18 bytes per arc)
-    uint64_t A = (ws_bytes - b.total) / 18;
-    BatchPlan b2 = plan_batch(nq, A);
-    while (b2.total > ws_bytes && A) { A = A / 16 * 15; b2 = plan_batch(nq, A); }
+  {  // largest arc bound whose plan fits this workspace (the plan grows by ~50 bytes per arc)
+    uint64_t A = (ws_bytes - b.total) / 50;
+    BatchPlan b2 = plan_batch(nq, A, unit);
+    while (b2.total > ws_bytes && A) { A = A / 16 * 15; b2 = plan_batch(nq, A, unit); }
     if (b2.total <= ws_bytes) b = b2;
   }
-  const Tuning tn = g_tuning;
   uint8_t* w = (uint8_t*)ws;
   uint32_t* scal = (uint32_t*)(w + b.off_scal);  // [0] closure count, [1] unique count
   WGA_CUDA(cudaMemsetAsync(scal, 0, 256, st));
@@ -1239,7 +1383,7 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   count_launch();
   if (!d_succ) {  // sizing call: only the outdegrees of the queries (first symbol of each record)
     uint32_t* deg = all;
-    k_outdegree<<<(unsigned)((nq + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, 0, qid, (uint32_t)nq, deg, nullptr, g->d_err);
+    k_heads<<<(unsigned)((nq + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, 0, qid, (uint32_t)nq, deg, nullptr, nullptr, g->d_err);
     size_t cbs = b.cub_bytes;
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(deg, U32ToU64());
     WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + b.off_cub, cbs, it, d_offsets, (int64_t)(nq + 1), st));
@@ -1285,19 +1429,13 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   // ---- decode the node list U into a temporary CSR
   uint8_t* iw = w + b.off_inner;
   WGA_CUDA(cudaMemsetAsync(iw, 0, 256, st));
-  WorkspacePlan p = plan_workspace(nU);
-  if (p.fixed_bytes + 4096 > b.inner_bytes) throw Error(WGA_E_WORKSPACE, "workspace too small");
+  WorkspacePlan p = plan_workspace(nU, unit);
+  if (p.fixed_bytes + 4ull * CH * 32 > b.inner_bytes) throw Error(WGA_E_WORKSPACE, "workspace too small");
   Scalars* sc = (Scalars*)iw;
   RangeView rv{};
-  rv.lo = 0; rv.first = 0; rv.n = nU; rv.h = 0; rv.nodes = U;
-  rv.outdeg = (uint32_t*)(iw + p.off_outdeg);
-  rv.phase1 = (uint4*)(iw + p.off_phase1);
+  rv.lo = 0; rv.n = nU; rv.h = 0; rv.nodes = U;
+  bind_views(rv, iw, p, sc, b.inner_bytes, unit);
   rv.offs = (uint64_t*)(w + b.off_offsU);
-  rv.meta = (uint64_t*)(iw + p.off_meta);
-  rv.arena = (uint32_t*)(iw + p.off_arena);
-  rv.arena_cap = (b.inner_bytes - p.off_arena) / 4;
-  rv.cursor = &sc->cursor;
-  rv.maxlevel = &sc->maxlevel;
   rv.halo_succ = nullptr; rv.halo_cap = 0;
   rv.succ = (uint32_t*)(w + b.off_succU); rv.succ_cap = b.cap_arcs;
   rv.err = g->d_err;
@@ -1329,10 +1467,26 @@ void launch_offsets_add(uint64_t* off, uint64_t n, uint64_t base, cudaStream_t s
 }
 
 void debug_expand_table(wga_graph* g, int c, void* h_out, uint64_t n_slots) {
-  if (!g->on_device) throw Error(WGA_E_CUDA, "graph was opened host-only");
   if (c < 0 || c >= WGA_COMPONENTS) throw Error(WGA_E_ARG, "bad component");
   uint64_t want = 1ull << g->prelude.tables[c].frame_size;
   if (n_slots != want) throw Error(WGA_E_ARG, "n_slots must be 2^frame_size");
+  if (!g->on_device) {  // host-only handle: the same bucket + popcount lookup on the host copy of the packed tables
+    const PackedTablesData& p = g->packed;
+    uint32_t* o = (uint32_t*)h_out;
+    for (uint32_t slot = 0; slot < n_slots; ++slot, o += 4) {
+      const Bkt& bk = p.bkt[p.bkt_off[c] + (slot >> 5)];
+      const uint32_t j = bk.j0 + (uint32_t)__builtin_popcount(bk.mask & ((2u << (slot & 31u)) - 1u));
+      const Ent& e = p.ent[p.ent_off[c] + j];
+      const uint32_t folds = e.bf >> 16;
+      if (folds == 0xFFFFu) { o[0] = o[1] = o[2] = o[3] = 0; continue; }
+      const uint64_t q = ((uint64_t)(e.bf & 0xFFFFu) << (folds * p.R[c])) | ((uint64_t)folds << 48);
+      o[0] = (e.cf >> 16) | ((e.cf & 0xFFFFu) << 16);
+      o[1] = 0;
+      o[2] = (uint32_t)q;
+      o[3] = (uint32_t)(q >> 32);
+    }
+    return;
+  }
   uint4* d = nullptr;
   WGA_CUDA(cudaMalloc(&d, n_slots * 16));
   k_expand_table<<<(unsigned)((n_slots + 255) / 256), 256>>>(g->dev.tb, c, (uint32_t)n_slots, d);
@@ -1351,7 +1505,7 @@ void debug_decode_symbols(wga_graph* g, const uint8_t* h_comps, uint64_t n, uint
   WGA_CUDA(cudaMalloc(&dout, (n ? n : 1) * 8));
   WGA_CUDA(cudaMalloc(&dend, 24));
   cudaMemcpy(dc, h_comps, n, cudaMemcpyHostToDevice);
-  k_decode_symbols<<<1, 1>>>(g->dev, dc, n, (int64_t)(ptr - g->stream_base), state, dout, dend);
+  k_decode_symbols<<<1, 1>>>(g->dev, dc, n, ptr - g->stream_base, state, dout, dend);
   count_launch();
   uint64_t end[3] = {0, 0, 0};
   cudaMemcpy(h_out, dout, n * 8, cudaMemcpyDeviceToHost);

@@ -8,17 +8,16 @@
 
 namespace wga {
 
-// Packed tables as the kernels see them (pointers to global memory; kernels may stage them in smem).
+// Packed tables as the kernels see them (global memory; K1 stages them in shared memory).  See common.hpp.
 struct DevTables {
-  const uint16_t* lut;
-  const uint2* ent;
-  uint32_t lut_off[WGA_COMPONENTS];
+  const uint2* bkt;  // {start mask, owner of the first slot} per bucket of 32 slots
+  const uint2* ent;  // {cumul | freq << 16, base | folds << 16} per non-zero symbol, + one sentinel per component
+  uint32_t bkt_off[WGA_COMPONENTS];
   uint32_t ent_off[WGA_COMPONENTS];
+  uint32_t nb[WGA_COMPONENTS];    // buckets
+  uint32_t nent[WGA_COMPONENTS];  // entries including the sentinel
   uint8_t L[WGA_COMPONENTS];
   uint8_t R[WGA_COMPONENTS];
-  uint8_t shift[WGA_COMPONENTS];
-  uint32_t lut_total;  // u16 elements
-  uint32_t ent_total;  // uint2 elements
 };
 
 struct DevGraph {
@@ -37,104 +36,113 @@ struct DevGraph {
 // error bits written to the device error word
 enum : uint32_t {
   ERR_CORRUPT = 1u,       // stream / table inconsistency (reference would panic or return garbage)
-  ERR_WORKSPACE = 2u,     // block staging overflow
+  ERR_WORKSPACE = 2u,     // workspace or output buffer too small
   ERR_RANGE = 4u,         // a reference leaves the decoded range (halo missing)
   ERR_SYMBOL_WIDTH = 8u,  // decoded value does not fit 32 bits
+  ERR_LIMIT = 16u,        // a documented implementation limit (copy-block count, record length)
 };
 
 #define WGA_LOWER_BOUND 65536u  // INTERVAL_LOWER_BOUND, src/ans/mod.rs:21
 
-// Per-component decode parameters packed for one 16-byte (shared-memory) load:
-//   x = lut_off | L << 16 | shift << 21 | R << 26      y = ent_off     z = floor(65536/R)+1 (division by R)
+// Per-component decode parameters packed for one 16-byte load:
+//   x = frame mask (2^L-1) | L << 16 | R << 21     y = bucket offset     z = entry offset     w = floor(65536/R)+1
 __host__ __device__ inline uint4 comp_params(const DevTables& tb, int c) {
   const uint32_t R = tb.R[c] ? tb.R[c] : 1u;
-  return make_uint4(tb.lut_off[c] | ((uint32_t)tb.L[c] << 16) | ((uint32_t)tb.shift[c] << 21) | (R << 26),
-                    tb.ent_off[c], 65536u / R + 1u, 0u);
+  const uint32_t L = tb.L[c];
+  return make_uint4(((1u << L) - 1u) | (L << 16) | (R << 21), tb.bkt_off[c], tb.ent_off[c], 65536u / R + 1u);
+}
+
+// Table accessors.  Global: both levels through the read-only path.
+struct GlobalTables {
+  const uint2* bkt;
+  const uint2* ent;
+  __device__ __forceinline__ uint2 bucket(uint32_t i) const { return __ldg(bkt + i); }
+  __device__ __forceinline__ uint2 entry(const uint4&, uint32_t off, uint32_t j) const { return __ldg(ent + off + j); }
+  __device__ __forceinline__ uint32_t recip(const uint4& cp) const { return cp.w; }
+};
+
+// The decoder of one record: (state, index of the next word below, prefetched next word).
+// The next word is loaded right after the previous extend consumed one, so that the 16-bit renormalisation
+// (decoder.rs:89-93) never waits for memory: the load overlaps the table lookups of the following symbol.
+struct Dec {
+  uint32_t state;
+  uint32_t sp;  // words of the resident span below the record's read position
+  uint32_t w;   // stream[sp-1] (0 when sp == 0)
+};
+
+__device__ __forceinline__ void dec_prime(Dec& d, const uint16_t* __restrict__ stream) {
+  d.w = d.sp ? (uint32_t)__ldg(stream + d.sp - 1) : 0u;
 }
 
 // One 16-bit extend (decoder.rs:89-93).  false = the stream is exhausted.
-// StreamT: anything indexable by the word index (a plain pointer, or WindowedStream below).
-template <class PtrT, class StreamT>
-__device__ __forceinline__ bool ans_extend(uint32_t& state, PtrT& ptr, const StreamT stream) {
-  if (ptr <= 0) return false;
-  --ptr;
-  state = (state << 16) | stream[ptr];
+__device__ __forceinline__ bool ans_extend(Dec& d, const uint16_t* __restrict__ stream) {
+  if (d.sp == 0) return false;
+  d.state = (d.state << 16) | d.w;
+  --d.sp;
+  d.w = d.sp ? (uint32_t)__ldg(stream + d.sp - 1) : 0u;
   return true;
+}
+
+// The fold loop of the reference takes R bits per trip (decoder.rs:74-85, up to 38 trips).  Between two
+// extends the trips only shift the state, so they are done in one step per extend: with n = bit length of the
+// state, the next j = ceil((n-16)/R) trips need no extend (the state stays >= 2^16 until the j-th shift), they
+// consume the low j*R bits, and the chunks enter `fold` first-taken-highest, i.e. in reversed group order.
+static __device__ __noinline__ uint64_t ans_unfold(uint32_t sym, uint32_t folds, uint32_t R, uint32_t recip, Dec& d,
+                                            const uint16_t* __restrict__ stream, uint32_t& err) {
+  const uint32_t rmask = (1u << R) - 1u;
+  uint32_t rem = folds;
+  uint64_t fold = 0;
+  do {
+    const uint32_t n = 32u - (uint32_t)__clz((int)d.state);  // 17..32 (state >= 2^16 here)
+    uint32_t t = ((n - 16u + R - 1u) * recip) >> 16;           // ceil((n-16)/R): trips until state < 2^16
+    t = max(min(t, rem), 1u);  // >= 1 also on corrupt input (state < 2^16 after a failed extend)
+    const uint32_t nb = t * R;                                 // <= 31 bits
+    uint32_t bits = d.state & ((1u << nb) - 1u);
+    d.state >>= nb;
+    uint32_t grp;
+    if (R == 1) grp = __brev(bits) >> (32u - nb);
+    else {
+      grp = 0;
+      for (uint32_t q = 0; q < t; ++q) { grp = (grp << R) | (bits & rmask); bits >>= R; }
+    }
+    fold = (fold << nb) | grp;
+    rem -= t;
+    if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
+  } while (rem);
+  return ((uint64_t)sym << (folds * R)) | fold;
 }
 
 // One ANS symbol.  Restates ANSDecoder::decode (src/ans/decoder.rs:58-87) on the packed tables:
 //   slot  = state & (2^L-1)                                   decoder.rs:59
-//   entry = owner(slot)                                       decoder.rs:60  (lut + forward walk)
+//   entry = owner(slot)                                       decoder.rs:60  (bucket + popcount of the start mask)
 //   state = (state >> L)*freq + slot - cumul                  decoder.rs:62-65
 //   one conditional 16-bit extend                             decoder.rs:67-69, 89-93
 //   folds x { [extend]; fold=(fold<<R)|(state&(2^R-1)); state>>=R; [extend] }   decoder.rs:74-85
 //   result = (base << folds*R) | fold                         decoder.rs:86 with quasi_fold (model4decoder.rs:56-68)
-// The fold loop of the reference takes R bits per trip (up to 38 trips).  Between two extends the trips
-// only shift the state, so they are done here in one step per extend: with n = bit length of the state,
-// the next j = ceil((n-16)/R) trips need no extend (the state stays >= 2^16 until the j-th shift), they
-// consume the low j*R bits, and the chunks enter `fold` first-taken-highest, i.e. in reversed group order.
-// LUT / ENT are pointers to the component-indexed packed tables (global or shared memory); cp = comp_params(c).
-// Everything after the table lookup: state update, extend, folds.  e = entry that owns `slot`.
-// PtrT: index of the next word below in `stream` (int64_t, or uint32_t when the resident span has < 2^32 words).
-template <class PtrT, class StreamT>
-__device__ __forceinline__ uint64_t ans_apply(const uint4 cp, const uint2 e, const uint32_t slot, uint32_t& state,
-                                              PtrT& ptr, const StreamT stream, uint32_t& err) {
+template <class Tab>
+__device__ __forceinline__ uint64_t ans_decode_cp(const uint4 cp, const Tab& tab, Dec& d,
+                                                  const uint16_t* __restrict__ stream, uint32_t& err) {
+  const uint32_t slot = d.state & (cp.x & 0xFFFFu);
   const uint32_t L = (cp.x >> 16) & 31u;
+  const uint2 bk = tab.bucket(cp.y + (slot >> 5));
+  const uint32_t j = bk.y + (uint32_t)__popc(bk.x & ((2u << (slot & 31u)) - 1u));
+  const uint2 e = tab.entry(cp, cp.z, j);
   const uint32_t folds = e.y >> 16;
   if (folds == 0xFFFFu) {  // sentinel: slot beyond the sum of frequencies
     err |= ERR_CORRUPT;
     return 0;
   }
-  state = (state >> L) * (e.x >> 16) + slot - (e.x & 0xFFFFu);
-  if (state < WGA_LOWER_BOUND && !ans_extend(state, ptr, stream)) { err |= ERR_CORRUPT; return 0; }
-  uint64_t sym = e.y & 0xFFFFu;
-  if (folds) {
-    const uint32_t R = cp.x >> 26;
-    const uint32_t rmask = (1u << R) - 1u;
-    uint32_t rem = folds;
-    uint64_t fold = 0;
-    do {
-      const uint32_t n = 32u - (uint32_t)__clz((int)state);     // 17..32 (state >= 2^16 here)
-      uint32_t t = ((n - 16u + R - 1u) * cp.z) >> 16;            // ceil((n-16)/R): trips until state < 2^16
-      t = max(min(t, rem), 1u);  // >= 1 also on corrupt input (state < 2^16 after an extend)
-      const uint32_t nb = t * R;                                 // <= 25 bits
-      uint32_t bits = state & ((1u << nb) - 1u);
-      state >>= nb;
-      uint32_t grp;
-      if (R == 1) grp = __brev(bits) >> (32u - nb);
-      else {
-        grp = 0;
-        for (uint32_t q = 0; q < t; ++q) { grp = (grp << R) | (bits & rmask); bits >>= R; }
-      }
-      fold = (fold << nb) | grp;
-      rem -= t;
-      if (state < WGA_LOWER_BOUND && !ans_extend(state, ptr, stream)) { err |= ERR_CORRUPT; return 0; }
-    } while (rem);
-    sym = (sym << (folds * R)) | fold;
-  }
-  return sym;
+  d.state = (d.state >> L) * (e.x >> 16) + slot - (e.x & 0xFFFFu);
+  if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
+  const uint32_t sym = e.y & 0xFFFFu;
+  if (folds == 0) return sym;
+  return ans_unfold(sym, folds, (cp.x >> 21) & 31u, tab.recip(cp), d, stream, err);
 }
 
-template <class LutPtr, class EntPtr, class PtrT>
-__device__ __forceinline__ uint64_t ans_decode_cp(const uint4 cp, LutPtr lut, EntPtr ent, uint32_t& state,
-                                                  PtrT& ptr, const uint16_t* __restrict__ stream, uint32_t& err) {
-  const uint32_t L = (cp.x >> 16) & 31u;
-  const uint32_t slot = state & ((1u << L) - 1u);
-  uint32_t j = lut[(cp.x & 0xFFFFu) + (slot >> ((cp.x >> 21) & 31u))];
-  const uint32_t eo = cp.y;
-  uint2 e = ent[eo + j];
-  while (slot - (e.x & 0xFFFFu) >= (e.x >> 16)) {  // rare: several symbols share the bucket
-    ++j;
-    e = ent[eo + j];
-  }
-  return ans_apply(cp, e, slot, state, ptr, stream, err);
-}
-
-template <class LutPtr, class EntPtr>
-__device__ __forceinline__ uint64_t ans_decode(const DevTables& tb, LutPtr lut, EntPtr ent, int c,
-                                               uint32_t& state, int64_t& ptr,
+template <class Tab>
+__device__ __forceinline__ uint64_t ans_decode(const DevTables& tb, const Tab& tab, int c, Dec& d,
                                                const uint16_t* __restrict__ stream, uint32_t& err) {
-  return ans_decode_cp(comp_params(tb, c), lut, ent, state, ptr, stream, err);
+  return ans_decode_cp(comp_params(tb, c), tab, d, stream, err);
 }
 
 __device__ __forceinline__ int64_t nat2int(uint64_t x) {

@@ -18,12 +18,9 @@ PackedTablesData pack_tables(const ComponentModel tables[WGA_COMPONENTS]) {
     if (t.frame_size > 16) throw Error(WGA_E_FORMAT, "frame size > 2^16");
     if (t.radix == 0 || t.radix > 16 || t.fidelity == 0) throw Error(WGA_E_FORMAT, "bad radix/fidelity");
     const uint32_t L = (uint32_t)t.frame_size;
-    const uint32_t lut_bits = L < (uint32_t)LUT_BITS ? L : (uint32_t)LUT_BITS;
-    const uint32_t shift = L - lut_bits;
     p.L[c] = (uint8_t)L;
     p.R[c] = (uint8_t)t.radix;
-    p.shift[c] = (uint8_t)shift;
-    p.lut_off[c] = (uint32_t)p.lut.size();
+    p.bkt_off[c] = (uint32_t)p.bkt.size();
     p.ent_off[c] = (uint32_t)p.ent.size();
     const uint32_t frame = 1u << L;
     // non-zero symbols in index order; running sum gives the slot ranges (model4decoder.rs:24-43)
@@ -52,17 +49,27 @@ PackedTablesData pack_tables(const ComponentModel tables[WGA_COMPONENTS]) {
     }
     // sentinel: owns every slot >= sum of frequencies (unused slots; the reference leaves default entries)
     Ent s;
-    s.cf = (last_slot & 0xFFFFu) | (0xFFFFu << 16);
+    s.cf = 0xFFFFu << 16;
     s.bf = 0xFFFFu << 16;
     p.ent.push_back(s);
     starts.push_back(last_slot);
     p.nnz[c] = nnz;
-    // lut: owner of the first slot of every bucket
-    uint32_t j = 0;
-    for (uint32_t b = 0; b < (1u << lut_bits); ++b) {
-      uint32_t slot = b << shift;
-      while (j < nnz && starts[j + 1] <= slot) ++j;
-      p.lut.push_back((uint16_t)j);
+    p.nent[c] = nnz + 1;
+    // buckets of 32 slots: owner of the first slot + mask of the slots (1..31) where a symbol's range starts
+    const uint32_t nb = frame > 32 ? frame / 32 : 1;
+    p.nb[c] = nb;
+    uint32_t j = 0;  // owner of the current slot
+    for (uint32_t b = 0; b < nb; ++b) {
+      const uint32_t s0 = b * 32;
+      while (j < nnz && starts[j + 1] <= s0) ++j;
+      Bkt k;
+      k.j0 = j;
+      k.mask = 0;
+      uint32_t q = j;
+      for (uint32_t sl = 1; sl < 32 && s0 + sl < frame; ++sl) {
+        if (q < nnz && starts[q + 1] == s0 + sl) { k.mask |= 1u << sl; ++q; }
+      }
+      p.bkt.push_back(k);
     }
   }
   return p;
@@ -77,7 +84,7 @@ wga_graph::~wga_graph() {
     cudaFree(d_stream);
     cudaFree(d_states);
     cudaFree(d_ptrs);
-    cudaFree(d_lut);
+    cudaFree(d_bkt);
     cudaFree(d_ent);
     cudaFree(d_err);
     if (h_pub) cudaFreeHost((void*)h_pub);
@@ -194,7 +201,7 @@ void wga_graph::upload() {
   const uint64_t N = prelude.number_of_nodes;
   if (phases.states.size() != N || phases.pointers.size() != N)
     throw Error(WGA_E_FORMAT, "the GPU decode needs .states and .pointers with one phase per node");
-  if (prelude.compression_window > 0xFFFF) throw Error(WGA_E_UNSUPPORTED, "compression window > 65535");
+  if (prelude.compression_window > 4095) throw Error(WGA_E_UNSUPPORTED, "compression window > 4095");
   if (N >= (1ull << 32)) throw Error(WGA_E_UNSUPPORTED, "graphs with >= 2^32 nodes need 64-bit successors");
   int dev = 0;
   WGA_CUDA(cudaGetDevice(&dev));
@@ -220,9 +227,9 @@ void wga_graph::upload() {
     WGA_CUDA(cudaMemcpy(d_ptrs, phases.pointers.data() + (N - res_last), n_res * 8, cudaMemcpyHostToDevice));
   }
   packed = pack_tables(prelude.tables);
-  WGA_CUDA(cudaMalloc(&d_lut, packed.lut.size() * 2 + 16));
+  WGA_CUDA(cudaMalloc(&d_bkt, packed.bkt.size() * 8 + 16));
   WGA_CUDA(cudaMalloc(&d_ent, packed.ent.size() * 8 + 16));
-  WGA_CUDA(cudaMemcpy(d_lut, packed.lut.data(), packed.lut.size() * 2, cudaMemcpyHostToDevice));
+  WGA_CUDA(cudaMemcpy(d_bkt, packed.bkt.data(), packed.bkt.size() * 8, cudaMemcpyHostToDevice));
   WGA_CUDA(cudaMemcpy(d_ent, packed.ent.data(), packed.ent.size() * 8, cudaMemcpyHostToDevice));
   WGA_CUDA(cudaMalloc(&d_err, 4));
   WGA_CUDA(cudaMemset(d_err, 0, 4));
@@ -236,17 +243,16 @@ void wga_graph::upload() {
   }
   on_device = true;
 
-  this->dev.tb.lut = d_lut;
+  this->dev.tb.bkt = d_bkt;
   this->dev.tb.ent = d_ent;
   for (int c = 0; c < WGA_COMPONENTS; ++c) {
-    this->dev.tb.lut_off[c] = packed.lut_off[c];
+    this->dev.tb.bkt_off[c] = packed.bkt_off[c];
     this->dev.tb.ent_off[c] = packed.ent_off[c];
+    this->dev.tb.nb[c] = packed.nb[c];
+    this->dev.tb.nent[c] = packed.nent[c];
     this->dev.tb.L[c] = packed.L[c];
     this->dev.tb.R[c] = packed.R[c];
-    this->dev.tb.shift[c] = packed.shift[c];
   }
-  this->dev.tb.lut_total = (uint32_t)packed.lut.size();
-  this->dev.tb.ent_total = (uint32_t)packed.ent.size();
   this->dev.stream = d_stream;
   this->dev.stream_base = stream_base;
   this->dev.stream_words = stream_words;

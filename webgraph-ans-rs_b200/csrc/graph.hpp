@@ -35,7 +35,7 @@ struct wga_graph {
   uint64_t stream_base = 0, stream_words = 0;
   uint32_t* d_states = nullptr;  // res_last-res_first entries; entry k = node res_last-1-k
   uint64_t* d_ptrs = nullptr;
-  uint16_t* d_lut = nullptr;
+  uint2* d_bkt = nullptr;
   uint2* d_ent = nullptr;
   uint32_t* d_err = nullptr;  // device error word
   // 64 bytes of mapped pinned host memory: kernels publish the scalars the host needs (halo start, arc totals,

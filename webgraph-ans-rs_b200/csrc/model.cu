@@ -12,8 +12,9 @@
 //                           the canonical bins.  Every folding keeps <= 10 significant bits, so it is a
 //                           function of (bit length, top 10 bits) = the canonical bin.
 //        cub segmented sort symbols by ascending (frequency, index)  (:132-138; stable tie-break)
-//    K5b k_scale            scale_freqs (src/utils/data_utils.rs:15-39) + approximated cost (:297-327) for all
-//                           52 foldings x 17 frame sizes of every component, one serial chain per thread.
+//    K5b k_scale            scale_freqs (src/utils/data_utils.rs:15-39) + approximated cost (:297-327, summed in
+//                           symbol-index order like the reference) for all 52 foldings x 17 frame sizes of every
+//                           component, one serial chain per thread.
 //    K5c k_select_emit      the acceptance loop (:140-206), then the winner's table (:216-234).
 //  This file is compiled with -fmad=false: scale_freqs is IEEE f64 `* / + floor` evaluated exactly as the
 //  reference writes it, so the frequency tables are bit-exact with the CPU.  Costs use CUDA's log2 (<= 1 ulp
@@ -233,11 +234,15 @@ __device__ bool scale_freqs_dev(const uint64_t* __restrict__ sorted, uint32_t n,
 }
 
 // ------------------------------------------------------------------------------------------ K5b
-// grid (NP, NC), 32 threads: thread k handles frame 2^k
-__global__ void k_scale(const uint64_t* __restrict__ sorted_keys, const uint32_t* __restrict__ nnz,
-                        const unsigned long long* __restrict__ totals_u, double* __restrict__ cost,
-                        uint8_t* __restrict__ ok) {
-  const int p = blockIdx.x, c = blockIdx.y, k = threadIdx.x;
+// One launch per component c: grid NP, 32 threads: thread k handles frame 2^k.  scale_freqs visits the symbols in
+// ascending frequency, the approximated cost (:297-327) is summed in SYMBOL-INDEX order as the reference does
+// (a different summation order can flip `ratio <= THETA` / `new_cost >= lowest_cost` on a knife-edge input), so
+// the approximated frequencies first go to a scratch slice [p][k][symbol] and are then read back in index order.
+__global__ void k_scale(int c, const uint64_t* __restrict__ sorted_keys, const uint32_t* __restrict__ nnz,
+                        const uint32_t* __restrict__ biggest, const unsigned long long* __restrict__ folded,
+                        const unsigned long long* __restrict__ totals_u, uint32_t* __restrict__ approx_all,
+                        double* __restrict__ cost, uint8_t* __restrict__ ok) {
+  const int p = blockIdx.x, k = threadIdx.x;
   if (k >= NF) return;
   const int F = c_fid[p], R = c_rad[p];
   const uint32_t n = nnz[c * NP + p];
@@ -247,18 +252,25 @@ __global__ void k_scale(const uint64_t* __restrict__ sorted_keys, const uint32_t
   if (n == 0) return;
   const unsigned long long m = 1ull << k;
   if (m < n) return;  // the reference starts at next_power_of_two(n) (:125-128)
-  const uint64_t* sorted = sorted_keys + ((uint64_t)c * NP + p) * FOLD_MAX;
+  const uint64_t seg = ((uint64_t)c * NP + p) * FOLD_MAX;
+  const uint64_t* sorted = sorted_keys + seg;
+  uint32_t* approx = approx_all + ((uint64_t)p * NF + k) * FOLD_MAX;
+  const bool good = scale_freqs_dev(sorted, n, totals_u[c], (long long)m,
+                                    [&](uint32_t sym, unsigned long long, unsigned long long a) { approx[sym] = (uint32_t)a; });
+  ok[idx] = good ? 1 : 0;
+  if (!good) return;
   const uint32_t thr = 1u << (F + R - 1);
   const uint32_t off = ((1u << R) - 1) << (F - 1);
   const double frame = (double)m;
+  const uint32_t len = biggest[c * NP + p] + 1;
   double info = 0.0;
-  bool good = scale_freqs_dev(sorted, n, totals_u[c], (long long)m,
-                              [&](uint32_t sym, unsigned long long f, unsigned long long a) {
-                                double folds = sym < thr ? 0.0 : (double)((sym - thr) / off + 1);
-                                double prob = (double)a / frame;
-                                info += (-log2(prob) + folds * (double)R) * (double)f;  // :322-323
-                              });
-  ok[idx] = good ? 1 : 0;
+  for (uint32_t sym = 0; sym < len; ++sym) {
+    const unsigned long long f = folded[seg + sym];
+    if (f == 0) continue;  // approximated frequency 0 <=> folded frequency 0 (:308-310)
+    const double folds = sym < thr ? 0.0 : (double)((sym - thr) / off + 1);
+    const double prob = (double)approx[sym] / frame;
+    info += (-log2(prob) + folds * (double)R) * (double)f;  // :322-323
+  }
   cost[idx] = info;
 }
 
@@ -537,8 +549,8 @@ void ModelBuilder::build(ComponentModel out[WGA_COMPONENTS], double* h_original_
   impl_->init();
   cudaStream_t st = 0;
   const size_t NSEG = (size_t)NC * NP;
-  DevBuf folded, keys_a, keys_b, nnz, biggest, totals, totals_u, cost, ok, occ, approx, entries, table_len, params,
-      final_cost, tmp;
+  DevBuf folded, keys_a, keys_b, nnz, biggest, totals, totals_u, cost, ok, occ, approx, approx_all, entries, table_len,
+      params, final_cost, tmp;
   folded.ensure(NSEG * FOLD_MAX * 8);
   keys_a.ensure(NSEG * FOLD_MAX * 8);
   keys_b.ensure(NSEG * FOLD_MAX * 8);
@@ -609,8 +621,12 @@ void ModelBuilder::build(ComponentModel out[WGA_COMPONENTS], double* h_original_
                                                 (int64_t)(NSEG * FOLD_MAX), (int64_t)NSEG, sb, se, st));
     count_launch(3);
   }
-  k_scale<<<dim3(NP, NC), 32, 0, st>>>(keys_b.as<uint64_t>(), nnz.as<uint32_t>(), totals_u.as<unsigned long long>(),
-                                       cost.as<double>(), ok.as<uint8_t>());
+  approx_all.ensure((size_t)NP * NF * FOLD_MAX * 4);
+  for (int c = 0; c < NC; ++c)
+    k_scale<<<NP, 32, 0, st>>>(c, keys_b.as<uint64_t>(), nnz.as<uint32_t>(), biggest.as<uint32_t>(),
+                               folded.as<unsigned long long>(), totals_u.as<unsigned long long>(),
+                               approx_all.as<uint32_t>(), cost.as<double>(), ok.as<uint8_t>());
+  count_launch(NC - 1);
   EmitOut eo{entries.as<wga_encoder_entry>(), table_len.as<uint32_t>(), params.as<uint32_t>(), final_cost.as<double>()};
   k_select_emit<<<NC, 256, 0, st>>>(keys_b.as<uint64_t>(), nnz.as<uint32_t>(), biggest.as<uint32_t>(),
                                     totals_u.as<unsigned long long>(), cost.as<double>(), ok.as<uint8_t>(),
