@@ -132,7 +132,9 @@ STRESS_TUNINGS = [
     dict(tile=5, refill=32),                      # tiles smaller than the look-back window
     dict(slotcap=96, rowcap=6),                   # tiles that do not fit shared memory: sub-tiling, nodes left to the global pass
     dict(dbig=8),                                 # most nodes resolved by the global pass (k_hard_*)
-    dict(tile=192, slotcap=700, rowcap=24, k1_blocks=3),
+    dict(tile=200, slotcap=700, rowcap=24, k1_blocks=3),
+    dict(tile=60, rowcap=9, seg=5),               # 128-thread tiles; most records staged compactly; many short merge segments
+    dict(seg=4),
 ]
 
 

@@ -43,12 +43,14 @@ std::atomic<uint64_t> g_kernel_launches{0};
 
 // run-time tuning (tests change these to exercise tile boundaries, sub-tiling and the hard-node path)
 struct Tuning {
-  uint32_t tile = 192;        // nodes per K2 tile = nodes per K1 unit (<= K2_NT - look-back window)
-  uint32_t slotcap = 10240;   // K2: successors a tile keeps in shared memory (words)
-  uint32_t rowcap = 128;      // K2: rows of K1 output a tile keeps in shared memory
+  uint32_t tile = 104;        // nodes per K2 tile = nodes per K1 unit (tile + look-back window <= 256 threads)
+  uint32_t slotcap = 4608;    // K2: successors a tile keeps in shared memory (words)
+  uint32_t rowcap = 96;       // K2: rows of K1 output a tile keeps in shared memory
   uint32_t dbig = 1024;       // outdegree from which a node is resolved from global memory
   uint32_t k1_blocks = 0;     // K1 grid; 0 = one block per SM
   uint32_t refill = 6;        // K1: lanes that must be free before the warp fetches new nodes
+  uint32_t seg = 32;          // K2: positions per merge segment
+  uint32_t dbg = 0;           // (profiling) 1: merge tasks return at once, 2: after their set-up
   uint32_t e2e_chunk = 1u << 19;  // nodes per chunk of the pipelined host entry point
 };
 static Tuning g_tuning;
@@ -61,6 +63,8 @@ int set_tuning(const char* key, uint64_t value) {
   else if (k == "dbig") g_tuning.dbig = (uint32_t)value;
   else if (k == "k1_blocks") g_tuning.k1_blocks = (uint32_t)value;
   else if (k == "refill") g_tuning.refill = (uint32_t)value;
+  else if (k == "seg") g_tuning.seg = (uint32_t)value;
+  else if (k == "dbg") g_tuning.dbg = (uint32_t)value;
   else if (k == "e2e_chunk") g_tuning.e2e_chunk = (uint32_t)value;
   else if (k == "reset") g_tuning = Tuning();
   else return WGA_E_ARG;
@@ -95,8 +99,7 @@ struct RangeView {
   const uint32_t* nodes;  // nullptr: node t is lo + t; else a sorted, duplicate-free list of node ids (random access)
   uint32_t h;         // halo nodes: first - lo
   uint32_t* outdeg;   // n+1
-  uint2* ph;          // n : decoder (state, stream index) after the record's head
-  uint32_t* rb;       // n : head word
+  uint4* nrec;        // n : from K0: decoder (state, stream index) after the record's head, outdegree, head word
   uint64_t* offs;     // n+1, relative to lo
   uint2* meta;        // n : record word of K1
   uint8_t* hardflag;  // n : 0 resolved by its tile, 1 needs the global pass, 2 final without it
@@ -117,6 +120,7 @@ struct RangeView {
   uint32_t* succ;       // caller's array: successors of nodes >= first
   uint64_t succ_cap;
   uint32_t* err;
+  unsigned long long* stats;  // optional per-phase cycle counters of k_tile (WGA_K2_STATS=1), else nullptr
 };
 
 // Index of the node referenced by node t with reference offset r (r != 0).  In a sorted duplicate-free
@@ -162,7 +166,7 @@ __device__ __forceinline__ void load_phase(const DevGraph& g, uint64_t v, Dec& d
 // offset, block count -- and the decoder state after it.  The block count is validated by K1, which knows the
 // outdegree of the referenced node.
 __global__ void __launch_bounds__(TPB) k_heads(DevGraph g, uint64_t lo, const uint32_t* nodes, uint32_t n,
-                                               uint32_t* outdeg, uint2* ph, uint32_t* rb, uint32_t* err_out) {
+                                               uint32_t* outdeg, uint4* nrec, uint32_t* err_out) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n) return;
   if (t == n) { outdeg[n] = 0; return; }
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(TPB) k_heads(DevGraph g, uint64_t lo, const ui
   if (d > 0xFFFFFFFEull) { err |= ERR_SYMBOL_WIDTH; d = 0; }
   if (err) d = 0;
   outdeg[t] = (uint32_t)d;
-  if (ph) {
+  if (nrec) {
     uint32_t rt = 0, b = 0;
     if (d != 0 && g.window != 0) {
       const uint64_t x = ans_decode(g.tb, tab, ReferenceOffset, dc, g.stream, err);
@@ -191,8 +195,7 @@ __global__ void __launch_bounds__(TPB) k_heads(DevGraph g, uint64_t lo, const ui
       }
     }
     if (err) { rt = 0; b = 0; }
-    ph[t] = make_uint2(dc.state, dc.sp);
-    rb[t] = rt | (b << RT_BITS);
+    nrec[t] = make_uint4(dc.state, dc.sp, (uint32_t)d, rt | (b << RT_BITS));
   }
   if (err) atomicOr(err_out, err);
 }
@@ -255,6 +258,7 @@ struct K1Tables {
   uint32_t ent_words;
 };
 
+template <bool ALLHOT>
 struct SmemTables {
   const uint2* bkt;   // shared
   const uint2* ent;   // shared (hot prefix of every component)
@@ -263,7 +267,7 @@ struct SmemTables {
   const uint32_t* recip_tab;  // shared: floor(65536/R)+1
   __device__ __forceinline__ uint2 bucket(uint32_t i) const { return bkt[i]; }
   __device__ __forceinline__ uint2 entry(const uint4& cp, uint32_t off, uint32_t j) const {
-    if (j < cp.w) return ent[off + j];
+    if (ALLHOT || j < cp.w) return ent[off + j];
     return __ldg(gent + gent_off[(cp.x >> 26)] + j);
   }
   __device__ __forceinline__ uint32_t recip(const uint4& cp) const { return recip_tab[(cp.x >> 21) & 31u]; }
@@ -280,8 +284,8 @@ __device__ __forceinline__ bool add_nat(uint32_t v, uint64_t x, uint32_t& out) {
   return (x >> 33) == 0 && (neg ? half < v : (out >= v && out != 0xFFFFFFFFu));
 }
 
-// LIST: node t is rv.nodes[t] (random access) instead of rv.lo + t.
-template <bool LIST>
+// LIST: node t is rv.nodes[t] (random access) instead of rv.lo + t.  ALLHOT: every table entry is in shared memory.
+template <bool LIST, bool ALLHOT>
 __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView rv, K1Tables kt, uint32_t refill_min) {
   extern __shared__ __align__(16) unsigned char k1_smem[];
   uint4* s_cp = reinterpret_cast<uint4*>(k1_smem);                        // 9 x 16 B
@@ -306,13 +310,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
     }
   }
   __syncthreads();
-  const SmemTables tab{s_bkt, s_ent, g.tb.ent, s_goff, s_recip};
+  const SmemTables<ALLHOT> tab{s_bkt, s_ent, g.tb.ent, s_goff, s_recip};
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t stream_id = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
   const uint32_t minint = g.min_interval;
   const uint32_t c_extras = minint ? (uint32_t)IntervalCount : (uint32_t)FirstResidual;
   const uint32_t lo32 = (uint32_t)rv.lo;
+  const uint16_t* __restrict__ const stream = g.stream;
 
   // warp-uniform
   uint32_t nx = 0, ne = 0;      // nodes [nx, ne) of the current unit are not yet handed out
@@ -331,29 +336,36 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
     uint32_t err = 0;
     bool finish = false;
     // ---------------------------------------------------------------- hand out nodes
-    {
-      const uint32_t nf = __ballot_sync(FULL, c == C_FETCH);
+    const uint32_t nf = __ballot_sync(FULL, c == C_FETCH);
+    if (nf) {
       const uint32_t busy = __ballot_sync(FULL, c < C_FETCH);
-      if (nf && (busy == 0 || (uint32_t)__popc(nf) >= refill_min)) {
-        if (nx >= ne && !exhausted) {
-          uint32_t u = 0;
-          if (lane == 0) u = atomicAdd(rv.unit_ctr, 1u);
-          u = __shfl_sync(FULL, u, 0);
-          if (u >= rv.n_units) exhausted = true;
-          else {
+      const uint32_t cnt = (uint32_t)__popc(nf);
+      if (busy == 0 || cnt >= refill_min) {
+        const uint32_t r = (uint32_t)__popc(nf & lt_mask);  // rank among the fetching lanes
+        uint32_t my = NOT_FOUND;
+        uint32_t taken = 0;
+        while (taken < cnt) {  // (uniform) the fetchers may straddle a unit boundary
+          if (nx >= ne) {
+            if (exhausted) break;
+            uint32_t u = 0;
+            if (lane == 0) u = atomicAdd(rv.unit_ctr, 1u);
+            u = __shfl_sync(FULL, u, 0);
+            if (u >= rv.n_units) { exhausted = true; break; }
             nx = u * rv.unit;
             ne = min(nx + rv.unit, rv.n);
             if (lane == 0) rv.unit_stream[u] = stream_id;
           }
+          const uint32_t take = min(ne - nx, cnt - taken);
+          if (r >= taken && r < taken + take) my = nx + (r - taken);
+          nx += take;
+          taken += take;
         }
         if (c == C_FETCH) {
-          const uint32_t my = nx + (uint32_t)__popc(nf & lt_mask);
-          if (exhausted) c = C_IDLE;
-          else if (my < ne) {
+          if (my == NOT_FOUND) { if (exhausted) c = C_IDLE; }
+          else {
             t = my;
-            const uint2 p = rv.ph[t];
-            const uint32_t rbw = rv.rb[t];
-            d = rv.outdeg[t];
+            const uint4 p = rv.nrec[t];
+            d = p.z;
             v = LIST ? rv.nodes[t] : lo32 + t;
             dc.state = p.x;
             dc.sp = p.y;
@@ -364,11 +376,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
             wp = nullptr;
             if (d == 0) finish = true;
             else {
-              dec_prime(dc, g.stream);
-              const uint32_t rt = rbw & RT_MASK;
-              b = rbw >> RT_BITS;
+              dec_prime(dc, stream);
+              const uint32_t rt = p.w & RT_MASK;
+              b = p.w >> RT_BITS;
               if (rt == 0) { extras = d; c = c_extras; }
               else {
+                flags = 8u;  // (internal) the node has a reference
                 dref = rv.outdeg[t - rt];
                 if (b > dref && b - dref > 1u) err |= ERR_CORRUPT;  // at most dref + 1 blocks
                 else if (b == 0) {
@@ -376,85 +389,82 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
                   else { extras = d - dref; if (extras) c = c_extras; else finish = true; }
                 } else { k = b; pos = 0; copied = 0; c = Blocks; }
               }
-              if (rt) flags |= 8u;  // (internal) the node has a reference
             }
           }
         }
-        nx = min(ne, nx + (uint32_t)__popc(nf));
       }
+      if (__all_sync(FULL, c == C_IDLE)) break;
     }
-    if (__all_sync(FULL, c == C_IDLE)) break;
     // ---------------------------------------------------------------- one symbol per busy lane
     const bool decoding = c < C_FETCH && !err && !finish;
     uint32_t val = 0;
     if (decoding) {
-      const uint64_t x = ans_decode_cp(s_cp[c], tab, dc, g.stream, err);
+      const uint64_t x = ans_decode_cp(s_cp[c], tab, dc, stream, err);
       const uint32_t xl = (uint32_t)x;
       const bool wide = (x >> 32) != 0;  // only nat2int arguments (first residual / interval start) may need 33 bits
-      switch (c) {
-        case Blocks: {
-          const uint32_t len = xl + ((k != b) ? 1u : 0u);  // first block literal, later ones minus 1
-          if (wide || len < xl || len > dref - pos) { err |= ERR_CORRUPT; break; }
-          const uint32_t done = b - k;  // blocks before this one: even = copy block
-          if ((done & 1u) == 0) copied += len;
+      if (c >= FirstResidual) {
+        bool ok;
+        if (c == FirstResidual) {
+          ok = add_nat(v, x, val);
+          if (ok && extras >= DSOLO) {  // long run: park it at the tail of the node's own slot
+            uint32_t* slot = node_slot(rv, t);
+            if (!slot) { err |= ERR_WORKSPACE; ok = true; }
+            else {
+              wp = slot + (d - extras);
+              flags |= MF_INSLOT;
+              if (!(flags & 8u) && ni == 0) flags |= MF_FINAL;  // no reference, no interval: the slot is the final list
+            }
+          }
+          c = Residual;
+        } else {
+          val = prev + 1u + xl;
+          ok = !wide && val > prev && val != 0xFFFFFFFFu;
+        }
+        if (!ok) err |= ERR_SYMBOL_WIDTH;
+        prev = val;
+        if (--extras == 0) finish = true;
+      } else if (c == Blocks) {
+        const uint32_t len = xl + ((k != b) ? 1u : 0u);  // first block literal, later ones minus 1
+        if (wide || len < xl || len > dref - pos) err |= ERR_CORRUPT;
+        else {
+          if (((b - k) & 1u) == 0) copied += len;  // blocks before this one: even = copy block
           pos += len;
           val = pos;  // cumulative end
           if (--k == 0) {
             if ((b & 1u) == 0) copied += dref - pos;  // even count: the tail is copied too
-            if (copied > d) { err |= ERR_CORRUPT; break; }
-            extras = d - copied;
-            if (extras) c = c_extras; else finish = true;
+            if (copied > d) err |= ERR_CORRUPT;
+            else {
+              extras = d - copied;
+              if (extras) c = c_extras; else finish = true;
+            }
           }
-          break;
         }
-        case IntervalCount: {
-          if (wide || xl > extras || (uint64_t)xl * minint > extras) { err |= ERR_CORRUPT; break; }
+      } else if (c == IntervalCount) {
+        if (wide || xl > extras || (uint64_t)xl * minint > extras) err |= ERR_CORRUPT;
+        else {
           ni = xl;
           val = xl;
           k = 0;
           c = ni ? (uint32_t)IntervalStart : (uint32_t)FirstResidual;
-          break;
         }
-        case IntervalStart: {
-          bool ok;
-          if (k == 0) ok = add_nat(v, x, val);
-          else { val = prev + 1u + xl; ok = !wide && val > prev && val != 0xFFFFFFFFu; }  // prev: end of the last one
-          if (!ok) { err |= ERR_SYMBOL_WIDTH; break; }
-          prev = val;
-          c = IntervalLen;
-          break;
-        }
-        case IntervalLen: {
-          const uint32_t len = xl + minint;
-          const uint32_t end = prev + len;  // one past the end of this interval
-          if (wide || len < xl || len > extras || len == 0) { err |= ERR_CORRUPT; break; }
-          if (end < prev) { err |= ERR_SYMBOL_WIDTH; break; }
+      } else if (c == IntervalStart) {
+        bool ok;
+        if (k == 0) ok = add_nat(v, x, val);
+        else { val = prev + 1u + xl; ok = !wide && val > prev && val != 0xFFFFFFFFu; }  // prev: end of the last one
+        if (!ok) err |= ERR_SYMBOL_WIDTH;
+        prev = val;
+        c = IntervalLen;
+      } else {  // IntervalLen
+        const uint32_t len = xl + minint;
+        const uint32_t end = prev + len;  // one past the end of this interval
+        if (wide || len < xl || len > extras || len == 0) err |= ERR_CORRUPT;
+        else if (end < prev) err |= ERR_SYMBOL_WIDTH;
+        else {
           val = len;
           prev = end;
           extras -= len;
           if (++k == ni) { if (extras) c = FirstResidual; else finish = true; }
           else c = IntervalStart;
-          break;
-        }
-        case FirstResidual: {
-          if (!add_nat(v, x, val)) { err |= ERR_SYMBOL_WIDTH; break; }
-          prev = val;
-          if (extras >= DSOLO) {  // long run: park it at the tail of the node's own slot
-            uint32_t* slot = node_slot(rv, t);
-            if (!slot) { err |= ERR_WORKSPACE; break; }
-            wp = slot + (d - extras);
-            flags |= MF_INSLOT;
-            if (!(flags & 8u) && ni == 0) flags |= MF_FINAL;  // no reference, no interval: the slot is the final list
-          }
-          if (--extras) c = Residual; else finish = true;
-          break;
-        }
-        default: {  // Residual
-          val = prev + 1u + xl;
-          if (wide || val <= prev || val == 0xFFFFFFFFu) { err |= ERR_SYMBOL_WIDTH; break; }
-          prev = val;
-          if (--extras == 0) finish = true;
-          break;
         }
       }
     }
@@ -474,8 +484,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
         rows_ok = cid != 0xFFFFFFFFu;
         rowp = rv.rows + (size_t)(rows_ok ? cid : 0u) * CH * 32 + lane;
       }
-      if (to_row && rows_ok) *rowp = val;
-      if (to_row) ++ns;
+      if (to_row) {
+        if (rows_ok) *rowp = val;
+        ++ns;
+      }
       rowp += 32;
       ++row;
     }
@@ -493,18 +505,18 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
 }
 
 // -------------------------------------------------------------------------------------------- K2: tile kernel
-constexpr int K2_NT = 256;
+constexpr int K2_NT_MAX = 256;
 constexpr uint32_t HMAX = 64;    // look-back window of a tile (nodes before it that it may have to re-resolve)
 constexpr uint32_t LMAXT = 8;    // deepest reference chain a tile resolves
 constexpr uint32_t NCLS = 8, NBINS = (LMAXT + 1) * NCLS;
-constexpr uint32_t HRECCAP = 1536;  // words of look-back records staged in shared memory
+constexpr uint32_t HRECCAP = 1536;  // words of records staged compactly in shared memory (look-back nodes, long records)
 
 __device__ __forceinline__ uint32_t d_class(uint32_t d) {  // 0 = largest
   return d > 96 ? 0u : d > 64 ? 1u : d > 48 ? 2u : d > 32 ? 3u : d > 16 ? 4u : d > 8 ? 5u : d > 4 ? 6u : 7u;
 }
 
 struct TileCfg {
-  uint32_t tile, slotcap, rowcap, dbig;
+  uint32_t tile, slotcap, rowcap, dbig, nt, seg, taskcap, dbg;
 };
 
 // word k of a record in shared memory (the tile's rows: stride 32; staged look-back records: stride 1)
@@ -524,7 +536,9 @@ struct GlobalRec {
 //   rec(k) = word k of the node's K1 record: [cumulative copy-block ends x b][interval count][start,len x ni][residuals]
 // inslot: the residuals are not in the record but parked at the tail of `out` (MF_INSLOT); they are consumed before
 // the write position reaches them (written <= copied + interval elements + residuals consumed).
-template <class Rec>
+// The next element of the copy run and of the residual run is loaded one step ahead, so that the per-element
+// dependency chain is min / compare / select only.  PADDED: `ref` has one readable word behind its last element.
+template <bool PADDED, class Rec>
 __device__ __forceinline__ void merge_list(uint32_t* __restrict__ out, uint32_t d, const uint32_t* __restrict__ ref,
                                            uint32_t dref, uint32_t b, uint32_t ns, uint32_t minint, const Rec rec,
                                            bool inslot) {
@@ -552,31 +566,34 @@ __device__ __forceinline__ void merge_list(uint32_t* __restrict__ out, uint32_t 
     tail = out;
   }
   // ---- heads of the three runs
-  uint32_t ci = 0, cend = 0, kb = 0, cval = INF;
+  uint32_t ci = 0, cend = 0, kb = 0, cval = INF, cnext = INF;
   auto next_copy_block = [&]() {  // after copy block kb (even): skip block kb+1, copy block kb+2
     for (;;) {
       kb += 2;
       if (kb - 1 < b) { ci = rec(kb - 1); cend = kb < b ? rec(kb) : dref; }
       else { ci = cend = dref; cval = INF; return; }
       if (cend > dref) cend = dref;
-      if (ci < cend) { cval = ref[ci]; return; }
+      if (ci < cend) { cval = ref[ci]; cnext = (PADDED || ci + 1 < dref) ? ref[ci + 1] : INF; return; }
     }
   };
   if (ref) {
     cend = b ? min(rec(0), dref) : dref;
-    if (ci < cend) cval = ref[0]; else next_copy_block();
+    if (ci < cend) { cval = ref[0]; cnext = (PADDED || 1 < dref) ? ref[1] : INF; } else next_copy_block();
   }
   uint32_t ival = INF, ilim = 0;
   if (ni) { ival = rec(ip); ilim = ival + rec(ip + 1); ip += 2; }
-  uint32_t rval = INF;
+  uint32_t rval = INF, rnext = INF;
   if (rp < rend) rval = tail ? tail[rp] : rec(rp);
+  if (!tail && rp + 1 < rend) rnext = rec(rp + 1);
   // ---- merge
   for (uint32_t p = 0; p < d; ++p) {
     const uint32_t mn = min(cval, min(ival, rval));
     if (mn == cval) {
-      if (++ci < cend) cval = ref[ci]; else next_copy_block();
+      if (++ci < cend) { cval = cnext; cnext = (PADDED || ci + 1 < dref) ? ref[ci + 1] : INF; } else next_copy_block();
     } else if (mn == rval) {
-      rval = ++rp < rend ? (tail ? tail[rp] : rec(rp)) : INF;
+      ++rp;
+      if (tail) rval = rp < rend ? tail[rp] : INF;
+      else { rval = rnext; rnext = rp + 1 < rend ? rec(rp + 1) : INF; }
     } else {
       if (++ival == ilim) {
         if (ip < iend) { ival = rec(ip); ilim = ival + rec(ip + 1); ip += 2; } else ival = INF;
@@ -586,28 +603,145 @@ __device__ __forceinline__ void merge_list(uint32_t* __restrict__ out, uint32_t 
   }
 }
 
-__global__ void __launch_bounds__(K2_NT) k_tile(RangeView rv, TileCfg cfg, uint32_t minint, uint32_t lookback) {
+// ---- element-parallel resolve of one level of a tile, everything in shared memory ----------------------------
+// A successor list is the sorted union of three sorted runs with distinct values: the kept elements of the
+// referenced list (copy-block mask), the interval elements, the residuals.  So the final position of an element is
+// its rank in its own run plus the number of elements of the other two runs below it -- no serial merge, no
+// dependency between elements.  Work items of a level: chunks of GCH consecutive positions of a referenced list
+// (block state and ranks advance incrementally inside a chunk), single residuals, single intervals (their elements
+// are consecutive in the output).  All lanes of all warps take items from one flat index space per level.
+constexpr uint32_t GCH = 4;
+
+// the K1 record of a node as the tile sees it: word k at s[base + k * stride]
+struct TileRec {
+  const uint32_t* p;
+  uint32_t stride;
+  __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return p[k * stride]; }
+};
+
+struct NodeCtx {
+  uint32_t* out;
+  const uint32_t* ref;  // nullptr: no (usable) reference
+  uint32_t d, dref, b, ni, ipb, rb0, nres;
+  TileRec rec;
+  // copy blocks: cumulative ends E(q); block q is a copy block when q is even; after the b listed blocks the tail
+  __device__ __forceinline__ uint32_t E(uint32_t q) const { return min(rec(q), dref); }
+  // block that holds position j, and the kept elements before j
+  __device__ __forceinline__ void block_at(uint32_t j, uint32_t& q, uint32_t& bend, uint32_t& kept) const {
+    uint32_t prev = 0;
+    q = 0;
+    kept = 0;
+    while (q < b) {
+      const uint32_t e = E(q);
+      if (e > j) break;
+      if (!(q & 1u)) kept += e - prev;
+      prev = e;
+      ++q;
+    }
+    bend = q < b ? E(q) : dref;
+    if (!(q & 1u)) kept += j - prev;
+  }
+  __device__ __forceinline__ uint32_t res_below(uint32_t x) const {  // residuals < x
+    uint32_t lo = 0, hi = nres;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (rec(rb0 + mid) < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
+  __device__ __forceinline__ uint32_t int_below(uint32_t x) const {  // interval elements < x
+    uint32_t cnt = 0;
+    for (uint32_t k = 0; k < ni; ++k) {
+      const uint32_t st = rec(ipb + 2 * k), len = rec(ipb + 2 * k + 1);
+      if (x > st) cnt += min(x - st, len);
+    }
+    return cnt;
+  }
+  __device__ __forceinline__ uint32_t kept_below(uint32_t x) const {  // kept elements of the referenced list < x
+    if (!ref) return 0;
+    uint32_t lo = 0, hi = dref;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (ref[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    uint32_t q, bend, kept;
+    block_at(lo, q, bend, kept);
+    return kept;
+  }
+};
+
+__device__ __forceinline__ void item_ref_chunk(const NodeCtx& c, uint32_t u) {
+  const uint32_t j0 = u * GCH;
+  uint32_t q, bend, kept;
+  c.block_at(j0, q, bend, kept);
+  uint32_t rcnt = c.res_below(c.ref[j0]);
+#pragma unroll
+  for (uint32_t i = 0; i < GCH; ++i) {
+    const uint32_t j = j0 + i;
+    if (j >= c.dref) break;
+    const uint32_t x = c.ref[j];
+    while (j >= bend && q <= c.b) { ++q; bend = q < c.b ? c.E(q) : c.dref; }
+    while (rcnt < c.nres && c.rec(c.rb0 + rcnt) < x) ++rcnt;
+    if (!(q & 1u)) {
+      const uint32_t pos = kept + rcnt + c.int_below(x);
+      if (pos < c.d) c.out[pos] = x;
+      ++kept;
+    }
+  }
+}
+__device__ __forceinline__ void item_residual(const NodeCtx& c, uint32_t i) {
+  const uint32_t x = c.rec(c.rb0 + i);
+  const uint32_t pos = i + c.kept_below(x) + c.int_below(x);
+  if (pos < c.d) c.out[pos] = x;
+}
+__device__ __forceinline__ void item_interval(const NodeCtx& c, uint32_t k) {
+  uint32_t pos = 0;
+  for (uint32_t q = 0; q < k; ++q) pos += c.rec(c.ipb + 2 * q + 1);
+  const uint32_t st = c.rec(c.ipb + 2 * k), len = c.rec(c.ipb + 2 * k + 1);
+  pos += c.kept_below(st) + c.res_below(st);
+  for (uint32_t e = 0; e < len && pos + e < c.d; ++e) c.out[pos + e] = st + e;
+}
+
+constexpr uint32_t F21 = (1u << 21) - 1;
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_tile(RangeView rv, TileCfg cfg, uint32_t minint, uint32_t lookback) {
   extern __shared__ __align__(16) uint32_t k2_smem[];
   uint32_t* const s_slots = k2_smem;                             // slotcap + 8
-  uint32_t* const s_rows = s_slots + cfg.slotcap + 8;            // rowcap * 32
-  uint32_t* const s_hrec = s_rows + cfg.rowcap * 32;             // HRECCAP
-  uint32_t* const s_d = s_hrec + HRECCAP;                        // per candidate: outdegree
-  uint32_t* const s_so = s_d + K2_NT;                            //   slot offset
-  uint32_t* const s_rb = s_so + K2_NT;                           //   head word
-  uint32_t* const s_row0 = s_rb + K2_NT;                         //   record: first row
-  uint32_t* const s_my = s_row0 + K2_NT;                         //   record: words | lane << 24 | flags << 29
-  uint32_t* const s_hro = s_my + K2_NT;                          //   look-back record: offset in s_hrec, or INF = global
-  uint32_t* const s_st = s_hro + K2_NT;                          //   bit 0 big, 1 hard, 2 part, 3 need ; level << 8
-  uint32_t* const s_order = s_st + K2_NT;                        // tasks by (level, outdegree class)
-  uint32_t* const s_bin = s_order + K2_NT;                       // NBINS + 1
-  uint32_t* const s_binbase = s_bin + NBINS + 8;                 // NBINS + 1
-  __shared__ uint32_t s_scal[8];  // 0 total slots, 1 rmin, 2 rmax, 3 hrec used, 4 maxlev, 5 holes, 6 limit, 7 retry
-  typedef cub::BlockScan<uint32_t, K2_NT> BlockScan;
-  __shared__ typename BlockScan::TempStorage s_scan;
+  uint32_t* const s_rows = s_slots + cfg.slotcap + 8;            // (rowcap + 1) * 32
+  uint32_t* const s_hrec = s_rows + (cfg.rowcap + 1) * 32;       // HRECCAP + 8: records staged compactly
+  unsigned long long* const s_pre = reinterpret_cast<unsigned long long*>(s_hrec + HRECCAP + 8);  // NT + 2: item prefix (3 x 21 bits)
+  uint32_t* const s_d = reinterpret_cast<uint32_t*>(s_pre + NT + 2);  // per candidate: outdegree
+  uint32_t* const s_so = s_d + NT;                               //   slot offset
+  uint32_t* const s_rb = s_so + NT;                              //   head word
+  uint32_t* const s_row0 = s_rb + NT;                            //   record: first row
+  uint32_t* const s_my = s_row0 + NT;                            //   record: words | lane << 24 | flags << 29
+  uint32_t* const s_ck = s_my + NT;                              //   chunk of the record's first row | crosses << 31
+  uint32_t* const s_recp = s_ck + NT;                            //   staged record: word index in k2_smem | (stride 32) << 31
+  uint32_t* const s_st = s_recp + NT;                            //   bit 0 big, 1 hard, 2 part, 3 need, 4 long record ; level << 8
+  uint32_t* const s_ni = s_st + NT;                              //   interval count | has-count-word << 31
+  uint32_t* const s_order = s_ni + NT;                           // task nodes ordered by level
+  uint32_t* const s_bin = s_order + NT;                          // LMAXT + 2 : task nodes per level
+  uint32_t* const s_binbase = s_bin + 16;                        // LMAXT + 2
+  __shared__ uint32_t s_scal[8];  // 1 rmin, 2 rmax, 3 hrec used, 4 maxlev, 5 holes, 6 first overflowing candidate
+  typedef cub::BlockScan<uint32_t, NT> BlockScan;
+  typedef cub::BlockScan<unsigned long long, NT> BlockScan64;
+  __shared__ union { typename BlockScan::TempStorage a; typename BlockScan64::TempStorage b; } s_scan;
+  constexpr uint32_t NW = NT / 32;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t A = blockIdx.x * cfg.tile, B = min(A + cfg.tile, rv.n);
   const uint32_t my_stream = rv.unit_stream[blockIdx.x];
+  const uint32_t longrec = max(cfg.rowcap / 3, 1u);  // records longer than this are staged compactly, not with the rows
+  long long tk0 = 0;
+  auto tick = [&](int phase) {  // debug: cycles per phase, summed over tiles (thread 0 of every block)
+    if (rv.stats && tid == 0) {
+      const long long now = clock64();
+      atomicAdd(&rv.stats[phase], (unsigned long long)(now - tk0));
+      tk0 = now;
+    }
+  };
+  if (rv.stats && tid == 0) { tk0 = clock64(); atomicAdd(&rv.stats[15], 1ull); }
 
   for (uint32_t a = A; a < B;) {
     const uint32_t C0 = a > lookback ? a - lookback : 0u;
@@ -620,22 +754,32 @@ __global__ void __launch_bounds__(K2_NT) k_tile(RangeView rv, TileCfg cfg, uint3
     uint2 m = make_uint2(0, 0);
     const uint32_t t = C0 + tid;
     if (t < B) {
-      d = rv.outdeg[t];
-      rbw = rv.rb[t];
+      const uint4 nr = rv.nrec[t];
       m = rv.meta[t];
-      const uint32_t fl = m.y >> 29;
-      big = (d >= cfg.dbig || 2u * (m.y & NSYM_MAX) > cfg.rowcap || fl != 0) ? 1u : 0u;
+      const uint32_t us = rv.unit_stream[t / rv.unit];
+      d = nr.z;
+      rbw = nr.w;
+      const uint32_t fl = m.y >> 29, nsym = m.y & NSYM_MAX;
+      big = (d >= cfg.dbig || nsym > HRECCAP / 2 || fl != 0) ? 1u : 0u;
+      if (!big && (nsym > longrec || tid < own0)) big |= 16u;  // staged compactly (look-back records always are)
+      uint32_t ck = 0;
+      if (nsym && !(big & 1u)) {
+        ck = rv.stream_chunks[us * MAXC + (m.x >> CH_SHIFT)];
+        if ((m.x & (CH - 1)) + nsym > CH) ck |= 0x80000000u;  // the record continues in another chunk
+      }
       s_d[tid] = d;
       s_rb[tid] = rbw;
       s_row0[tid] = m.x;
       s_my[tid] = m.y;
+      s_ck[tid] = ck;
     }
     s_st[tid] = big;
     if (tid < 8) s_scal[tid] = 0;
     __syncthreads();
+    tick(0);
     // -------------------------------------------------------------- reference chains: depth, hardness, needed look-back nodes
     if (t < B) {
-      hard = big;
+      hard = big & 1u;
       uint32_t j = tid;
       while (!hard) {
         const uint32_t rt = s_rb[j] & RT_MASK;
@@ -648,29 +792,33 @@ __global__ void __launch_bounds__(K2_NT) k_tile(RangeView rv, TileCfg cfg, uint3
       }
     }
     __syncthreads();
+    const uint32_t nsym = m.y & NSYM_MAX;
+    const bool longr = (big & 16u) != 0;
+    uint32_t hro = INF;
     for (;;) {  // shrink the round until it fits shared memory
       M = limit - C0;
       const bool owned = tid >= own0 && tid < M;
       const bool part = tid < M && !hard && (owned || (s_st[tid] & 8u));
       uint32_t so = 0;
-      BlockScan(s_scan).ExclusiveSum(part ? d : 0u, so, total_slots);
-      const uint32_t nsym = m.y & NSYM_MAX;
-      if (tid == 0) { s_scal[1] = INF; s_scal[2] = 0; s_scal[6] = INF; }
+      BlockScan(s_scan.a).ExclusiveSum(part ? d : 0u, so, total_slots);
+      if (tid == 0) { s_scal[1] = INF; s_scal[2] = 0; s_scal[3] = 0; s_scal[6] = INF; }
       __syncthreads();
-      if (owned && part && nsym) {
-        atomicMin(&s_scal[1], m.x);
-        atomicMax(&s_scal[2], m.x + nsym);
+      hro = INF;
+      if (part && nsym) {
+        if (longr) hro = atomicAdd(&s_scal[3], nsym);
+        else {
+          atomicMin(&s_scal[1], m.x);
+          atomicMax(&s_scal[2], m.x + nsym);
+        }
       }
       // first candidate whose slot would not fit
       if (part && so + d > cfg.slotcap) atomicMin(&s_scal[6], tid);
       __syncthreads();
       const uint32_t rmin = s_scal[1], rmax = s_scal[2], over = s_scal[6];
-      fits = over == INF && (rmax <= rmin || rmax - rmin <= cfg.rowcap);
+      fits = over == INF && (rmax <= rmin || rmax - rmin <= cfg.rowcap) && s_scal[3] <= HRECCAP;
       if (fits || limit == a + 1) {
         s_so[tid] = so;
-        uint32_t st = (s_st[tid] & 9u) | (hard << 1) | (part && fits ? 4u : 0u) | (lev << 8);
-        __syncthreads();
-        s_st[tid] = st;
+        s_st[tid] = (s_st[tid] & 25u) | (hard << 1) | (part ? 4u : 0u) | (lev << 8);
         break;
       }
       // halve the owned range (or cut it at the first slot overflow, whichever is smaller)
@@ -679,21 +827,15 @@ __global__ void __launch_bounds__(K2_NT) k_tile(RangeView rv, TileCfg cfg, uint3
       limit = nl;
       __syncthreads();
     }
-    __syncthreads();
-    // a single node that does not fit with its ancestors: the global pass takes it
-    if (!fits) {
-      if (tid >= own0 && tid < M) hard = 1;
-    }
-    const uint32_t st_mine = s_st[tid];
-    const bool part = (st_mine & 4u) != 0;
+    // (a single node that does not fit with its ancestors: !fits, the global pass takes it)
     const bool owned = tid >= own0 && tid < M;
+    const bool part = fits && tid < M && !hard && (owned || (s_st[tid] & 8u));
     const uint32_t rmin = s_scal[1], rmax = s_scal[2];
     // -------------------------------------------------------------- owned nodes: hard list, flags
     if (owned) {
       const uint32_t fl = m.y >> 29;
       uint32_t hf = 0;
       if (!part) hf = (d == 0 || (fl & (MF_ERR | MF_FINAL))) ? 2u : 1u;
-      if (!part && d == 0) hf = 2u;
       rv.hardflag[t] = (uint8_t)hf;
       if (hf == 1u) {
         const uint32_t pos = atomicAdd(rv.hard_count, 1u);
@@ -701,67 +843,126 @@ __global__ void __launch_bounds__(K2_NT) k_tile(RangeView rv, TileCfg cfg, uint3
       }
       if (!part && d != 0) s_scal[5] = 1;  // hole in the owned slots: no bulk copy-out
     }
-    // -------------------------------------------------------------- stage in: the tile's rows, look-back records
-    if (fits && rmax > rmin) {
-      for (uint32_t r = rmin + warp; r < rmax; r += K2_NT / 32)
-        s_rows[(r - rmin) * 32 + lane] = *row_word(rv, my_stream, r, lane);
-    }
-    s_hro[tid] = INF;
-    if (part && !owned) {
-      const uint32_t nsym = m.y & NSYM_MAX;
-      if (nsym) {
-        const uint32_t o = atomicAdd(&s_scal[3], nsym);
-        if (o + nsym <= HRECCAP) s_hro[tid] = o;
+    if (!fits) { __syncthreads(); a = limit; continue; }
+    tick(1);
+    // -------------------------------------------------------------- stage in: the tile's rows, compact records
+    if (rmax > rmin) {  // 16-byte pieces, independent of one another: all the loads are in flight together
+      const uint32_t np = (rmax - rmin) * 8;
+#pragma unroll 4
+      for (uint32_t q = tid; q < np; q += NT) {
+        const uint32_t r = rmin + (q >> 3);
+        const uint32_t cid = rv.stream_chunks[my_stream * MAXC + (r >> CH_SHIFT)];
+        const uint4 v = *reinterpret_cast<const uint4*>(rv.rows + ((size_t)cid * CH + (r & (CH - 1))) * 32 + (q & 7u) * 4);
+        *reinterpret_cast<uint4*>(s_rows + (r - rmin) * 32 + (q & 7u) * 4) = v;
       }
     }
-    if (part) atomicMax(&s_scal[4], lev);
-    __syncthreads();
-    for (uint32_t i = warp; i < own0; i += K2_NT / 32) {  // one warp per look-back node
-      const uint32_t o = s_hro[i];
-      if (o == INF) continue;
-      const uint32_t my = s_my[i], nsym = my & NSYM_MAX, ln = (my >> 24) & 31u, r0 = s_row0[i];
-      const uint32_t s = rv.unit_stream[(C0 + i) / rv.unit];
-      for (uint32_t k = lane; k < nsym; k += 32) s_hrec[o + k] = *row_word(rv, s, r0 + k, ln);
+    s_recp[tid] = 0;
+    if (part && nsym) {
+      if (longr) {  // every thread copies its own compact record (a column of the rows: one word per row)
+        s_recp[tid] = (uint32_t)(s_hrec - k2_smem) + hro;
+        const uint32_t ck = s_ck[tid], ln = (m.y >> 24) & 31u;
+        if (!(ck >> 31)) {
+          const uint32_t* src = rv.rows + ((size_t)ck * CH + (m.x & (CH - 1))) * 32 + ln;
+#pragma unroll 4
+          for (uint32_t q = 0; q < nsym; ++q) s_hrec[hro + q] = src[(size_t)q * 32];
+        } else {
+          const uint32_t s = rv.unit_stream[t / rv.unit];
+          for (uint32_t q = 0; q < nsym; ++q) s_hrec[hro + q] = *row_word(rv, s, m.x + q, ln);
+        }
+      } else s_recp[tid] = ((uint32_t)(s_rows - k2_smem) + (m.x - rmin) * 32 + ((m.y >> 24) & 31u)) | 0x80000000u;
     }
-    // -------------------------------------------------------------- tasks by (level, outdegree class)
-    for (uint32_t i = tid; i <= NBINS; i += K2_NT) s_bin[i] = 0;
+    if (part) atomicMax(&s_scal[4], lev);
+    if (tid < 16) s_bin[tid] = 0;
     __syncthreads();
-    uint32_t bin = 0, rank = 0;
+    tick(2);
+    // -------------------------------------------------------------- work items per node; nodes ordered by level
     const bool task = part && d != 0;
+    const uint32_t rt = rbw & RT_MASK, bcnt = rbw >> RT_BITS;
+    uint32_t rank = 0;
     if (task) {
-      bin = lev * NCLS + d_class(d);
-      rank = atomicAdd(&s_bin[bin], 1u);
+      const TileRec myrec{k2_smem + (s_recp[tid] & 0x7FFFFFFFu), (s_recp[tid] >> 31) ? 32u : 1u};
+      const bool has_cnt = nsym > bcnt && minint != 0;
+      uint32_t ni = has_cnt ? myrec(bcnt) : 0u, nres = 0;
+      const uint32_t hdr = bcnt + (has_cnt ? 1u : 0u);
+      if (nsym < hdr || 2ull * ni > (uint64_t)(nsym - hdr)) ni = 0;  // inconsistent record
+      else nres = nsym - hdr - 2 * ni;
+      s_ni[tid] = ni | (has_cnt ? 0x80000000u : 0u);
+      (void)nres;
+      rank = atomicAdd(&s_bin[lev], 1u);
     }
     __syncthreads();
     if (tid == 0) {
       uint32_t acc = 0;
-      for (uint32_t i = 0; i < NBINS; ++i) { s_binbase[i] = acc; acc += s_bin[i]; }
-      s_binbase[NBINS] = acc;
+      for (uint32_t l = 0; l <= LMAXT + 1; ++l) { s_binbase[l] = acc; acc += s_bin[l]; }
     }
     __syncthreads();
-    if (task) s_order[s_binbase[bin] + rank] = tid;
+    if (task) s_order[s_binbase[lev] + rank] = tid;
+    // prefix of the item counts in level order: thread q holds the node at position q
     __syncthreads();
+    {
+      const uint32_t ntask = s_binbase[LMAXT + 1];
+      unsigned long long mine = 0, pre = 0, total = 0;
+      if (tid < ntask) {
+        // recompute the node's counts from its parsed record (cheaper than passing them through shared memory)
+        const uint32_t nn = s_order[tid];
+        const uint32_t rbn = s_rb[nn], nsn = s_my[nn] & NSYM_MAX, nin = s_ni[nn];
+        const uint32_t rtn = rbn & RT_MASK, bn = rbn >> RT_BITS;
+        const uint32_t hdr = bn + (nin >> 31);
+        const uint32_t nin_ = nin & 0x7FFFFFFFu;
+        const uint32_t nresn = nsn >= hdr + 2 * nin_ ? nsn - hdr - 2 * nin_ : 0u;
+        const uint32_t drefn = rtn ? s_d[nn - rtn] : 0u;
+        mine = (unsigned long long)((drefn + GCH - 1) / GCH) | ((unsigned long long)nresn << 21) | ((unsigned long long)nin_ << 42);
+      }
+      BlockScan64(s_scan.b).ExclusiveSum(mine, pre, total);
+      if (tid < ntask) s_pre[tid] = pre;
+      if (tid == 0) { s_pre[ntask] = total; }
+    }
+    __syncthreads();
+    tick(3);
     // -------------------------------------------------------------- resolve, one level after the other
     const uint32_t maxlev = s_scal[4];
     for (uint32_t l = 0; l <= maxlev; ++l) {
-      const uint32_t beg = s_binbase[l * NCLS], end = s_binbase[(l + 1) * NCLS];
-      for (uint32_t q = beg + tid; q < end; q += K2_NT) {
-        const uint32_t i = s_order[q];
-        const uint32_t di = s_d[i], rbi = s_rb[i], my = s_my[i];
-        const uint32_t rt = rbi & RT_MASK, bi = rbi >> RT_BITS, nsym = my & NSYM_MAX;
-        const uint32_t* ref = rt ? s_slots + s_so[i - rt] : nullptr;
-        const uint32_t dref = rt ? s_d[i - rt] : 0u;
-        uint32_t* out = s_slots + s_so[i];
-        if (i >= own0) merge_list(out, di, ref, dref, bi, nsym, minint, SmemRec{s_rows + (s_row0[i] - rmin) * 32 + ((my >> 24) & 31u), 32u}, false);
-        else if (s_hro[i] != INF) merge_list(out, di, ref, dref, bi, nsym, minint, SmemRec{s_hrec + s_hro[i], 1u}, false);
-        else  // a look-back record that did not fit the staging area: read it from global memory
-          merge_list(out, di, ref, dref, bi, nsym, minint,
-                     GlobalRec{&rv, rv.unit_stream[(C0 + i) / rv.unit], s_row0[i], (my >> 24) & 31u}, false);
+      const uint32_t lb = s_binbase[l], le = s_binbase[l + 1];
+      if (le > lb) {
+        const unsigned long long P0 = s_pre[lb], P1 = s_pre[le];
+        const uint32_t NA = (uint32_t)(P1 & F21) - (uint32_t)(P0 & F21);
+        const uint32_t NB = (uint32_t)((P1 >> 21) & F21) - (uint32_t)((P0 >> 21) & F21);
+        const uint32_t NC = (uint32_t)((P1 >> 42) & F21) - (uint32_t)((P0 >> 42) & F21);
+        for (uint32_t f = tid; f < NA + NB + NC; f += NT) {
+          const uint32_t kind = f < NA ? 0u : f < NA + NB ? 1u : 2u;
+          const uint32_t sh = kind * 21;
+          const uint32_t key = (uint32_t)((P0 >> sh) & F21) + (kind == 0 ? f : kind == 1 ? f - NA : f - NA - NB);
+          uint32_t lo = lb, hi = le;  // largest position whose prefix is <= key
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((uint32_t)((s_pre[mid] >> sh) & F21) <= key) lo = mid; else hi = mid;
+          }
+          const uint32_t u = key - (uint32_t)((s_pre[lo] >> sh) & F21);
+          const uint32_t n = s_order[lo];
+          const uint32_t rbn = s_rb[n], nin = s_ni[n], rp = s_recp[n];
+          const uint32_t rtn = rbn & RT_MASK;
+          NodeCtx c;
+          c.out = s_slots + s_so[n];
+          c.d = s_d[n];
+          c.dref = rtn ? s_d[n - rtn] : 0u;
+          c.ref = c.dref ? s_slots + s_so[n - rtn] : nullptr;
+          c.b = rbn >> RT_BITS;
+          c.ni = nin & 0x7FFFFFFFu;
+          c.ipb = c.b + (nin >> 31);
+          c.rb0 = c.ipb + 2 * c.ni;
+          const uint32_t nsn = s_my[n] & NSYM_MAX;
+          c.nres = nsn >= c.rb0 ? nsn - c.rb0 : 0u;
+          c.rec = TileRec{k2_smem + (rp & 0x7FFFFFFFu), (rp >> 31) ? 32u : 1u};
+          if (kind == 0) item_ref_chunk(c, u);
+          else if (kind == 1) item_residual(c, u);
+          else item_interval(c, u);
+        }
       }
       __syncthreads();
+      tick(4 + min(l, 3u));
     }
     // -------------------------------------------------------------- copy out the owned lists
-    if (fits) {
+    {
       const uint32_t s_beg = s_so[own0];
       const uint32_t s_end = total_slots;  // owned nodes are the last candidates
       const bool straddle = a < rv.h && limit > rv.h;
@@ -771,9 +972,9 @@ __global__ void __launch_bounds__(K2_NT) k_tile(RangeView rv, TileCfg cfg, uint3
         if (a < rv.h) { if (o1 <= rv.halo_cap) dst = rv.halo_succ + o0; }
         else { const uint64_t bs = rv.offs[rv.h]; if (o1 - bs <= rv.succ_cap) dst = rv.succ + (o0 - bs); }
         if (!dst) { if (tid == 0) atomicOr(rv.err, ERR_WORKSPACE); }
-        else for (uint32_t e = s_beg + tid; e < s_end; e += K2_NT) dst[e - s_beg] = s_slots[e];
+        else for (uint32_t e = s_beg + tid; e < s_end; e += NT) dst[e - s_beg] = s_slots[e];
       } else {
-        for (uint32_t i = own0 + warp; i < M; i += K2_NT / 32) {
+        for (uint32_t i = own0 + warp; i < M; i += NW) {
           if (!(s_st[i] & 4u) || s_d[i] == 0) continue;
           uint32_t* dst = node_slot(rv, C0 + i);
           if (!dst) { if (lane == 0) atomicOr(rv.err, ERR_WORKSPACE); continue; }
@@ -783,6 +984,7 @@ __global__ void __launch_bounds__(K2_NT) k_tile(RangeView rv, TileCfg cfg, uint3
       }
     }
     __syncthreads();
+    tick(8);
     a = limit;
   }
 }
@@ -796,7 +998,7 @@ __global__ void __launch_bounds__(256) k_hard_levels(RangeView rv) {
   if (i < nh) {
     uint32_t j = rv.hard_list[i];
     for (;;) {
-      const uint32_t rt = rv.rb[j] & RT_MASK;
+      const uint32_t rt = rv.nrec[j].w & RT_MASK;
       if (rt == 0) break;
       j -= rt;
       if (rv.hardflag[j] != 1) break;
@@ -813,7 +1015,7 @@ __global__ void __launch_bounds__(128) k_hard_resolve(RangeView rv, uint32_t lev
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *rv.hard_count || rv.hard_lev[i] != level) return;
   const uint32_t t = rv.hard_list[i];
-  const uint32_t d = rv.outdeg[t], rbw = rv.rb[t];
+  const uint32_t d = rv.outdeg[t], rbw = rv.nrec[t].w;
   const uint2 m = rv.meta[t];
   const uint32_t rt = rbw & RT_MASK, b = rbw >> RT_BITS, nsym = m.y & NSYM_MAX, fl = m.y >> 29;
   uint32_t* out = node_slot(rv, t);
@@ -825,7 +1027,7 @@ __global__ void __launch_bounds__(128) k_hard_resolve(RangeView rv, uint32_t lev
     dref = rv.outdeg[t - rt];
     if (!ref) { atomicOr(rv.err, ERR_WORKSPACE); return; }
   }
-  merge_list(out, d, ref, dref, b, nsym, minint, GlobalRec{&rv, rv.unit_stream[t / rv.unit], m.x, (m.y >> 24) & 31u},
+  merge_list<false>(out, d, ref, dref, b, nsym, minint, GlobalRec{&rv, rv.unit_stream[t / rv.unit], m.x, (m.y >> 24) & 31u},
              (fl & MF_INSLOT) != 0);
 }
 
@@ -973,10 +1175,11 @@ struct Scalars {
   uint32_t hard_count;
   uint32_t maxlevel;
 };
+static_assert(NBINS + 1 <= 96, "bin prefix handles three bins per lane");
 static_assert(sizeof(Scalars) <= 256, "Scalars must fit the cleared line");
 
 struct WorkspacePlan {
-  uint64_t off_outdeg, off_ph, off_rb, off_offs, off_meta, off_hflag, off_hlist, off_hlev, off_ustream, off_schunks, off_cub,
+  uint64_t off_outdeg, off_nrec, off_offs, off_meta, off_hflag, off_hlist, off_hlev, off_ustream, off_schunks, off_cub,
       off_halo, off_rows;
   uint64_t cub_bytes, halo_cap, fixed_bytes;
 };
@@ -986,8 +1189,7 @@ WorkspacePlan plan_workspace(uint64_t n, uint32_t unit) {
   uint64_t o = 0;
   o += 256;  // Scalars
   p.off_outdeg = o; o = align_up(o + 4 * (n + 1), 256);
-  p.off_ph = o; o = align_up(o + 8 * n, 256);
-  p.off_rb = o; o = align_up(o + 4 * n, 256);
+  p.off_nrec = o; o = align_up(o + 16 * n, 256);
   p.off_offs = o; o = align_up(o + 8 * (n + 1), 256);
   p.off_meta = o; o = align_up(o + 8 * n, 256);
   p.off_hflag = o; o = align_up(o + n, 256);
@@ -1007,10 +1209,16 @@ WorkspacePlan plan_workspace(uint64_t n, uint32_t unit) {
   return p;
 }
 
+// threads of a tile block: the look-back window plus the tile's nodes, one candidate per thread
+uint32_t tile_threads(const Tuning& tn, uint32_t window) {
+  const uint32_t lookback = std::min<uint32_t>(HMAX, window * LMAXT);
+  const uint32_t want = (tn.tile ? tn.tile : 1) + lookback;
+  return want <= 128 ? 128u : want <= 160 ? 160u : want <= 192 ? 192u : 256u;
+}
 uint32_t effective_tile(const Tuning& tn, uint32_t window) {
   const uint32_t lookback = std::min<uint32_t>(HMAX, window * LMAXT);
   uint32_t tile = tn.tile ? tn.tile : 1;
-  if (tile > K2_NT - lookback) tile = K2_NT - lookback;
+  if (tile > K2_NT_MAX - lookback) tile = K2_NT_MAX - lookback;
   return tile;
 }
 
@@ -1054,16 +1262,16 @@ void outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets
   if (first > last || last > g->res_last || first < g->res_first) throw Error(WGA_E_ARG, "range outside the resident nodes");
   uint64_t n = last - first;
   WorkspacePlan p = plan_workspace(n, 192);
-  if (ws_bytes < p.off_ph) throw Error(WGA_E_WORKSPACE, "workspace too small");
+  if (ws_bytes < p.off_nrec) throw Error(WGA_E_WORKSPACE, "workspace too small");
   uint8_t* w = (uint8_t*)ws;
   uint32_t* outdeg = (uint32_t*)(w + p.off_outdeg);
-  k_heads<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, first, nullptr, (uint32_t)n, outdeg, nullptr, nullptr, g->d_err);
+  k_heads<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, first, nullptr, (uint32_t)n, outdeg, nullptr, g->d_err);
   count_launch();
   // the scan's temporary storage lives behind the outdegrees (the other arrays of the plan are not used here)
   size_t cb = p.cub_bytes;
-  if (ws_bytes < p.off_ph + cb) throw Error(WGA_E_WORKSPACE, "workspace too small");
+  if (ws_bytes < p.off_nrec + cb) throw Error(WGA_E_WORKSPACE, "workspace too small");
   cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(outdeg, U32ToU64());
-  WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_ph, cb, it, d_offsets, (int64_t)(n + 1), st));
+  WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_nrec, cb, it, d_offsets, (int64_t)(n + 1), st));
   count_launch(2);
   WGA_CUDA(cudaGetLastError());
 }
@@ -1129,7 +1337,7 @@ uint64_t plan_k1_tables(const wga_graph* g, K1Tables& kt, int smem_limit) {
 }
 
 uint64_t tile_smem_bytes(const TileCfg& c) {
-  return 4ull * ((uint64_t)c.slotcap + 8 + 32ull * c.rowcap + HRECCAP + 8ull * K2_NT + 2 * (NBINS + 8));
+  return 4ull * ((uint64_t)c.slotcap + 8 + 32ull * (c.rowcap + 1) + HRECCAP + 8 + 2ull * (c.nt + 2) + 10ull * c.nt + 32);
 }
 
 }  // namespace
@@ -1142,7 +1350,7 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
   const uint64_t n = rv.n;
   const DeviceInfo& di = device_info(g->device);
   // ---- K0 + scan
-  k_heads<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, rv.lo, rv.nodes, (uint32_t)n, rv.outdeg, rv.ph, rv.rb, g->d_err);
+  k_heads<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, rv.lo, rv.nodes, (uint32_t)n, rv.outdeg, rv.nrec, g->d_err);
   count_launch();
   {
     size_t cb = p.cub_bytes;
@@ -1158,31 +1366,44 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
     uint32_t blocks = tn.k1_blocks ? tn.k1_blocks : (uint32_t)di.sms;
     blocks = std::min<uint32_t>(blocks, (rv.n_units + K1_WARPS - 1) / K1_WARPS);
     blocks = std::max<uint32_t>(1u, std::min<uint32_t>(blocks, MAX_STREAMS / K1_WARPS));
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[0]) {
-      WGA_CUDA(cudaFuncSetAttribute(k_entropy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin - 1024));
-      WGA_CUDA(cudaFuncSetAttribute(k_entropy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin - 1024));
-      attr_done[0] = true;
-    }
+    bool allhot = true;
+    for (int c = Blocks; c <= Residual; ++c) allhot = allhot && kt.cp[c].w >= g->packed.nent[c];
     const uint32_t refill = std::max<uint32_t>(1u, std::min<uint32_t>(32u, tn.refill));
-    if (rv.nodes) k_entropy<true><<<blocks, K1_THREADS, smem, st>>>(g->dev, rv, kt, refill);
-    else k_entropy<false><<<blocks, K1_THREADS, smem, st>>>(g->dev, rv, kt, refill);
+    auto launch = [&](auto kern) {
+      WGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin - 1024));
+      kern<<<blocks, K1_THREADS, smem, st>>>(g->dev, rv, kt, refill);
+    };
+    if (rv.nodes) { if (allhot) launch(k_entropy<true, true>); else launch(k_entropy<true, false>); }
+    else { if (allhot) launch(k_entropy<false, true>); else launch(k_entropy<false, false>); }
     count_launch();
   }
   mark(g, st);  // 2: entropy decode done
   // ---- K2: tiles
+  static unsigned long long* d_stats = nullptr;
+  static const bool want_stats = getenv("WGA_K2_STATS") != nullptr;
+  if (want_stats) {
+    if (!d_stats) WGA_CUDA(cudaMalloc(&d_stats, 16 * 8));
+    WGA_CUDA(cudaMemsetAsync(d_stats, 0, 16 * 8, st));
+    rv.stats = d_stats;
+  }
   const uint32_t window = (uint32_t)g->prelude.compression_window;
   const uint32_t lookback = std::min<uint32_t>(HMAX, window * LMAXT);
   {
-    TileCfg cfg{rv.unit, std::max<uint32_t>(64u, tn.slotcap), std::max<uint32_t>(1u, tn.rowcap), std::max<uint32_t>(2u, tn.dbig)};
+    TileCfg cfg{rv.unit, (std::max<uint32_t>(64u, tn.slotcap) + 3u) & ~3u, std::max<uint32_t>(3u, tn.rowcap),
+                std::min<uint32_t>(std::max<uint32_t>(2u, tn.dbig), 32768u), tile_threads(tn, window),
+                std::max<uint32_t>(4u, tn.seg), 0u, tn.dbg};
+    // every candidate is at least one task; the referenced lists and the residuals each fit the slots
+    cfg.taskcap = (cfg.nt + 2 * (cfg.slotcap / cfg.seg) + 8 + 3) & ~3u;
     const uint64_t smem = tile_smem_bytes(cfg);
     if ((int64_t)smem > (int64_t)di.smem_optin - 2048) throw Error(WGA_E_ARG, "tile tuning exceeds shared memory");
-    static uint64_t attr_bytes = 0;
-    if (attr_bytes < smem) {
-      WGA_CUDA(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_bytes = smem;
-    }
-    k_tile<<<rv.n_units, K2_NT, smem, st>>>(rv, cfg, g->dev.min_interval, lookback);
+    auto launch = [&](auto kern) {
+      WGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<rv.n_units, cfg.nt, smem, st>>>(rv, cfg, g->dev.min_interval, lookback);
+    };
+    if (cfg.nt == 128) launch(k_tile<128>);
+    else if (cfg.nt == 160) launch(k_tile<160>);
+    else if (cfg.nt == 192) launch(k_tile<192>);
+    else launch(k_tile<256>);
     count_launch();
   }
   mark(g, st);  // 3: tiles done
@@ -1193,6 +1414,13 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
   WGA_CUDA(cudaGetLastError());
   tot[0] = g->h_pub[1];
   tot[1] = g->h_pub[2];
+  if (want_stats) {
+    unsigned long long hs[16];
+    WGA_CUDA(cudaMemcpy(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost));
+    const double nb = hs[15] ? (double)hs[15] : 1.0;
+    fprintf(stderr, "[k_tile cycles/block] load %.0f plan %.0f stage %.0f tasks %.0f lev0 %.0f lev1 %.0f lev2 %.0f lev3+ %.0f out %.0f (blocks %llu)\n",
+            hs[0] / nb, hs[1] / nb, hs[2] / nb, hs[3] / nb, hs[4] / nb, hs[5] / nb, hs[6] / nb, hs[7] / nb, hs[8] / nb, hs[15]);
+  }
   uint32_t herr = (uint32_t)g->h_pub[4];
   const uint32_t nhard = (uint32_t)g->h_pub[5];
   if (tot[0] > rv.halo_cap) {
@@ -1239,8 +1467,7 @@ static void apply_env_tuning() {
 
 static void bind_views(RangeView& rv, uint8_t* w, const WorkspacePlan& p, Scalars* sc, uint64_t ws_bytes, uint32_t unit) {
   rv.outdeg = (uint32_t*)(w + p.off_outdeg);
-  rv.ph = (uint2*)(w + p.off_ph);
-  rv.rb = (uint32_t*)(w + p.off_rb);
+  rv.nrec = (uint4*)(w + p.off_nrec);
   rv.meta = (uint2*)(w + p.off_meta);
   rv.hardflag = (uint8_t*)(w + p.off_hflag);
   rv.hard_list = (uint32_t*)(w + p.off_hlist);
@@ -1383,7 +1610,7 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   count_launch();
   if (!d_succ) {  // sizing call: only the outdegrees of the queries (first symbol of each record)
     uint32_t* deg = all;
-    k_heads<<<(unsigned)((nq + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, 0, qid, (uint32_t)nq, deg, nullptr, nullptr, g->d_err);
+    k_heads<<<(unsigned)((nq + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, 0, qid, (uint32_t)nq, deg, nullptr, g->d_err);
     size_t cbs = b.cub_bytes;
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(deg, U32ToU64());
     WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + b.off_cub, cbs, it, d_offsets, (int64_t)(nq + 1), st));

@@ -87,8 +87,9 @@ __device__ __forceinline__ bool ans_extend(Dec& d, const uint16_t* __restrict__ 
 // extends the trips only shift the state, so they are done in one step per extend: with n = bit length of the
 // state, the next j = ceil((n-16)/R) trips need no extend (the state stays >= 2^16 until the j-th shift), they
 // consume the low j*R bits, and the chunks enter `fold` first-taken-highest, i.e. in reversed group order.
-static __device__ __noinline__ uint64_t ans_unfold(uint32_t sym, uint32_t folds, uint32_t R, uint32_t recip, Dec& d,
-                                            const uint16_t* __restrict__ stream, uint32_t& err) {
+// General form (any fold count, any radix); the decoders below only come here when the one-step form does not apply.
+__device__ __forceinline__ uint64_t ans_unfold_general(uint32_t sym, uint32_t folds, uint32_t R, uint32_t recip, Dec& d,
+                                                       const uint16_t* __restrict__ stream, uint32_t& err) {
   const uint32_t rmask = (1u << R) - 1u;
   uint32_t rem = folds;
   uint64_t fold = 0;
@@ -99,12 +100,8 @@ static __device__ __noinline__ uint64_t ans_unfold(uint32_t sym, uint32_t folds,
     const uint32_t nb = t * R;                                 // <= 31 bits
     uint32_t bits = d.state & ((1u << nb) - 1u);
     d.state >>= nb;
-    uint32_t grp;
-    if (R == 1) grp = __brev(bits) >> (32u - nb);
-    else {
-      grp = 0;
-      for (uint32_t q = 0; q < t; ++q) { grp = (grp << R) | (bits & rmask); bits >>= R; }
-    }
+    uint32_t grp = 0;
+    for (uint32_t q = 0; q < t; ++q) { grp = (grp << R) | (bits & rmask); bits >>= R; }
     fold = (fold << nb) | grp;
     rem -= t;
     if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
@@ -119,6 +116,9 @@ static __device__ __noinline__ uint64_t ans_unfold(uint32_t sym, uint32_t folds,
 //   one conditional 16-bit extend                             decoder.rs:67-69, 89-93
 //   folds x { [extend]; fold=(fold<<R)|(state&(2^R-1)); state>>=R; [extend] }   decoder.rs:74-85
 //   result = (base << folds*R) | fold                         decoder.rs:86 with quasi_fold (model4decoder.rs:56-68)
+// The folds are taken in ONE step when no extend falls between two trips ((folds-1)*R < bit length - 16: the state
+// stays >= 2^16 until the last shift) and the group reversal is cheap (radix 1: bit reversal; one or two groups);
+// that covers practically every folded symbol, so all lanes of a warp run the same short sequence.
 template <class Tab>
 __device__ __forceinline__ uint64_t ans_decode_cp(const uint4 cp, const Tab& tab, Dec& d,
                                                   const uint16_t* __restrict__ stream, uint32_t& err) {
@@ -136,7 +136,20 @@ __device__ __forceinline__ uint64_t ans_decode_cp(const uint4 cp, const Tab& tab
   if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
   const uint32_t sym = e.y & 0xFFFFu;
   if (folds == 0) return sym;
-  return ans_unfold(sym, folds, (cp.x >> 21) & 31u, tab.recip(cp), d, stream, err);
+  const uint32_t R = (cp.x >> 21) & 31u;
+  const uint32_t nb = folds * R;
+  const uint32_t room = 16u - (uint32_t)__clz((int)d.state);  // bit length - 16 (state >= 2^16)
+  if (nb - R < room && (R == 1 || folds <= 2)) {
+    const uint32_t bits = d.state & ((1u << nb) - 1u);  // nb <= 31
+    d.state >>= nb;
+    uint32_t grp;
+    if (R == 1) grp = __brev(bits) >> (32u - nb);
+    else if (folds == 2) grp = ((bits & ((1u << R) - 1u)) << R) | (bits >> R);
+    else grp = bits;
+    if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
+    return ((uint64_t)sym << nb) | grp;
+  }
+  return ans_unfold_general(sym, folds, R, tab.recip(cp), d, stream, err);
 }
 
 template <class Tab>
