@@ -175,8 +175,8 @@ int wga_debug_decode_symbols(wga_graph* g, const uint8_t* h_components, uint64_t
                              uint64_t* h_out, uint64_t* h_end_ptr, uint32_t* h_end_state);
 
 /* Kernel tuning knobs of the decode path (process-wide; the parity tests shrink them so that small graphs
- * cross tile boundaries, force sub-tiling and take the global-memory pass).  Keys: "tile", "slotcap", "rowcap",
- * "dbig", "k1_blocks", "refill", "e2e_chunk", "reset". */
+ * cross unit boundaries, refill lanes one by one and stride the grid).  Keys: "unit", "k1_blocks", "refill",
+ * "k2_blocks", "e2e_chunk", "reset". */
 int wga_debug_set_tuning(const char* key, uint64_t value);
 
 /* ---------------------------------------------------------------- model build -------------------- */

@@ -128,21 +128,18 @@ def test_graph_decode_matches_oracle(W, O, gpu, n, deg, params, seed):
 
 
 STRESS_TUNINGS = [
-    dict(tile=37, k1_blocks=1, refill=1),        # many tiny tiles / K1 units, one K1 block
-    dict(tile=5, refill=32),                      # tiles smaller than the look-back window
-    dict(slotcap=96, rowcap=6),                   # tiles that do not fit shared memory: sub-tiling, nodes left to the global pass
-    dict(dbig=8),                                 # most nodes resolved by the global pass (k_hard_*)
-    dict(tile=200, slotcap=700, rowcap=24, k1_blocks=3),
-    dict(tile=60, rowcap=9, seg=5),               # 128-thread tiles; most records staged compactly; many short merge segments
-    dict(seg=4),
+    dict(unit=37, k1_blocks=1, refill=1, k2_blocks=3),   # many tiny K1 units on one block; a K2 grid with long shares per block
+    dict(unit=5, refill=32, k2_blocks=1),
+    dict(unit=100000, k1_blocks=2, k2_blocks=5000),
+    dict(unit=64, refill=12),
 ]
 
 
 @pytest.mark.parametrize("tuning", range(len(STRESS_TUNINGS)))
 @pytest.mark.parametrize("n,deg,params,seed", [GRAPH_CASES[2], GRAPH_CASES[4], GRAPH_CASES[6], GRAPH_CASES[8]])
 def test_graph_decode_under_stress_tunings(W, O, gpu, n, deg, params, seed, tuning):
-    """Same parity check with the kernel knobs changed so that small graphs exercise tile boundaries,
-    sub-tiling, look-back records read from global memory and the global pass for nodes a tile cannot hold."""
+    """Same parity check with the kernel knobs changed so that small graphs exercise unit boundaries, rows that
+    continue in another chunk, lane refill and grid striding."""
     off, succ = make_case(n, deg, seed)
     og = O.OracleGraph.store_csr(off, succ, *params)
     g = open_oracle_graph(W, og)
@@ -161,7 +158,7 @@ def test_graph_decode_under_stress_tunings(W, O, gpu, n, deg, params, seed, tuni
 
 def test_long_records_take_the_cooperative_path(W, O, gpu):
     """Records with thousands of successors (power-law hubs): their residual runs are parked in the node's own
-    slot and the lists are resolved by the global pass (k_hard_*); all must equal the oracle."""
+    slot (not in the row stream) and merged in place; all must equal the oracle."""
     rng = np.random.default_rng(11)
     n = 60000
     off, succ = make_case(n, 6, 77)

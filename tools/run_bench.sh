@@ -1,1 +1,3 @@
-python tools/prof_decode.py web-1m 3 > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_tile" -s 2 -c 1 -o gpurun_out/prof_r02c python tools/prof_decode.py web-1m 3 > gpurun_out/ncu_r02c.log 2>&1; tail -2 gpurun_out/ncu_r02c.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python tools/prof_decode.py web-1m 3 2>&1 | tail -1
+python tools/prof_decode.py eu-2015-host-shaped 3 2>&1 | tail -1

@@ -10,24 +10,19 @@
 //    K0  k_heads       one lane per node, every lane at the same symbol: the fixed-shape head of every record from
 //                      (states[N-1-v], pointers[N-1-v]) -- outdegree, reference offset, block count -- and the
 //                      decoder state after it
-//        cub scan      outdegrees -> CSR offsets
+//        cub scans     outdegrees -> CSR offsets ; (block count + 1 + outdegree) -> record regions
 //    K1  k_entropy     phase one: entropy decode of the rest of every record.  Persistent kernel, one 1024-thread
 //                      block per SM with the decoder tables of the six components in SHARED memory (bucket +
 //                      popcount lookup, no search).  Warps are independent: each pulls units of consecutive nodes
 //                      from a global counter, its lanes take the nodes one by one (ballot-ranked, no atomics) and
-//                      run a per-symbol state machine; every busy lane decodes ONE symbol per iteration and the
-//                      32 produced words (cumulative copy-block ends, interval count, interval starts / lengths,
-//                      prefix-summed residuals) go out as ONE coalesced 128-byte row.  A record is therefore a
-//                      column segment (row0, lane, length) of the warp's row stream.
-//    K2  k_tile        phase two: one block per tile of consecutive nodes, everything in SHARED memory.  The tile's
-//                      rows arrive as one bulk copy; the few predecessor nodes referenced from outside the tile
-//                      (found by walking the reference chains of the tile's own nodes) are re-resolved locally, so
-//                      tiles are independent.  Nodes are bucketed by (reference-chain depth, outdegree class); per
-//                      depth, every lane merges one node -- copied elements of the already finished referenced
-//                      list (block mask), expanded intervals, residuals -- from / into shared memory, and the
-//                      finished tile leaves as one coalesced copy.
-//        k_hard_*      nodes a tile cannot hold (outdegree >= 1024, chains deeper than 8, chains leaving the
-//                      look-back window) are resolved afterwards from global memory, one launch per depth.
+//                      run a per-symbol state machine; every busy lane decodes ONE symbol per iteration and
+//                      appends one word to its node's record (cumulative copy-block ends, interval count, interval
+//                      starts / lengths, prefix-summed residuals).  Reference-free lists without intervals are
+//                      written straight into their CSR slot and are final after K1.
+//    K2  k_levels      phase two, by reference-chain depth: depth of every node that still needs work
+//        cub sort      stable sort by level -> one segment per level, node order kept inside a level
+//        k_resolve     per level, one node per lane: three-way merge (copied elements of the finished
+//                      referenced list, expanded intervals, residuals) into the node's CSR slot
 //    Random access (wga_successors_batch) runs the same kernels on the sorted reference closure of the
 //    query nodes (node-list mode) and gathers the query lists.
 // =============================================================================
@@ -43,28 +38,21 @@ std::atomic<uint64_t> g_kernel_launches{0};
 
 // run-time tuning (tests change these to exercise tile boundaries, sub-tiling and the hard-node path)
 struct Tuning {
-  uint32_t tile = 104;        // nodes per K2 tile = nodes per K1 unit (tile + look-back window <= 256 threads)
-  uint32_t slotcap = 4608;    // K2: successors a tile keeps in shared memory (words)
-  uint32_t rowcap = 96;       // K2: rows of K1 output a tile keeps in shared memory
-  uint32_t dbig = 1024;       // outdegree from which a node is resolved from global memory
+  uint32_t unit = 128;        // nodes per K1 unit (what a warp pulls from the global counter)
   uint32_t k1_blocks = 0;     // K1 grid; 0 = one block per SM
   uint32_t refill = 6;        // K1: lanes that must be free before the warp fetches new nodes
-  uint32_t seg = 32;          // K2: positions per merge segment
-  uint32_t dbg = 0;           // (profiling) 1: merge tasks return at once, 2: after their set-up
+  uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
+                              // equal share of the level, so a partial second wave would double the time
   uint32_t e2e_chunk = 1u << 19;  // nodes per chunk of the pipelined host entry point
 };
 static Tuning g_tuning;
 
 int set_tuning(const char* key, uint64_t value) {
   std::string k(key ? key : "");
-  if (k == "tile") g_tuning.tile = (uint32_t)value;
-  else if (k == "slotcap") g_tuning.slotcap = (uint32_t)value;
-  else if (k == "rowcap") g_tuning.rowcap = (uint32_t)value;
-  else if (k == "dbig") g_tuning.dbig = (uint32_t)value;
+  if (k == "unit") g_tuning.unit = (uint32_t)value;
   else if (k == "k1_blocks") g_tuning.k1_blocks = (uint32_t)value;
   else if (k == "refill") g_tuning.refill = (uint32_t)value;
-  else if (k == "seg") g_tuning.seg = (uint32_t)value;
-  else if (k == "dbg") g_tuning.dbg = (uint32_t)value;
+  else if (k == "k2_blocks") g_tuning.k2_blocks = (uint32_t)value;
   else if (k == "e2e_chunk") g_tuning.e2e_chunk = (uint32_t)value;
   else if (k == "reset") g_tuning = Tuning();
   else return WGA_E_ARG;
@@ -79,19 +67,19 @@ constexpr uint32_t FULL = 0xffffffffu;
 constexpr uint32_t INF = 0xffffffffu;  // "stream exhausted"; successor ids are <= 0xfffffffe
 constexpr uint32_t NOT_FOUND = 0xFFFFFFFFu;
 
-// ---- K1 output: rows ------------------------------------------------------------------------------------
-constexpr uint32_t CH_SHIFT = 7, CH = 1u << CH_SHIFT;  // rows per chunk (16 KB)
-constexpr uint32_t MAXC = 512;                         // chunks per row stream (one stream per K1 warp)
+// ---- K1 output: records --------------------------------------------------------------------------------
+// Every node owns a region of (block count + 2 + outdegree) words in the record buffer (offsets: a second scan
+// of the K0 heads); K1 writes the node's record there word by word:
+//   [cumulative copy-block ends x b][interval count][start,len x ni][number of residuals]
+// (2 ni <= outdegree because an interval covers at least two successors).  The residuals themselves (already
+// prefix-summed) are parked at the tail of the node's own CSR slot.
 constexpr int K1_THREADS = 1024;
 constexpr uint32_t K1_WARPS = K1_THREADS / 32;
-constexpr uint32_t MAX_STREAMS = 8192;
-// record word of node t (uint2): x = first row of the record in its stream
-//                                y = words (24 bits) | lane << 24 | flags << 29
+// record word of node t: words written (24 bits) | flags << 29
 constexpr uint32_t MF_ERR = 1u, MF_INSLOT = 2u, MF_FINAL = 4u;
 constexpr uint32_t NSYM_MAX = (1u << 24) - 1;
 // head word of node t (K0): reference offset in node-list positions (12 bits) | block count << 12
 constexpr uint32_t RT_BITS = 12, RT_MASK = (1u << RT_BITS) - 1, B_MAX = (1u << (32 - RT_BITS)) - 1;
-constexpr uint32_t DSOLO = 1024;  // residual runs at least this long are parked in the node's own slot, not in rows
 
 struct RangeView {
   uint64_t lo;        // first decoded node (halo start)
@@ -101,26 +89,19 @@ struct RangeView {
   uint32_t* outdeg;   // n+1
   uint4* nrec;        // n : from K0: decoder (state, stream index) after the record's head, outdegree, head word
   uint64_t* offs;     // n+1, relative to lo
-  uint2* meta;        // n : record word of K1
-  uint8_t* hardflag;  // n : 0 resolved by its tile, 1 needs the global pass, 2 final without it
-  uint32_t* hard_list;  // nodes with hardflag 1
-  uint32_t* hard_lev;
-  uint32_t* hard_count;
-  uint32_t* maxlevel;   // deepest chain among the hard nodes
-  uint32_t* rows;       // row storage: chunk c = rows[c*CH*32 ...]
-  uint32_t rows_cap;    // chunks
-  uint32_t* chunk_ctr;
-  uint32_t* stream_chunks;  // [streams][MAXC]
-  uint32_t* unit_stream;    // [units]
+  uint32_t* meta;     // n : record word of K1
+  uint64_t* roff;     // n+1 : record regions
+  uint32_t* recs;     // record buffer
+  uint64_t recs_cap;  // words
+  uint32_t* maxlevel;   // deepest reference chain seen by k_levels (only tracked from LCAP up)
   uint32_t* unit_ctr;
-  uint32_t unit;        // nodes per unit (= K2 tile)
+  uint32_t unit;        // nodes per K1 unit
   uint32_t n_units;
   uint32_t* halo_succ;  // successors of halo nodes
   uint64_t halo_cap;
   uint32_t* succ;       // caller's array: successors of nodes >= first
   uint64_t succ_cap;
   uint32_t* err;
-  unsigned long long* stats;  // optional per-phase cycle counters of k_tile (WGA_K2_STATS=1), else nullptr
 };
 
 // Index of the node referenced by node t with reference offset r (r != 0).  In a sorted duplicate-free
@@ -144,12 +125,6 @@ __device__ __forceinline__ uint32_t* node_slot(const RangeView& rv, uint32_t t) 
   if (t < rv.h) return e <= rv.halo_cap ? rv.halo_succ + o : nullptr;
   const uint64_t b = rv.offs[rv.h];
   return e - b <= rv.succ_cap ? rv.succ + (o - b) : nullptr;
-}
-
-// word k of a record that starts at (row0, lane) of row stream s
-__device__ __forceinline__ const uint32_t* row_word(const RangeView& rv, uint32_t s, uint32_t row, uint32_t lane) {
-  const uint32_t c = rv.stream_chunks[s * MAXC + (row >> CH_SHIFT)];
-  return rv.rows + ((size_t)c * CH + (row & (CH - 1))) * 32 + lane;
 }
 
 // (state, pointer) of node v: ANSBVGraphDecoderFactory::new_decoder (bvgraph_decoder_factory.rs:46-58)
@@ -202,6 +177,10 @@ __global__ void __launch_bounds__(TPB) k_heads(DevGraph g, uint64_t lo, const ui
 
 struct U32ToU64 {
   __host__ __device__ uint64_t operator()(uint32_t x) const { return (uint64_t)x; }
+};
+// words of a node's record region: block count + interval count word + at most one word per successor
+struct RecWords {
+  __host__ __device__ uint64_t operator()(const uint4& r) const { return (uint64_t)(r.w >> RT_BITS) + 2u + r.z; }
 };
 
 // -------------------------------------------------------------------------------------------- halo
@@ -313,7 +292,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
   const SmemTables<ALLHOT> tab{s_bkt, s_ent, g.tb.ent, s_goff, s_recip};
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t stream_id = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
   const uint32_t minint = g.min_interval;
   const uint32_t c_extras = minint ? (uint32_t)IntervalCount : (uint32_t)FirstResidual;
   const uint32_t lo32 = (uint32_t)rv.lo;
@@ -322,14 +300,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
   // warp-uniform
   uint32_t nx = 0, ne = 0;      // nodes [nx, ne) of the current unit are not yet handed out
   bool exhausted = false;
-  uint32_t row = 0;             // rows written so far by this warp
-  uint32_t* rowp = nullptr;     // row `row` of the stream, this lane's word
-  bool rows_ok = true;
-
   // per-lane record state
-  uint32_t c = C_FETCH, t = 0, v = 0, prev = 0, d = 0, dref = 0, k = 0, b = 0, copied = 0, pos = 0, extras = 0, ni = 0,
-           row0 = 0, ns = 0, flags = 0;
-  uint32_t* wp = nullptr;  // residuals parked in the node's own slot (MF_INSLOT)
+  uint32_t c = C_FETCH, t = 0, v = 0, prev = 0, d = 0, dref = 0, k = 0, b = 0, copied = 0, sgn = 1, ub = 0xFFFFFFFEu, extras = 0,
+           ni = 0, ns = 0, flags = 0;
+  uint32_t* wp = nullptr;    // residuals parked in the node's own slot (MF_INSLOT)
+  uint32_t* recw = nullptr;  // the node's region of the record buffer
   Dec dc{0, 0, 0};
 
   for (;;) {
@@ -353,7 +328,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
             if (u >= rv.n_units) { exhausted = true; break; }
             nx = u * rv.unit;
             ne = min(nx + rv.unit, rv.n);
-            if (lane == 0) rv.unit_stream[u] = stream_id;
           }
           const uint32_t take = min(ne - nx, cnt - taken);
           if (r >= taken && r < taken + take) my = nx + (r - taken);
@@ -369,16 +343,19 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
             v = LIST ? rv.nodes[t] : lo32 + t;
             dc.state = p.x;
             dc.sp = p.y;
-            row0 = row;
             ns = 0;
             flags = 0;
             ni = 0;
+            ub = 0xFFFFFFFEu;
             wp = nullptr;
             if (d == 0) finish = true;
             else {
               dec_prime(dc, stream);
               const uint32_t rt = p.w & RT_MASK;
               b = p.w >> RT_BITS;
+              const uint64_t ro = rv.roff[t];
+              recw = rv.recs + ro;
+              if (ro + b + 2 + d > rv.recs_cap) err |= ERR_WORKSPACE;
               if (rt == 0) { extras = d; c = c_extras; }
               else {
                 flags = 8u;  // (internal) the node has a reference
@@ -387,7 +364,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
                 else if (b == 0) {
                   if (dref > d) err |= ERR_CORRUPT;
                   else { extras = d - dref; if (extras) c = c_extras; else finish = true; }
-                } else { k = b; pos = 0; copied = 0; c = Blocks; }
+                } else { k = b; prev = 0xFFFFFFFFu; copied = 0; sgn = 1u; ub = dref; c = Blocks; }
               }
             }
           }
@@ -396,639 +373,259 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
       if (__all_sync(FULL, c == C_IDLE)) break;
     }
     // ---------------------------------------------------------------- one symbol per busy lane
+    // The step after the table lookup is the same instruction sequence for every component: the value is one of
+    //   gap  prev + 1 + x     copy-block ends (cumulative: prev starts at -1), later interval starts, residuals
+    //   nat  v + nat2int(x)   first interval start, first residual
+    //   len  x (+ min_interval_length)   interval count, interval length
+    // and counters / next component follow from a few selects, so the lanes of a warp do not diverge here.
     const bool decoding = c < C_FETCH && !err && !finish;
     uint32_t val = 0;
     if (decoding) {
       const uint64_t x = ans_decode_cp(s_cp[c], tab, dc, stream, err);
       const uint32_t xl = (uint32_t)x;
       const bool wide = (x >> 32) != 0;  // only nat2int arguments (first residual / interval start) may need 33 bits
-      if (c >= FirstResidual) {
-        bool ok;
-        if (c == FirstResidual) {
-          ok = add_nat(v, x, val);
-          if (ok && extras >= DSOLO) {  // long run: park it at the tail of the node's own slot
-            uint32_t* slot = node_slot(rv, t);
-            if (!slot) { err |= ERR_WORKSPACE; ok = true; }
-            else {
-              wp = slot + (d - extras);
-              flags |= MF_INSLOT;
-              if (!(flags & 8u) && ni == 0) flags |= MF_FINAL;  // no reference, no interval: the slot is the final list
-            }
-          }
-          c = Residual;
-        } else {
-          val = prev + 1u + xl;
-          ok = !wide && val > prev && val != 0xFFFFFFFFu;
-        }
-        if (!ok) err |= ERR_SYMBOL_WIDTH;
-        prev = val;
-        if (--extras == 0) finish = true;
-      } else if (c == Blocks) {
-        const uint32_t len = xl + ((k != b) ? 1u : 0u);  // first block literal, later ones minus 1
-        if (wide || len < xl || len > dref - pos) err |= ERR_CORRUPT;
+      const bool isblk = c == Blocks, isicnt = c == IntervalCount, isist = c == IntervalStart, isilen = c == IntervalLen,
+                 isres0 = c == FirstResidual;
+      const bool nat = isres0 || (isist && k == ni);  // k = intervals still to come
+      const bool gap = !nat && (isblk || isist || c == Residual);
+      uint32_t natv;
+      const bool natok = add_nat(v, x, natv);
+      const uint32_t gapv = prev + 1u + xl;
+      const uint32_t lenv = xl + (isilen ? minint : 0u);
+      val = nat ? natv : gap ? gapv : lenv;
+      const bool gapok = !wide && gapv >= prev + 1u && gapv <= ub;  // (block ends: ub = outdegree of the referenced node)
+      const bool lenok = !wide && lenv >= xl && lenv <= extras && (!isilen || (lenv != 0 && prev + lenv >= prev)) &&
+                         (!isicnt || (uint64_t)xl * minint <= extras);
+      if (!(nat ? natok : gap ? gapok : lenok)) err |= (nat || (gap && !isblk)) ? ERR_SYMBOL_WIDTH : ERR_CORRUPT;
+      if (nat || gap) prev = val;
+      else if (isilen) prev += lenv;  // one past the end of this interval
+      if (isblk) { copied += sgn * val; sgn = 0u - sgn; }  // alternating sum of the cumulative ends = copied elements
+      extras -= c >= FirstResidual ? 1u : (isilen ? lenv : 0u);
+      if (isicnt) { ni = xl; k = xl; }
+      else if (isblk || isilen) --k;
+      if (isblk && k == 0) {  // end of the block run: what is left for intervals and residuals
+        if ((b & 1u) == 0) copied += dref;  // even count: the tail of the referenced list is copied too
+        if (copied > d) err |= ERR_CORRUPT;
+        extras = d - copied;
+        ub = 0xFFFFFFFEu;
+      }
+      if (isres0 && !err) {
+        // The residuals go to the tail of the node's own slot (they are merged in place by K2: the write position
+        // never overtakes the unread ones); without reference and intervals they are the final list.
+        uint32_t* slot = node_slot(rv, t);
+        if (!slot) err |= ERR_WORKSPACE;
         else {
-          if (((b - k) & 1u) == 0) copied += len;  // blocks before this one: even = copy block
-          pos += len;
-          val = pos;  // cumulative end
-          if (--k == 0) {
-            if ((b & 1u) == 0) copied += dref - pos;  // even count: the tail is copied too
-            if (copied > d) err |= ERR_CORRUPT;
-            else {
-              extras = d - copied;
-              if (extras) c = c_extras; else finish = true;
-            }
-          }
-        }
-      } else if (c == IntervalCount) {
-        if (wide || xl > extras || (uint64_t)xl * minint > extras) err |= ERR_CORRUPT;
-        else {
-          ni = xl;
-          val = xl;
-          k = 0;
-          c = ni ? (uint32_t)IntervalStart : (uint32_t)FirstResidual;
-        }
-      } else if (c == IntervalStart) {
-        bool ok;
-        if (k == 0) ok = add_nat(v, x, val);
-        else { val = prev + 1u + xl; ok = !wide && val > prev && val != 0xFFFFFFFFu; }  // prev: end of the last one
-        if (!ok) err |= ERR_SYMBOL_WIDTH;
-        prev = val;
-        c = IntervalLen;
-      } else {  // IntervalLen
-        const uint32_t len = xl + minint;
-        const uint32_t end = prev + len;  // one past the end of this interval
-        if (wide || len < xl || len > extras || len == 0) err |= ERR_CORRUPT;
-        else if (end < prev) err |= ERR_SYMBOL_WIDTH;
-        else {
-          val = len;
-          prev = end;
-          extras -= len;
-          if (++k == ni) { if (extras) c = FirstResidual; else finish = true; }
-          else c = IntervalStart;
+          wp = slot + (d - extras - 1u);
+          flags |= (!(flags & 8u) && ni == 0) ? (MF_INSLOT | MF_FINAL) : MF_INSLOT;
+          recw[ns++] = extras + 1u;  // the record ends with the number of parked residuals
         }
       }
+      // next component
+      const bool run_more = (isblk || isicnt || isilen) && k != 0;
+      const bool more = extras != 0;
+      uint32_t nc = isist ? (uint32_t)IntervalLen
+                   : run_more ? (isblk ? (uint32_t)Blocks : (uint32_t)IntervalStart)
+                   : c >= FirstResidual ? (uint32_t)Residual
+                   : isblk ? c_extras : (uint32_t)FirstResidual;
+      finish = !isist && !run_more && !more;
+      c = nc;
     }
-    // ---------------------------------------------------------------- one coalesced row
-    const bool have = decoding && !err;
-    const bool to_row = have && wp == nullptr;
-    if (have && wp != nullptr) *wp++ = val;
-    if (__any_sync(FULL, to_row)) {
-      if ((row & (CH - 1)) == 0) {  // new chunk
-        uint32_t cid = 0;
-        if (lane == 0) {
-          cid = atomicAdd(rv.chunk_ctr, 1u);
-          if (cid < rv.rows_cap && (row >> CH_SHIFT) < MAXC) rv.stream_chunks[stream_id * MAXC + (row >> CH_SHIFT)] = cid;
-          else { cid = 0xFFFFFFFFu; atomicOr(rv.err, ERR_WORKSPACE); }
-        }
-        cid = __shfl_sync(FULL, cid, 0);
-        rows_ok = cid != 0xFFFFFFFFu;
-        rowp = rv.rows + (size_t)(rows_ok ? cid : 0u) * CH * 32 + lane;
-      }
-      if (to_row) {
-        if (rows_ok) *rowp = val;
-        ++ns;
-      }
-      rowp += 32;
-      ++row;
+    // ---------------------------------------------------------------- one word of the record
+    if (decoding && !err) {
+      if (wp != nullptr) *wp++ = val;
+      else recw[ns++] = val;
     }
     // ---------------------------------------------------------------- end of a record
     if (err) {
       atomicOr(rv.err, err);
-      rv.meta[t] = make_uint2(0u, (lane << 24) | (MF_ERR << 29));
+      rv.meta[t] = MF_ERR << 29;
       c = C_FETCH;
     } else if (finish) {
       if (ns > NSYM_MAX) { atomicOr(rv.err, ERR_LIMIT); flags |= MF_ERR; }
-      rv.meta[t] = make_uint2(row0, (ns & NSYM_MAX) | (lane << 24) | ((flags & 7u) << 29));
+      rv.meta[t] = (ns & NSYM_MAX) | ((flags & 7u) << 29);
       c = C_FETCH;
     }
   }
 }
 
-// -------------------------------------------------------------------------------------------- K2: tile kernel
-constexpr int K2_NT_MAX = 256;
-constexpr uint32_t HMAX = 64;    // look-back window of a tile (nodes before it that it may have to re-resolve)
-constexpr uint32_t LMAXT = 8;    // deepest reference chain a tile resolves
-constexpr uint32_t NCLS = 8, NBINS = (LMAXT + 1) * NCLS;
-constexpr uint32_t HRECCAP = 1536;  // words of records staged compactly in shared memory (look-back nodes, long records)
+// -------------------------------------------------------------------------------------------- K2
+// Phase two: copy-block resolution + interval expansion + merge, by reference-chain depth.
+//   k_levels   depth[v] = ref ? depth[v-ref]+1 : 0 for every node that still needs work
+//   cub sort   stable sort by depth: one contiguous segment per level, node order kept inside a level (the lanes of
+//              a warp then work on neighbouring nodes, whose records and referenced lists share sectors)
+//   k_resolve  one launch per level; one node per LANE, lanes pull nodes from their block's share of the level: a
+//              three-way merge of (copied elements of the finished referenced list, expanded intervals, residuals)
+//              into the node's CSR slot.  A large pool of nodes per level keeps every warp of the machine busy; a
+//              shared-memory tile per block was measured and lost (one busy warp per level under the barriers).
+constexpr uint32_t LCAP = 6;       // levels 0..LCAP-1 have their own segment; deeper nodes share segment LCAP
+constexpr uint32_t KEY_SKIP = 15;  // level bucket of nodes that are final after K1
+constexpr int RES_TPB = 128;
 
-__device__ __forceinline__ uint32_t d_class(uint32_t d) {  // 0 = largest
-  return d > 96 ? 0u : d > 64 ? 1u : d > 48 ? 2u : d > 32 ? 3u : d > 16 ? 4u : d > 8 ? 5u : d > 4 ? 6u : 7u;
-}
-
-struct TileCfg {
-  uint32_t tile, slotcap, rowcap, dbig, nt, seg, taskcap, dbg;
-};
-
-// word k of a record in shared memory (the tile's rows: stride 32; staged look-back records: stride 1)
-struct SmemRec {
-  const uint32_t* p;
-  uint32_t stride;
-  __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return p[k * stride]; }
-};
-// word k of a record in global memory (chunks are not contiguous)
-struct GlobalRec {
-  const RangeView* rv;
-  uint32_t s, r0, ln;
-  __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return *row_word(*rv, s, r0 + k, ln); }
-};
-
-// One successor list: merge of (copied elements of the finished referenced list, expanded intervals, residuals).
-//   rec(k) = word k of the node's K1 record: [cumulative copy-block ends x b][interval count][start,len x ni][residuals]
-// inslot: the residuals are not in the record but parked at the tail of `out` (MF_INSLOT); they are consumed before
-// the write position reaches them (written <= copied + interval elements + residuals consumed).
-// The next element of the copy run and of the residual run is loaded one step ahead, so that the per-element
-// dependency chain is min / compare / select only.  PADDED: `ref` has one readable word behind its last element.
-template <bool PADDED, class Rec>
-__device__ __forceinline__ void merge_list(uint32_t* __restrict__ out, uint32_t d, const uint32_t* __restrict__ ref,
-                                           uint32_t dref, uint32_t b, uint32_t ns, uint32_t minint, const Rec rec,
-                                           bool inslot) {
-  // ---- layout of the record
-  uint32_t idx = b, ni = 0;
-  if (ns > b && minint) ni = rec(idx++);
-  uint32_t ip = idx, iend = idx + 2 * ni;  // interval pairs
-  uint32_t rp = iend, rend = ns;           // residuals
-  if (ns < b || 2 * (uint64_t)ni > (uint64_t)(ns - idx)) { ni = 0; ip = iend = rp = rend = 0; b = 0; }  // inconsistent record
-  const uint32_t* tail = nullptr;
-  if (inslot) {  // parked residuals: d - copied - interval elements of them
-    uint64_t used = 0;
-    for (uint32_t q = 0; q < ni; ++q) used += rec(ip + 2 * q + 1);
-    if (ref) {
-      if (b == 0) used += dref;
-      else {
-        uint32_t prev = 0;
-        for (uint32_t q = 0; q < b; ++q) { const uint32_t e = rec(q); if ((q & 1u) == 0) used += e - prev; prev = e; }
-        if ((b & 1u) == 0) used += dref - prev;
-      }
-    }
-    if (used > d) return;  // K1 checked this
-    rend = d;
-    rp = (uint32_t)used;  // index into out
-    tail = out;
-  }
-  // ---- heads of the three runs
-  uint32_t ci = 0, cend = 0, kb = 0, cval = INF, cnext = INF;
-  auto next_copy_block = [&]() {  // after copy block kb (even): skip block kb+1, copy block kb+2
-    for (;;) {
-      kb += 2;
-      if (kb - 1 < b) { ci = rec(kb - 1); cend = kb < b ? rec(kb) : dref; }
-      else { ci = cend = dref; cval = INF; return; }
-      if (cend > dref) cend = dref;
-      if (ci < cend) { cval = ref[ci]; cnext = (PADDED || ci + 1 < dref) ? ref[ci + 1] : INF; return; }
-    }
-  };
-  if (ref) {
-    cend = b ? min(rec(0), dref) : dref;
-    if (ci < cend) { cval = ref[0]; cnext = (PADDED || 1 < dref) ? ref[1] : INF; } else next_copy_block();
-  }
-  uint32_t ival = INF, ilim = 0;
-  if (ni) { ival = rec(ip); ilim = ival + rec(ip + 1); ip += 2; }
-  uint32_t rval = INF, rnext = INF;
-  if (rp < rend) rval = tail ? tail[rp] : rec(rp);
-  if (!tail && rp + 1 < rend) rnext = rec(rp + 1);
-  // ---- merge
-  for (uint32_t p = 0; p < d; ++p) {
-    const uint32_t mn = min(cval, min(ival, rval));
-    if (mn == cval) {
-      if (++ci < cend) { cval = cnext; cnext = (PADDED || ci + 1 < dref) ? ref[ci + 1] : INF; } else next_copy_block();
-    } else if (mn == rval) {
-      ++rp;
-      if (tail) rval = rp < rend ? tail[rp] : INF;
-      else { rval = rnext; rnext = rp + 1 < rend ? rec(rp + 1) : INF; }
-    } else {
-      if (++ival == ilim) {
-        if (ip < iend) { ival = rec(ip); ilim = ival + rec(ip + 1); ip += 2; } else ival = INF;
-      }
-    }
-    out[p] = mn;  // after the heads moved on: out[p] may be the parked residual that was just read
-  }
-}
-
-// ---- element-parallel resolve of one level of a tile, everything in shared memory ----------------------------
-// A successor list is the sorted union of three sorted runs with distinct values: the kept elements of the
-// referenced list (copy-block mask), the interval elements, the residuals.  So the final position of an element is
-// its rank in its own run plus the number of elements of the other two runs below it -- no serial merge, no
-// dependency between elements.  Work items of a level: chunks of GCH consecutive positions of a referenced list
-// (block state and ranks advance incrementally inside a chunk), single residuals, single intervals (their elements
-// are consecutive in the output).  All lanes of all warps take items from one flat index space per level.
-constexpr uint32_t GCH = 4;
-
-// the K1 record of a node as the tile sees it: word k at s[base + k * stride]
-struct TileRec {
-  const uint32_t* p;
-  uint32_t stride;
-  __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return p[k * stride]; }
-};
-
-struct NodeCtx {
-  uint32_t* out;
-  const uint32_t* ref;  // nullptr: no (usable) reference
-  uint32_t d, dref, b, ni, ipb, rb0, nres;
-  TileRec rec;
-  // copy blocks: cumulative ends E(q); block q is a copy block when q is even; after the b listed blocks the tail
-  __device__ __forceinline__ uint32_t E(uint32_t q) const { return min(rec(q), dref); }
-  // block that holds position j, and the kept elements before j
-  __device__ __forceinline__ void block_at(uint32_t j, uint32_t& q, uint32_t& bend, uint32_t& kept) const {
-    uint32_t prev = 0;
-    q = 0;
-    kept = 0;
-    while (q < b) {
-      const uint32_t e = E(q);
-      if (e > j) break;
-      if (!(q & 1u)) kept += e - prev;
-      prev = e;
-      ++q;
-    }
-    bend = q < b ? E(q) : dref;
-    if (!(q & 1u)) kept += j - prev;
-  }
-  __device__ __forceinline__ uint32_t res_below(uint32_t x) const {  // residuals < x
-    uint32_t lo = 0, hi = nres;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (rec(rb0 + mid) < x) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-  }
-  __device__ __forceinline__ uint32_t int_below(uint32_t x) const {  // interval elements < x
-    uint32_t cnt = 0;
-    for (uint32_t k = 0; k < ni; ++k) {
-      const uint32_t st = rec(ipb + 2 * k), len = rec(ipb + 2 * k + 1);
-      if (x > st) cnt += min(x - st, len);
-    }
-    return cnt;
-  }
-  __device__ __forceinline__ uint32_t kept_below(uint32_t x) const {  // kept elements of the referenced list < x
-    if (!ref) return 0;
-    uint32_t lo = 0, hi = dref;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (ref[mid] < x) lo = mid + 1; else hi = mid;
-    }
-    uint32_t q, bend, kept;
-    block_at(lo, q, bend, kept);
-    return kept;
-  }
-};
-
-__device__ __forceinline__ void item_ref_chunk(const NodeCtx& c, uint32_t u) {
-  const uint32_t j0 = u * GCH;
-  uint32_t q, bend, kept;
-  c.block_at(j0, q, bend, kept);
-  uint32_t rcnt = c.res_below(c.ref[j0]);
-#pragma unroll
-  for (uint32_t i = 0; i < GCH; ++i) {
-    const uint32_t j = j0 + i;
-    if (j >= c.dref) break;
-    const uint32_t x = c.ref[j];
-    while (j >= bend && q <= c.b) { ++q; bend = q < c.b ? c.E(q) : c.dref; }
-    while (rcnt < c.nres && c.rec(c.rb0 + rcnt) < x) ++rcnt;
-    if (!(q & 1u)) {
-      const uint32_t pos = kept + rcnt + c.int_below(x);
-      if (pos < c.d) c.out[pos] = x;
-      ++kept;
-    }
-  }
-}
-__device__ __forceinline__ void item_residual(const NodeCtx& c, uint32_t i) {
-  const uint32_t x = c.rec(c.rb0 + i);
-  const uint32_t pos = i + c.kept_below(x) + c.int_below(x);
-  if (pos < c.d) c.out[pos] = x;
-}
-__device__ __forceinline__ void item_interval(const NodeCtx& c, uint32_t k) {
-  uint32_t pos = 0;
-  for (uint32_t q = 0; q < k; ++q) pos += c.rec(c.ipb + 2 * q + 1);
-  const uint32_t st = c.rec(c.ipb + 2 * k), len = c.rec(c.ipb + 2 * k + 1);
-  pos += c.kept_below(st) + c.res_below(st);
-  for (uint32_t e = 0; e < len && pos + e < c.d; ++e) c.out[pos + e] = st + e;
-}
-
-constexpr uint32_t F21 = (1u << 21) - 1;
-
-template <int NT>
-__global__ void __launch_bounds__(NT) k_tile(RangeView rv, TileCfg cfg, uint32_t minint, uint32_t lookback) {
-  extern __shared__ __align__(16) uint32_t k2_smem[];
-  uint32_t* const s_slots = k2_smem;                             // slotcap + 8
-  uint32_t* const s_rows = s_slots + cfg.slotcap + 8;            // (rowcap + 1) * 32
-  uint32_t* const s_hrec = s_rows + (cfg.rowcap + 1) * 32;       // HRECCAP + 8: records staged compactly
-  unsigned long long* const s_pre = reinterpret_cast<unsigned long long*>(s_hrec + HRECCAP + 8);  // NT + 2: item prefix (3 x 21 bits)
-  uint32_t* const s_d = reinterpret_cast<uint32_t*>(s_pre + NT + 2);  // per candidate: outdegree
-  uint32_t* const s_so = s_d + NT;                               //   slot offset
-  uint32_t* const s_rb = s_so + NT;                              //   head word
-  uint32_t* const s_row0 = s_rb + NT;                            //   record: first row
-  uint32_t* const s_my = s_row0 + NT;                            //   record: words | lane << 24 | flags << 29
-  uint32_t* const s_ck = s_my + NT;                              //   chunk of the record's first row | crosses << 31
-  uint32_t* const s_recp = s_ck + NT;                            //   staged record: word index in k2_smem | (stride 32) << 31
-  uint32_t* const s_st = s_recp + NT;                            //   bit 0 big, 1 hard, 2 part, 3 need, 4 long record ; level << 8
-  uint32_t* const s_ni = s_st + NT;                              //   interval count | has-count-word << 31
-  uint32_t* const s_order = s_ni + NT;                           // task nodes ordered by level
-  uint32_t* const s_bin = s_order + NT;                          // LMAXT + 2 : task nodes per level
-  uint32_t* const s_binbase = s_bin + 16;                        // LMAXT + 2
-  __shared__ uint32_t s_scal[8];  // 1 rmin, 2 rmax, 3 hrec used, 4 maxlev, 5 holes, 6 first overflowing candidate
-  typedef cub::BlockScan<uint32_t, NT> BlockScan;
-  typedef cub::BlockScan<unsigned long long, NT> BlockScan64;
-  __shared__ union { typename BlockScan::TempStorage a; typename BlockScan64::TempStorage b; } s_scan;
-  constexpr uint32_t NW = NT / 32;
-
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t A = blockIdx.x * cfg.tile, B = min(A + cfg.tile, rv.n);
-  const uint32_t my_stream = rv.unit_stream[blockIdx.x];
-  const uint32_t longrec = max(cfg.rowcap / 3, 1u);  // records longer than this are staged compactly, not with the rows
-  long long tk0 = 0;
-  auto tick = [&](int phase) {  // debug: cycles per phase, summed over tiles (thread 0 of every block)
-    if (rv.stats && tid == 0) {
-      const long long now = clock64();
-      atomicAdd(&rv.stats[phase], (unsigned long long)(now - tk0));
-      tk0 = now;
-    }
-  };
-  if (rv.stats && tid == 0) { tk0 = clock64(); atomicAdd(&rv.stats[15], 1ull); }
-
-  for (uint32_t a = A; a < B;) {
-    const uint32_t C0 = a > lookback ? a - lookback : 0u;
-    const uint32_t own0 = a - C0;
-    uint32_t limit = B;  // owned nodes of this round: [a, limit)
-    uint32_t M, total_slots;
-    bool fits;
-    // -------------------------------------------------------------- descriptors (one candidate per thread)
-    uint32_t d = 0, rbw = 0, big = 0, lev = 0, hard = 0;
-    uint2 m = make_uint2(0, 0);
-    const uint32_t t = C0 + tid;
-    if (t < B) {
-      const uint4 nr = rv.nrec[t];
-      m = rv.meta[t];
-      const uint32_t us = rv.unit_stream[t / rv.unit];
-      d = nr.z;
-      rbw = nr.w;
-      const uint32_t fl = m.y >> 29, nsym = m.y & NSYM_MAX;
-      big = (d >= cfg.dbig || nsym > HRECCAP / 2 || fl != 0) ? 1u : 0u;
-      if (!big && (nsym > longrec || tid < own0)) big |= 16u;  // staged compactly (look-back records always are)
-      uint32_t ck = 0;
-      if (nsym && !(big & 1u)) {
-        ck = rv.stream_chunks[us * MAXC + (m.x >> CH_SHIFT)];
-        if ((m.x & (CH - 1)) + nsym > CH) ck |= 0x80000000u;  // the record continues in another chunk
-      }
-      s_d[tid] = d;
-      s_rb[tid] = rbw;
-      s_row0[tid] = m.x;
-      s_my[tid] = m.y;
-      s_ck[tid] = ck;
-    }
-    s_st[tid] = big;
-    if (tid < 8) s_scal[tid] = 0;
-    __syncthreads();
-    tick(0);
-    // -------------------------------------------------------------- reference chains: depth, hardness, needed look-back nodes
-    if (t < B) {
-      hard = big & 1u;
-      uint32_t j = tid;
-      while (!hard) {
-        const uint32_t rt = s_rb[j] & RT_MASK;
-        if (rt == 0) break;
-        if (rt > j) { hard = 1; break; }  // the chain leaves the look-back window
-        j -= rt;
-        if (s_st[j] & 1u) hard = 1;
-        else if (++lev > LMAXT) hard = 1;
-        else if (tid >= own0) atomicOr(&s_st[j], 8u);
-      }
-    }
-    __syncthreads();
-    const uint32_t nsym = m.y & NSYM_MAX;
-    const bool longr = (big & 16u) != 0;
-    uint32_t hro = INF;
-    for (;;) {  // shrink the round until it fits shared memory
-      M = limit - C0;
-      const bool owned = tid >= own0 && tid < M;
-      const bool part = tid < M && !hard && (owned || (s_st[tid] & 8u));
-      uint32_t so = 0;
-      BlockScan(s_scan.a).ExclusiveSum(part ? d : 0u, so, total_slots);
-      if (tid == 0) { s_scal[1] = INF; s_scal[2] = 0; s_scal[3] = 0; s_scal[6] = INF; }
-      __syncthreads();
-      hro = INF;
-      if (part && nsym) {
-        if (longr) hro = atomicAdd(&s_scal[3], nsym);
-        else {
-          atomicMin(&s_scal[1], m.x);
-          atomicMax(&s_scal[2], m.x + nsym);
-        }
-      }
-      // first candidate whose slot would not fit
-      if (part && so + d > cfg.slotcap) atomicMin(&s_scal[6], tid);
-      __syncthreads();
-      const uint32_t rmin = s_scal[1], rmax = s_scal[2], over = s_scal[6];
-      fits = over == INF && (rmax <= rmin || rmax - rmin <= cfg.rowcap) && s_scal[3] <= HRECCAP;
-      if (fits || limit == a + 1) {
-        s_so[tid] = so;
-        s_st[tid] = (s_st[tid] & 25u) | (hard << 1) | (part ? 4u : 0u) | (lev << 8);
-        break;
-      }
-      // halve the owned range (or cut it at the first slot overflow, whichever is smaller)
-      uint32_t nl = a + max(1u, (limit - a) / 2);
-      if (over != INF && over > own0 && C0 + over < nl) nl = C0 + over;
-      limit = nl;
-      __syncthreads();
-    }
-    // (a single node that does not fit with its ancestors: !fits, the global pass takes it)
-    const bool owned = tid >= own0 && tid < M;
-    const bool part = fits && tid < M && !hard && (owned || (s_st[tid] & 8u));
-    const uint32_t rmin = s_scal[1], rmax = s_scal[2];
-    // -------------------------------------------------------------- owned nodes: hard list, flags
-    if (owned) {
-      const uint32_t fl = m.y >> 29;
-      uint32_t hf = 0;
-      if (!part) hf = (d == 0 || (fl & (MF_ERR | MF_FINAL))) ? 2u : 1u;
-      rv.hardflag[t] = (uint8_t)hf;
-      if (hf == 1u) {
-        const uint32_t pos = atomicAdd(rv.hard_count, 1u);
-        rv.hard_list[pos] = t;
-      }
-      if (!part && d != 0) s_scal[5] = 1;  // hole in the owned slots: no bulk copy-out
-    }
-    if (!fits) { __syncthreads(); a = limit; continue; }
-    tick(1);
-    // -------------------------------------------------------------- stage in: the tile's rows, compact records
-    if (rmax > rmin) {  // 16-byte pieces, independent of one another: all the loads are in flight together
-      const uint32_t np = (rmax - rmin) * 8;
-#pragma unroll 4
-      for (uint32_t q = tid; q < np; q += NT) {
-        const uint32_t r = rmin + (q >> 3);
-        const uint32_t cid = rv.stream_chunks[my_stream * MAXC + (r >> CH_SHIFT)];
-        const uint4 v = *reinterpret_cast<const uint4*>(rv.rows + ((size_t)cid * CH + (r & (CH - 1))) * 32 + (q & 7u) * 4);
-        *reinterpret_cast<uint4*>(s_rows + (r - rmin) * 32 + (q & 7u) * 4) = v;
-      }
-    }
-    s_recp[tid] = 0;
-    if (part && nsym) {
-      if (longr) {  // every thread copies its own compact record (a column of the rows: one word per row)
-        s_recp[tid] = (uint32_t)(s_hrec - k2_smem) + hro;
-        const uint32_t ck = s_ck[tid], ln = (m.y >> 24) & 31u;
-        if (!(ck >> 31)) {
-          const uint32_t* src = rv.rows + ((size_t)ck * CH + (m.x & (CH - 1))) * 32 + ln;
-#pragma unroll 4
-          for (uint32_t q = 0; q < nsym; ++q) s_hrec[hro + q] = src[(size_t)q * 32];
-        } else {
-          const uint32_t s = rv.unit_stream[t / rv.unit];
-          for (uint32_t q = 0; q < nsym; ++q) s_hrec[hro + q] = *row_word(rv, s, m.x + q, ln);
-        }
-      } else s_recp[tid] = ((uint32_t)(s_rows - k2_smem) + (m.x - rmin) * 32 + ((m.y >> 24) & 31u)) | 0x80000000u;
-    }
-    if (part) atomicMax(&s_scal[4], lev);
-    if (tid < 16) s_bin[tid] = 0;
-    __syncthreads();
-    tick(2);
-    // -------------------------------------------------------------- work items per node; nodes ordered by level
-    const bool task = part && d != 0;
-    const uint32_t rt = rbw & RT_MASK, bcnt = rbw >> RT_BITS;
-    uint32_t rank = 0;
-    if (task) {
-      const TileRec myrec{k2_smem + (s_recp[tid] & 0x7FFFFFFFu), (s_recp[tid] >> 31) ? 32u : 1u};
-      const bool has_cnt = nsym > bcnt && minint != 0;
-      uint32_t ni = has_cnt ? myrec(bcnt) : 0u, nres = 0;
-      const uint32_t hdr = bcnt + (has_cnt ? 1u : 0u);
-      if (nsym < hdr || 2ull * ni > (uint64_t)(nsym - hdr)) ni = 0;  // inconsistent record
-      else nres = nsym - hdr - 2 * ni;
-      s_ni[tid] = ni | (has_cnt ? 0x80000000u : 0u);
-      (void)nres;
-      rank = atomicAdd(&s_bin[lev], 1u);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t acc = 0;
-      for (uint32_t l = 0; l <= LMAXT + 1; ++l) { s_binbase[l] = acc; acc += s_bin[l]; }
-    }
-    __syncthreads();
-    if (task) s_order[s_binbase[lev] + rank] = tid;
-    // prefix of the item counts in level order: thread q holds the node at position q
-    __syncthreads();
-    {
-      const uint32_t ntask = s_binbase[LMAXT + 1];
-      unsigned long long mine = 0, pre = 0, total = 0;
-      if (tid < ntask) {
-        // recompute the node's counts from its parsed record (cheaper than passing them through shared memory)
-        const uint32_t nn = s_order[tid];
-        const uint32_t rbn = s_rb[nn], nsn = s_my[nn] & NSYM_MAX, nin = s_ni[nn];
-        const uint32_t rtn = rbn & RT_MASK, bn = rbn >> RT_BITS;
-        const uint32_t hdr = bn + (nin >> 31);
-        const uint32_t nin_ = nin & 0x7FFFFFFFu;
-        const uint32_t nresn = nsn >= hdr + 2 * nin_ ? nsn - hdr - 2 * nin_ : 0u;
-        const uint32_t drefn = rtn ? s_d[nn - rtn] : 0u;
-        mine = (unsigned long long)((drefn + GCH - 1) / GCH) | ((unsigned long long)nresn << 21) | ((unsigned long long)nin_ << 42);
-      }
-      BlockScan64(s_scan.b).ExclusiveSum(mine, pre, total);
-      if (tid < ntask) s_pre[tid] = pre;
-      if (tid == 0) { s_pre[ntask] = total; }
-    }
-    __syncthreads();
-    tick(3);
-    // -------------------------------------------------------------- resolve, one level after the other
-    const uint32_t maxlev = s_scal[4];
-    for (uint32_t l = 0; l <= maxlev; ++l) {
-      const uint32_t lb = s_binbase[l], le = s_binbase[l + 1];
-      if (le > lb) {
-        const unsigned long long P0 = s_pre[lb], P1 = s_pre[le];
-        const uint32_t NA = (uint32_t)(P1 & F21) - (uint32_t)(P0 & F21);
-        const uint32_t NB = (uint32_t)((P1 >> 21) & F21) - (uint32_t)((P0 >> 21) & F21);
-        const uint32_t NC = (uint32_t)((P1 >> 42) & F21) - (uint32_t)((P0 >> 42) & F21);
-        for (uint32_t f = tid; f < NA + NB + NC; f += NT) {
-          const uint32_t kind = f < NA ? 0u : f < NA + NB ? 1u : 2u;
-          const uint32_t sh = kind * 21;
-          const uint32_t key = (uint32_t)((P0 >> sh) & F21) + (kind == 0 ? f : kind == 1 ? f - NA : f - NA - NB);
-          uint32_t lo = lb, hi = le;  // largest position whose prefix is <= key
-          while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if ((uint32_t)((s_pre[mid] >> sh) & F21) <= key) lo = mid; else hi = mid;
-          }
-          const uint32_t u = key - (uint32_t)((s_pre[lo] >> sh) & F21);
-          const uint32_t n = s_order[lo];
-          const uint32_t rbn = s_rb[n], nin = s_ni[n], rp = s_recp[n];
-          const uint32_t rtn = rbn & RT_MASK;
-          NodeCtx c;
-          c.out = s_slots + s_so[n];
-          c.d = s_d[n];
-          c.dref = rtn ? s_d[n - rtn] : 0u;
-          c.ref = c.dref ? s_slots + s_so[n - rtn] : nullptr;
-          c.b = rbn >> RT_BITS;
-          c.ni = nin & 0x7FFFFFFFu;
-          c.ipb = c.b + (nin >> 31);
-          c.rb0 = c.ipb + 2 * c.ni;
-          const uint32_t nsn = s_my[n] & NSYM_MAX;
-          c.nres = nsn >= c.rb0 ? nsn - c.rb0 : 0u;
-          c.rec = TileRec{k2_smem + (rp & 0x7FFFFFFFu), (rp >> 31) ? 32u : 1u};
-          if (kind == 0) item_ref_chunk(c, u);
-          else if (kind == 1) item_residual(c, u);
-          else item_interval(c, u);
-        }
-      }
-      __syncthreads();
-      tick(4 + min(l, 3u));
-    }
-    // -------------------------------------------------------------- copy out the owned lists
-    {
-      const uint32_t s_beg = s_so[own0];
-      const uint32_t s_end = total_slots;  // owned nodes are the last candidates
-      const bool straddle = a < rv.h && limit > rv.h;
-      if (!s_scal[5] && !straddle && s_end > s_beg) {
-        const uint64_t o0 = rv.offs[a], o1 = rv.offs[limit];
-        uint32_t* dst = nullptr;
-        if (a < rv.h) { if (o1 <= rv.halo_cap) dst = rv.halo_succ + o0; }
-        else { const uint64_t bs = rv.offs[rv.h]; if (o1 - bs <= rv.succ_cap) dst = rv.succ + (o0 - bs); }
-        if (!dst) { if (tid == 0) atomicOr(rv.err, ERR_WORKSPACE); }
-        else for (uint32_t e = s_beg + tid; e < s_end; e += NT) dst[e - s_beg] = s_slots[e];
-      } else {
-        for (uint32_t i = own0 + warp; i < M; i += NW) {
-          if (!(s_st[i] & 4u) || s_d[i] == 0) continue;
-          uint32_t* dst = node_slot(rv, C0 + i);
-          if (!dst) { if (lane == 0) atomicOr(rv.err, ERR_WORKSPACE); continue; }
-          const uint32_t* srcp = s_slots + s_so[i];
-          for (uint32_t e = lane; e < s_d[i]; e += 32) dst[e] = srcp[e];
-        }
-      }
-    }
-    __syncthreads();
-    tick(8);
-    a = limit;
-  }
-}
-
-// -------------------------------------------------------------------------------------------- K2: global pass
-// Nodes the tiles left out (hardflag 1).  Depth among themselves: ancestors that are already final count 0.
-__global__ void __launch_bounds__(256) k_hard_levels(RangeView rv) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t nh = *rv.hard_count;
+__global__ void __launch_bounds__(256) k_levels(RangeView rv, uint8_t* keys, uint32_t* vals, uint32_t* lev_out, uint32_t* hist) {
+  __shared__ uint32_t s_hist[16];
+  if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t lev = 0;
-  if (i < nh) {
-    uint32_t j = rv.hard_list[i];
-    for (;;) {
-      const uint32_t rt = rv.nrec[j].w & RT_MASK;
-      if (rt == 0) break;
-      j -= rt;
-      if (rv.hardflag[j] != 1) break;
-      ++lev;
+  if (t < rv.n) {
+    const uint32_t fl = rv.meta[t] >> 29;
+    uint32_t lb = KEY_SKIP;
+    if (rv.outdeg[t] != 0 && !(fl & (MF_ERR | MF_FINAL))) {
+      uint32_t u = t, r = rv.nrec[t].w & RT_MASK;
+      while (r) {  // chain of referenced nodes (K0 made sure it stays inside the decoded nodes)
+        u -= r;
+        ++lev;
+        r = rv.nrec[u].w & RT_MASK;
+      }
+      lb = min(lev, LCAP);
+      lev_out[t] = lev;
     }
-    rv.hard_lev[i] = lev;
+    keys[t] = (uint8_t)lb;
+    vals[t] = t;
+    atomicAdd(&s_hist[lb], 1u);
   }
   for (int o = 16; o; o >>= 1) lev = max(lev, __shfl_xor_sync(FULL, lev, o));
-  if ((threadIdx.x & 31) == 0 && lev) atomicMax(rv.maxlevel, lev);
+  if ((threadIdx.x & 31) == 0 && lev >= LCAP) atomicMax(rv.maxlevel, lev);
+  __syncthreads();
+  if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
 }
 
-// One lane per hard node of the given depth: the same merge, from global memory.
-__global__ void __launch_bounds__(128) k_hard_resolve(RangeView rv, uint32_t level, uint32_t minint) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= *rv.hard_count || rv.hard_lev[i] != level) return;
-  const uint32_t t = rv.hard_list[i];
-  const uint32_t d = rv.outdeg[t], rbw = rv.nrec[t].w;
-  const uint2 m = rv.meta[t];
-  const uint32_t rt = rbw & RT_MASK, b = rbw >> RT_BITS, nsym = m.y & NSYM_MAX, fl = m.y >> 29;
-  uint32_t* out = node_slot(rv, t);
-  if (!out) { atomicOr(rv.err, ERR_WORKSPACE); return; }
-  const uint32_t* ref = nullptr;
-  uint32_t dref = 0;
-  if (rt) {
-    ref = node_slot(rv, t - rt);
-    dref = rv.outdeg[t - rt];
-    if (!ref) { atomicOr(rv.err, ERR_WORKSPACE); return; }
+// hist[16] -> seg[17] (exclusive prefix): nodes of level bucket l are order[seg[l] .. seg[l+1])
+__global__ void k_segments(const uint32_t* hist, uint32_t* seg) {
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int l = 0; l < 16; ++l) { seg[l] = acc; acc += hist[l]; }
+    seg[16] = acc;
   }
-  merge_list<false>(out, d, ref, dref, b, nsym, minint, GlobalRec{&rv, rv.unit_stream[t / rv.unit], m.x, (m.y >> 24) & 31u},
-             (fl & MF_INSLOT) != 0);
+}
+
+// One level of phase two.  Lane-per-node state machine: every lane holds one node and emits ONE successor per
+// step -- the minimum of the three run heads -- so that all lanes of a warp run the same short merge step
+// regardless of how their lists are composed.  Lanes that finish a node wait until SETUP_BATCH lanes are free and
+// then fetch + set up their next nodes together (the set-up is several dependent loads).  Each block owns a
+// contiguous share of the level's segment and hands its nodes out in order.
+//   record of node t (K1), contiguous in the record buffer:
+//     [cumulative copy-block ends x b][interval count][start,len x ni][residuals]
+//   MF_INSLOT: the residuals are not in the record but parked at the tail of the node's own slot; they are consumed
+//   before the write position reaches them (written <= copied + interval elements + residuals consumed).
+constexpr uint32_t HS = 16;  // header words (copy-block ends, interval count, interval pairs) a lane caches in shared memory
+
+__global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_t* order, const uint32_t* seg, uint32_t lb,
+                                                     uint32_t exact_level, const uint32_t* lev, uint32_t minint) {
+  __shared__ uint32_t s_hdr[RES_TPB * (HS + 1)];
+  __shared__ uint32_t s_next;
+  uint32_t* const hdr = s_hdr + threadIdx.x * (HS + 1);  // odd stride: conflict-free
+  const uint32_t beg = seg[lb], end = seg[lb + 1];
+  const uint32_t len = end - beg;
+  const uint32_t share = (len + gridDim.x - 1) / gridDim.x;
+  const uint32_t cb = beg + min(len, blockIdx.x * share), ce = beg + min(len, (blockIdx.x + 1) * share);
+  if (cb >= ce) return;
+  if (threadIdx.x == 0) s_next = cb;
+  __syncthreads();
+  constexpr uint32_t SETUP_BATCH = 8;
+  constexpr int STEPS_PER_VOTE = 2;  // merge steps between two scheduling votes
+  enum { S_FETCH, S_MERGE, S_IDLE };
+  int st = S_FETCH;
+  uint32_t* out = nullptr;          // the node's slot; p = successors written, d = outdegree
+  const uint32_t* ref = nullptr;    // the referenced list; [ci, cend) = current copy block
+  const uint32_t* hp = nullptr;     // header of the record: this lane's shared-memory copy, or the record itself when too long
+  const uint32_t* res = nullptr;    // the residuals: in the record, or parked at the tail of `out` (MF_INSLOT)
+  uint32_t p = 0, d = 0, ci = 0, cend = 0, dref = 0, rj = 0, nres = 0;
+  uint32_t cval = INF, ival = INF, ilim = 0, rval = INF, b = 0, kb = 0, ip = 0, iend = 0;
+  // the current copy block is exhausted: skip block kb+1, then copy block kb+2 (block ends are cumulative)
+  auto next_copy_block = [&]() {
+    cval = INF;
+    for (;;) {
+      kb += 2;
+      if (kb - 1 >= b) { ci = cend = dref; return; }
+      ci = min(hp[kb - 1], dref);
+      cend = kb < b ? min(hp[kb], dref) : dref;
+      if (ci < cend) { cval = ref[ci]; return; }
+    }
+  };
+  for (;;) {
+    const uint32_t fetchers = __ballot_sync(FULL, st == S_FETCH);
+    const uint32_t mergers = __ballot_sync(FULL, st == S_MERGE);
+    if ((fetchers | mergers) == 0) break;
+    if (fetchers && (mergers == 0 || __popc(fetchers) >= SETUP_BATCH)) {
+      if (st == S_FETCH) {
+        uint32_t i = atomicAdd(&s_next, 1u);
+        uint32_t t = 0;
+        bool have = false;
+        while (i < ce) {  // (levels deeper than LCAP share a segment: skip nodes of other levels)
+          t = order[i];
+          if (!exact_level || lev[t] == exact_level) { have = true; break; }
+          i = atomicAdd(&s_next, 1u);
+        }
+        if (!have) st = S_IDLE;
+        else {
+          const uint4 nr = rv.nrec[t];
+          const uint32_t m = rv.meta[t];
+          const uint32_t* recp = rv.recs + rv.roff[t];
+          const uint32_t rt = nr.w & RT_MASK, ns = m & NSYM_MAX, fl = m >> 29;
+          d = nr.z;
+          b = nr.w >> RT_BITS;
+          out = node_slot(rv, t);
+          ref = nullptr;
+          dref = 0;
+          if (rt) {
+            ref = node_slot(rv, t - rt);
+            dref = rv.outdeg[t - rt];
+          }
+          if (!out || (rt && !ref)) { atomicOr(rv.err, ERR_WORKSPACE); d = 0; }
+          // layout of the record
+          uint32_t ni = 0, H = b;
+          if (ns > b && minint) { ni = recp[b]; H = b + 1; }
+          if (ns < H || 2 * (uint64_t)ni > (uint64_t)(ns - H)) { ni = 0; b = 0; H = 0; d = 0; }  // inconsistent record
+          ip = H;
+          H += 2 * ni;
+          iend = H;
+          if (H <= HS) {
+            for (uint32_t w = 0; w < H; ++w) hdr[w] = recp[w];
+            hp = hdr;
+          } else hp = recp;
+          nres = 0;
+          if (fl & MF_INSLOT) {  // parked residuals: the last words of the slot; their number ends the record
+            nres = ns > H ? recp[H] : 0u;
+            if (nres > d) { nres = 0; d = 0; }
+          }
+          res = out + (d - nres);
+          // heads of the three runs
+          p = 0;
+          rj = 0;
+          rval = nres ? res[0] : INF;
+          ival = INF;
+          if (ni) { ival = hp[ip]; ilim = ival + hp[ip + 1]; ip += 2; }
+          cval = INF;
+          ci = cend = 0;
+          kb = 0;
+          if (rt) {
+            cend = b ? min(hp[0], dref) : dref;
+            if (ci < cend) cval = ref[0]; else next_copy_block();  // (only the first block can be empty)
+          }
+          st = (d != 0) ? S_MERGE : S_FETCH;
+        }
+      }
+    }
+#pragma unroll
+    for (int step = 0; step < STEPS_PER_VOTE; ++step) {
+      if (st == S_MERGE) {
+        const uint32_t mn = min(cval, min(ival, rval));
+        out[p] = mn;
+        if (mn == cval) {
+          if (++ci == cend) next_copy_block(); else cval = ref[ci];  // (loading one element ahead was measured: no gain)
+        } else if (mn == rval) {
+          // (in-slot residuals: res[rj + 1] is still unread input: written <= copied + intervals + residuals consumed)
+          rval = ++rj < nres ? res[rj] : INF;
+        } else {
+          if (++ival == ilim) {
+            if (ip < iend) { ival = hp[ip]; ilim = ival + hp[ip + 1]; ip += 2; } else ival = INF;
+          }
+        }
+        if (++p == d) st = S_FETCH;
+      }
+    }
+  }
 }
 
 // -------------------------------------------------------------------------------------------- random access
@@ -1149,14 +746,13 @@ __global__ void k_offsets_rebase(const uint64_t* src, uint64_t base, uint64_t* d
 }
 
 // scalars the host needs after a decode -> mapped host memory (no DMA copy: see wga_graph::h_pub)
-__global__ void k_publish(const uint64_t* tot0, const uint64_t* tot1, const uint32_t* maxlevel, const uint32_t* hard_count,
-                          const uint32_t* err, uint64_t* pub) {
+__global__ void k_publish(const uint64_t* tot0, const uint64_t* tot1, const uint32_t* maxlevel, const uint32_t* err,
+                          uint64_t* pub) {
   if (threadIdx.x == 0) {
     pub[1] = *tot0;
     pub[2] = *tot1;
     pub[3] = *maxlevel;
     pub[4] = *err;
-    pub[5] = *hard_count;
   }
 }
 
@@ -1171,70 +767,56 @@ inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 struct Scalars {
   uint64_t lo;                // k_halo result
   uint32_t unit_ctr;
-  uint32_t chunk_ctr;
-  uint32_t hard_count;
   uint32_t maxlevel;
+  uint32_t hist[16];          // nodes per level bucket
+  uint32_t seg[17];           // exclusive prefix of hist
 };
-static_assert(NBINS + 1 <= 96, "bin prefix handles three bins per lane");
 static_assert(sizeof(Scalars) <= 256, "Scalars must fit the cleared line");
 
 struct WorkspacePlan {
-  uint64_t off_outdeg, off_nrec, off_offs, off_meta, off_hflag, off_hlist, off_hlev, off_ustream, off_schunks, off_cub,
-      off_halo, off_rows;
+  uint64_t off_outdeg, off_nrec, off_offs, off_roff, off_meta, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_recs;
   uint64_t cub_bytes, halo_cap, fixed_bytes;
 };
 
-WorkspacePlan plan_workspace(uint64_t n, uint32_t unit) {
+WorkspacePlan plan_workspace(uint64_t n) {
   WorkspacePlan p{};
   uint64_t o = 0;
   o += 256;  // Scalars
   p.off_outdeg = o; o = align_up(o + 4 * (n + 1), 256);
   p.off_nrec = o; o = align_up(o + 16 * n, 256);
   p.off_offs = o; o = align_up(o + 8 * (n + 1), 256);
-  p.off_meta = o; o = align_up(o + 8 * n, 256);
-  p.off_hflag = o; o = align_up(o + n, 256);
-  p.off_hlist = o; o = align_up(o + 4 * n, 256);
-  p.off_hlev = o; o = align_up(o + 4 * n, 256);
-  p.off_ustream = o; o = align_up(o + 4 * ((n + unit - 1) / unit + 1), 256);
-  p.off_schunks = o; o = align_up(o + 4ull * MAX_STREAMS * MAXC, 256);
-  size_t scan_bytes = 0;
+  p.off_roff = o; o = align_up(o + 8 * (n + 1), 256);
+  p.off_meta = o; o = align_up(o + 4 * n, 256);
+  p.off_lev = o; o = align_up(o + 4 * n, 256);
+  for (int i = 0; i < 2; ++i) { p.off_keys[i] = o; o = align_up(o + n, 256); }
+  for (int i = 0; i < 2; ++i) { p.off_vals[i] = o; o = align_up(o + 4 * n, 256); }
+  size_t scan_bytes = 0, sort_bytes = 0;
   cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(nullptr, U32ToU64());
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, it, (uint64_t*)nullptr, (int64_t)(n + 1));
-  p.cub_bytes = scan_bytes;
+  cub::DoubleBuffer<uint8_t> dk(nullptr, nullptr);
+  cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int64_t)n, 0, 4);
+  p.cub_bytes = std::max(scan_bytes, sort_bytes);
   p.off_cub = o; o = align_up(o + p.cub_bytes, 256);
   p.halo_cap = 1u << 20;  // successors of halo nodes (u32 each)
   p.off_halo = o; o = align_up(o + 4 * p.halo_cap, 256);
-  p.off_rows = align_up(o, 16384);
-  p.fixed_bytes = p.off_rows;
+  p.off_recs = align_up(o, 256);
+  p.fixed_bytes = p.off_recs;
   return p;
 }
 
-// threads of a tile block: the look-back window plus the tile's nodes, one candidate per thread
-uint32_t tile_threads(const Tuning& tn, uint32_t window) {
-  const uint32_t lookback = std::min<uint32_t>(HMAX, window * LMAXT);
-  const uint32_t want = (tn.tile ? tn.tile : 1) + lookback;
-  return want <= 128 ? 128u : want <= 160 ? 160u : want <= 192 ? 192u : 256u;
-}
-uint32_t effective_tile(const Tuning& tn, uint32_t window) {
-  const uint32_t lookback = std::min<uint32_t>(HMAX, window * LMAXT);
-  uint32_t tile = tn.tile ? tn.tile : 1;
-  if (tile > K2_NT_MAX - lookback) tile = K2_NT_MAX - lookback;
-  return tile;
-}
+uint32_t effective_unit(const Tuning& tn) { return std::max<uint32_t>(1u, tn.unit); }
 
 }  // namespace
 
 uint64_t decode_workspace_size(const wga_graph* g, uint64_t first, uint64_t last) {
   uint64_t n = last - first + 4096;  // room for a halo
-  WorkspacePlan p = plan_workspace(n, effective_tile(g_tuning, (uint32_t)g->prelude.compression_window));
+  WorkspacePlan p = plan_workspace(n);
   double frac = g->prelude.number_of_nodes ? (double)(last - first) / (double)g->prelude.number_of_nodes : 1.0;
   uint64_t arcs_est = (uint64_t)((double)g->prelude.number_of_arcs * frac) + (1u << 20);
-  // rows: one 4-byte word per decoded symbol, 32 lanes per row of which about three quarters are busy; a record has
-  // at most (blocks + 1 + outdegree) words
-  uint64_t rows_bytes = 8 * arcs_est + 48 * n + (32ull << 20);
-  // every K1 warp that gets work owns at least one chunk
-  const uint32_t tile = effective_tile(g_tuning, (uint32_t)g->prelude.compression_window);
-  rows_bytes += std::min<uint64_t>((n + tile - 1) / tile, MAX_STREAMS) * (4ull * CH * 32);
+  // record buffer: (block count + 1 + outdegree) words per node; the block counts sum to about three per node on web
+  // graphs and are bounded by (outdegree of the referenced node + 1)
+  uint64_t rows_bytes = 4 * (arcs_est + arcs_est / 4 + 8 * n) + (16ull << 20);
   return p.fixed_bytes + rows_bytes;
 }
 
@@ -1261,7 +843,7 @@ void outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets
   if (!g->on_device) throw Error(WGA_E_CUDA, "graph was opened host-only");
   if (first > last || last > g->res_last || first < g->res_first) throw Error(WGA_E_ARG, "range outside the resident nodes");
   uint64_t n = last - first;
-  WorkspacePlan p = plan_workspace(n, 192);
+  WorkspacePlan p = plan_workspace(n);
   if (ws_bytes < p.off_nrec) throw Error(WGA_E_WORKSPACE, "workspace too small");
   uint8_t* w = (uint8_t*)ws;
   uint32_t* outdeg = (uint32_t*)(w + p.off_outdeg);
@@ -1336,10 +918,6 @@ uint64_t plan_k1_tables(const wga_graph* g, K1Tables& kt, int smem_limit) {
   return head + 8ull * bo + 8ull * eo;
 }
 
-uint64_t tile_smem_bytes(const TileCfg& c) {
-  return 4ull * ((uint64_t)c.slotcap + 8 + 32ull * (c.rowcap + 1) + HRECCAP + 8 + 2ull * (c.nt + 2) + 10ull * c.nt + 32);
-}
-
 }  // namespace
 
 // K0 .. K2 on the nodes described by rv (a contiguous range, or a sorted node list), then one host
@@ -1356,16 +934,19 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
     size_t cb = p.cub_bytes;
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(rv.outdeg, U32ToU64());
     WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_cub, cb, it, rv.offs, (int64_t)(n + 1), st));
-    count_launch(2);
+    cb = p.cub_bytes;
+    cub::TransformInputIterator<uint64_t, RecWords, const uint4*> itr(rv.nrec, RecWords());
+    WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_cub, cb, itr, rv.roff, (int64_t)n, st));
+    count_launch(4);
   }
-  mark(g, st);  // 1: heads + scan done
+  mark(g, st);  // 1: heads + scans done
   // ---- K1: entropy decode into rows
   {
     K1Tables kt{};
     const uint64_t smem = plan_k1_tables(g, kt, di.smem_optin);
     uint32_t blocks = tn.k1_blocks ? tn.k1_blocks : (uint32_t)di.sms;
     blocks = std::min<uint32_t>(blocks, (rv.n_units + K1_WARPS - 1) / K1_WARPS);
-    blocks = std::max<uint32_t>(1u, std::min<uint32_t>(blocks, MAX_STREAMS / K1_WARPS));
+    blocks = std::max<uint32_t>(1u, blocks);
     bool allhot = true;
     for (int c = Blocks; c <= Residual; ++c) allhot = allhot && kt.cp[c].w >= g->packed.nent[c];
     const uint32_t refill = std::max<uint32_t>(1u, std::min<uint32_t>(32u, tn.refill));
@@ -1378,51 +959,45 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
     count_launch();
   }
   mark(g, st);  // 2: entropy decode done
-  // ---- K2: tiles
-  static unsigned long long* d_stats = nullptr;
-  static const bool want_stats = getenv("WGA_K2_STATS") != nullptr;
-  if (want_stats) {
-    if (!d_stats) WGA_CUDA(cudaMalloc(&d_stats, 16 * 8));
-    WGA_CUDA(cudaMemsetAsync(d_stats, 0, 16 * 8, st));
-    rv.stats = d_stats;
-  }
-  const uint32_t window = (uint32_t)g->prelude.compression_window;
-  const uint32_t lookback = std::min<uint32_t>(HMAX, window * LMAXT);
-  {
-    TileCfg cfg{rv.unit, (std::max<uint32_t>(64u, tn.slotcap) + 3u) & ~3u, std::max<uint32_t>(3u, tn.rowcap),
-                std::min<uint32_t>(std::max<uint32_t>(2u, tn.dbig), 32768u), tile_threads(tn, window),
-                std::max<uint32_t>(4u, tn.seg), 0u, tn.dbg};
-    // every candidate is at least one task; the referenced lists and the residuals each fit the slots
-    cfg.taskcap = (cfg.nt + 2 * (cfg.slotcap / cfg.seg) + 8 + 3) & ~3u;
-    const uint64_t smem = tile_smem_bytes(cfg);
-    if ((int64_t)smem > (int64_t)di.smem_optin - 2048) throw Error(WGA_E_ARG, "tile tuning exceeds shared memory");
-    auto launch = [&](auto kern) {
-      WGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<rv.n_units, cfg.nt, smem, st>>>(rv, cfg, g->dev.min_interval, lookback);
-    };
-    if (cfg.nt == 128) launch(k_tile<128>);
-    else if (cfg.nt == 160) launch(k_tile<160>);
-    else if (cfg.nt == 192) launch(k_tile<192>);
-    else launch(k_tile<256>);
+  // ---- K2: levels, stable sort by level, one resolve launch per level
+  uint32_t* lev = (uint32_t*)(w + p.off_lev);
+  cub::DoubleBuffer<uint8_t> dkeys((uint8_t*)(w + p.off_keys[0]), (uint8_t*)(w + p.off_keys[1]));
+  cub::DoubleBuffer<uint32_t> dvals((uint32_t*)(w + p.off_vals[0]), (uint32_t*)(w + p.off_vals[1]));
+  const bool have_refs = g->prelude.compression_window != 0 || g->prelude.min_interval_length != 0;
+  uint32_t grid = tn.k2_blocks;
+  if (have_refs) {
+    k_levels<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rv, dkeys.Current(), dvals.Current(), lev, sc->hist);
     count_launch();
+    size_t cb = p.cub_bytes;
+    WGA_CUDA(cub::DeviceRadixSort::SortPairs(w + p.off_cub, cb, dkeys, dvals, (int64_t)n, 0, 4, st));
+    count_launch(3);
+    k_segments<<<1, 32, 0, st>>>(sc->hist, sc->seg);
+    count_launch();
+    mark(g, st);  // 3: levels + sort done
+    if (!grid) {
+      int per_sm = 8;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resolve, RES_TPB, 0);
+      per_sm = per_sm > 10 ? 10 : (per_sm > 0 ? per_sm : 1);  // swept: more resident warps thrash L1
+      grid = (uint32_t)(di.sms * per_sm);
+    }
+    const uint32_t nlev = g->prelude.compression_window ? LCAP : 1;  // without references everything is level 0
+    for (uint32_t l = 0; l < nlev; ++l) {
+      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, l, 0, lev, g->dev.min_interval);
+      count_launch();
+    }
+  } else {
+    mark(g, st);
   }
-  mark(g, st);  // 3: tiles done
-  // ---- totals, hard nodes, error word
-  k_publish<<<1, 32, 0, st>>>(rv.offs + rv.h, rv.offs + n, &sc->maxlevel, &sc->hard_count, g->d_err, g->d_pub);
+  mark(g, st);  // 4: resolve done
+  // ---- totals, deepest level, error word
+  k_publish<<<1, 32, 0, st>>>(rv.offs + rv.h, rv.offs + n, &sc->maxlevel, g->d_err, g->d_pub);
   count_launch();
   WGA_CUDA(cudaStreamSynchronize(st));
   WGA_CUDA(cudaGetLastError());
   tot[0] = g->h_pub[1];
   tot[1] = g->h_pub[2];
-  if (want_stats) {
-    unsigned long long hs[16];
-    WGA_CUDA(cudaMemcpy(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost));
-    const double nb = hs[15] ? (double)hs[15] : 1.0;
-    fprintf(stderr, "[k_tile cycles/block] load %.0f plan %.0f stage %.0f tasks %.0f lev0 %.0f lev1 %.0f lev2 %.0f lev3+ %.0f out %.0f (blocks %llu)\n",
-            hs[0] / nb, hs[1] / nb, hs[2] / nb, hs[3] / nb, hs[4] / nb, hs[5] / nb, hs[6] / nb, hs[7] / nb, hs[8] / nb, hs[15]);
-  }
-  uint32_t herr = (uint32_t)g->h_pub[4];
-  const uint32_t nhard = (uint32_t)g->h_pub[5];
+  const uint32_t maxlevel = (uint32_t)g->h_pub[3];
+  const uint32_t herr = (uint32_t)g->h_pub[4];
   if (tot[0] > rv.halo_cap) {
     if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
     throw Error(WGA_E_WORKSPACE, "halo successors exceed the workspace");
@@ -1432,20 +1007,15 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
     throw Error(WGA_E_WORKSPACE, "d_succ too small: need " + std::to_string(tot[1] - tot[0]) + " elements");
   }
   check_device_error(g, herr, st);
-  // ---- nodes the tiles left to the global pass, one launch per depth
-  if (nhard) {
-    k_hard_levels<<<(nhard + 255) / 256, 256, 0, st>>>(rv);
-    k_publish<<<1, 32, 0, st>>>(rv.offs + rv.h, rv.offs + n, &sc->maxlevel, &sc->hard_count, g->d_err, g->d_pub);
-    count_launch(2);
-    WGA_CUDA(cudaStreamSynchronize(st));
-    const uint32_t maxlevel = (uint32_t)g->h_pub[3];
-    for (uint32_t l = 0; l <= maxlevel; ++l) {
-      k_hard_resolve<<<(nhard + 127) / 128, 128, 0, st>>>(rv, l, g->dev.min_interval);
+  // ---- reference chains deeper than LCAP (e.g. graphs compressed with an unbounded max_ref_count): one
+  //      launch per extra level over the shared deep segment
+  if (have_refs && maxlevel >= LCAP) {
+    for (uint32_t l = LCAP; l <= maxlevel; ++l) {
+      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, LCAP, l, lev, g->dev.min_interval);
       count_launch();
     }
     check_device_error(g, read_device_error(g, st), st);
   }
-  mark(g, st);  // 4: global pass done
 }
 
 static void apply_env_tuning() {
@@ -1468,18 +1038,11 @@ static void apply_env_tuning() {
 static void bind_views(RangeView& rv, uint8_t* w, const WorkspacePlan& p, Scalars* sc, uint64_t ws_bytes, uint32_t unit) {
   rv.outdeg = (uint32_t*)(w + p.off_outdeg);
   rv.nrec = (uint4*)(w + p.off_nrec);
-  rv.meta = (uint2*)(w + p.off_meta);
-  rv.hardflag = (uint8_t*)(w + p.off_hflag);
-  rv.hard_list = (uint32_t*)(w + p.off_hlist);
-  rv.hard_lev = (uint32_t*)(w + p.off_hlev);
-  rv.hard_count = &sc->hard_count;
+  rv.meta = (uint32_t*)(w + p.off_meta);
   rv.maxlevel = &sc->maxlevel;
-  rv.rows = (uint32_t*)(w + p.off_rows);
-  const uint64_t chunks = (ws_bytes - p.off_rows) / (4ull * CH * 32);
-  rv.rows_cap = (uint32_t)std::min<uint64_t>(chunks, 0xFFFFFFF0ull);
-  rv.chunk_ctr = &sc->chunk_ctr;
-  rv.stream_chunks = (uint32_t*)(w + p.off_schunks);
-  rv.unit_stream = (uint32_t*)(w + p.off_ustream);
+  rv.roff = (uint64_t*)(w + p.off_roff);
+  rv.recs = (uint32_t*)(w + p.off_recs);
+  rv.recs_cap = (ws_bytes - p.off_recs) / 4;
   rv.unit_ctr = &sc->unit_ctr;
   rv.unit = unit;
   rv.n_units = (rv.n + unit - 1) / unit;
@@ -1515,9 +1078,9 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     if (lo < g->res_first) throw Error(WGA_E_ARG, "reference chain leaves the resident shard");
   }
   const uint64_t n = last - lo;
-  const uint32_t unit = effective_tile(tn, (uint32_t)g->prelude.compression_window);
-  WorkspacePlan p = plan_workspace(n, unit);
-  if (ws_bytes < p.fixed_bytes + 4ull * CH * 32) throw Error(WGA_E_WORKSPACE, "workspace too small");
+  const uint32_t unit = effective_unit(tn);
+  WorkspacePlan p = plan_workspace(n);
+  if (ws_bytes < p.fixed_bytes + 4096) throw Error(WGA_E_WORKSPACE, "workspace too small");
   RangeView rv{};
   rv.lo = lo; rv.n = (uint32_t)n; rv.h = (uint32_t)(first - lo);
   bind_views(rv, w, p, sc, ws_bytes, unit);
@@ -1567,9 +1130,8 @@ BatchPlan plan_batch(uint64_t nq, uint64_t max_total_arcs, uint32_t unit) {
   b.off_cub = o; o = align_up(o + b.cub_bytes, 256);
   b.off_offsU = o; o = align_up(o + 8 * (b.cap_nodes + 1), 256);
   b.off_succU = o; o = align_up(o + 4 * b.cap_arcs, 256);
-  WorkspacePlan p = plan_workspace(b.cap_nodes, unit);
-  b.inner_bytes = p.fixed_bytes + 8 * b.cap_arcs + 48 * b.cap_nodes + (16ull << 20) +
-                  std::min<uint64_t>((b.cap_nodes + unit - 1) / unit, MAX_STREAMS) * (4ull * CH * 32);
+  WorkspacePlan p = plan_workspace(b.cap_nodes);
+  b.inner_bytes = p.fixed_bytes + 4 * (b.cap_arcs + b.cap_arcs / 4 + 8 * b.cap_nodes) + (16ull << 20);
   b.off_inner = align_up(o, 16384); o = b.off_inner + b.inner_bytes;
   b.total = o;
   return b;
@@ -1577,7 +1139,7 @@ BatchPlan plan_batch(uint64_t nq, uint64_t max_total_arcs, uint32_t unit) {
 }  // namespace
 
 uint64_t successors_workspace_size(const wga_graph* g, uint64_t n_queries, uint64_t max_total_arcs) {
-  return plan_batch(n_queries, max_total_arcs, effective_tile(g_tuning, (uint32_t)g->prelude.compression_window)).total;
+  return plan_batch(n_queries, max_total_arcs, effective_unit(g_tuning)).total;
 }
 
 void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64_t* d_offsets, uint32_t* d_succ,
@@ -1591,7 +1153,7 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   }
   apply_env_tuning();
   const Tuning tn = g_tuning;
-  const uint32_t unit = effective_tile(tn, (uint32_t)g->prelude.compression_window);
+  const uint32_t unit = effective_unit(tn);
   // the caller sizes the workspace with an upper bound of the arcs it expects; recover it from the size
   BatchPlan b = plan_batch(nq, 0, unit);
   if (ws_bytes < b.total) throw Error(WGA_E_WORKSPACE, "workspace too small");
@@ -1656,8 +1218,8 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   // ---- decode the node list U into a temporary CSR
   uint8_t* iw = w + b.off_inner;
   WGA_CUDA(cudaMemsetAsync(iw, 0, 256, st));
-  WorkspacePlan p = plan_workspace(nU, unit);
-  if (p.fixed_bytes + 4ull * CH * 32 > b.inner_bytes) throw Error(WGA_E_WORKSPACE, "workspace too small");
+  WorkspacePlan p = plan_workspace(nU);
+  if (p.fixed_bytes + 4096 > b.inner_bytes) throw Error(WGA_E_WORKSPACE, "workspace too small");
   Scalars* sc = (Scalars*)iw;
   RangeView rv{};
   rv.lo = 0; rv.n = nU; rv.h = 0; rv.nodes = U;

@@ -83,32 +83,6 @@ __device__ __forceinline__ bool ans_extend(Dec& d, const uint16_t* __restrict__ 
   return true;
 }
 
-// The fold loop of the reference takes R bits per trip (decoder.rs:74-85, up to 38 trips).  Between two
-// extends the trips only shift the state, so they are done in one step per extend: with n = bit length of the
-// state, the next j = ceil((n-16)/R) trips need no extend (the state stays >= 2^16 until the j-th shift), they
-// consume the low j*R bits, and the chunks enter `fold` first-taken-highest, i.e. in reversed group order.
-// General form (any fold count, any radix); the decoders below only come here when the one-step form does not apply.
-__device__ __forceinline__ uint64_t ans_unfold_general(uint32_t sym, uint32_t folds, uint32_t R, uint32_t recip, Dec& d,
-                                                       const uint16_t* __restrict__ stream, uint32_t& err) {
-  const uint32_t rmask = (1u << R) - 1u;
-  uint32_t rem = folds;
-  uint64_t fold = 0;
-  do {
-    const uint32_t n = 32u - (uint32_t)__clz((int)d.state);  // 17..32 (state >= 2^16 here)
-    uint32_t t = ((n - 16u + R - 1u) * recip) >> 16;           // ceil((n-16)/R): trips until state < 2^16
-    t = max(min(t, rem), 1u);  // >= 1 also on corrupt input (state < 2^16 after a failed extend)
-    const uint32_t nb = t * R;                                 // <= 31 bits
-    uint32_t bits = d.state & ((1u << nb) - 1u);
-    d.state >>= nb;
-    uint32_t grp = 0;
-    for (uint32_t q = 0; q < t; ++q) { grp = (grp << R) | (bits & rmask); bits >>= R; }
-    fold = (fold << nb) | grp;
-    rem -= t;
-    if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
-  } while (rem);
-  return ((uint64_t)sym << (folds * R)) | fold;
-}
-
 // One ANS symbol.  Restates ANSDecoder::decode (src/ans/decoder.rs:58-87) on the packed tables:
 //   slot  = state & (2^L-1)                                   decoder.rs:59
 //   entry = owner(slot)                                       decoder.rs:60  (bucket + popcount of the start mask)
@@ -116,9 +90,11 @@ __device__ __forceinline__ uint64_t ans_unfold_general(uint32_t sym, uint32_t fo
 //   one conditional 16-bit extend                             decoder.rs:67-69, 89-93
 //   folds x { [extend]; fold=(fold<<R)|(state&(2^R-1)); state>>=R; [extend] }   decoder.rs:74-85
 //   result = (base << folds*R) | fold                         decoder.rs:86 with quasi_fold (model4decoder.rs:56-68)
-// The folds are taken in ONE step when no extend falls between two trips ((folds-1)*R < bit length - 16: the state
-// stays >= 2^16 until the last shift) and the group reversal is cheap (radix 1: bit reversal; one or two groups);
-// that covers practically every folded symbol, so all lanes of a warp run the same short sequence.
+// The fold loop of the reference takes R bits per trip (up to 38 trips).  Between two extends the trips only shift
+// the state, so they are done in one step per extend: with n = bit length of the state, the next
+// t = ceil((n-16)/R) trips need no extend (the state stays >= 2^16 until the t-th shift), they consume the low t*R
+// bits, and the chunks enter `fold` first-taken-highest, i.e. in reversed group order (radix 1: a bit reversal).
+// One loop for every folded symbol (usually one or two passes), so that the folded lanes of a warp stay together.
 template <class Tab>
 __device__ __forceinline__ uint64_t ans_decode_cp(const uint4 cp, const Tab& tab, Dec& d,
                                                   const uint16_t* __restrict__ stream, uint32_t& err) {
@@ -127,29 +103,37 @@ __device__ __forceinline__ uint64_t ans_decode_cp(const uint4 cp, const Tab& tab
   const uint2 bk = tab.bucket(cp.y + (slot >> 5));
   const uint32_t j = bk.y + (uint32_t)__popc(bk.x & ((2u << (slot & 31u)) - 1u));
   const uint2 e = tab.entry(cp, cp.z, j);
-  const uint32_t folds = e.y >> 16;
-  if (folds == 0xFFFFu) {  // sentinel: slot beyond the sum of frequencies
+  uint32_t rem = e.y >> 16;  // folds
+  if (rem == 0xFFFFu) {  // sentinel: slot beyond the sum of frequencies
     err |= ERR_CORRUPT;
     return 0;
   }
   d.state = (d.state >> L) * (e.x >> 16) + slot - (e.x & 0xFFFFu);
   if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
-  const uint32_t sym = e.y & 0xFFFFu;
-  if (folds == 0) return sym;
-  const uint32_t R = (cp.x >> 21) & 31u;
-  const uint32_t nb = folds * R;
-  const uint32_t room = 16u - (uint32_t)__clz((int)d.state);  // bit length - 16 (state >= 2^16)
-  if (nb - R < room && (R == 1 || folds <= 2)) {
-    const uint32_t bits = d.state & ((1u << nb) - 1u);  // nb <= 31
-    d.state >>= nb;
-    uint32_t grp;
-    if (R == 1) grp = __brev(bits) >> (32u - nb);
-    else if (folds == 2) grp = ((bits & ((1u << R) - 1u)) << R) | (bits >> R);
-    else grp = bits;
-    if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
-    return ((uint64_t)sym << nb) | grp;
+  uint64_t val = e.y & 0xFFFFu;
+  if (rem) {
+    const uint32_t R = (cp.x >> 21) & 31u;
+    const uint32_t recip = tab.recip(cp);  // floor(65536/R)+1
+    const uint32_t rmask = (1u << R) - 1u;
+    do {
+      const uint32_t room = 16u - (uint32_t)__clz((int)d.state);  // bit length - 16 (>= 1 while state >= 2^16)
+      uint32_t t = ((room + R - 1u) * recip) >> 16;                // ceil(room/R): trips until state < 2^16
+      t = max(min(t, rem), 1u);  // >= 1 also on corrupt input (state < 2^16 after a failed extend)
+      const uint32_t nb = t * R;                                   // <= 31 bits
+      uint32_t bits = d.state & ((1u << nb) - 1u);
+      d.state >>= nb;
+      uint32_t grp;
+      if (R == 1) grp = __brev(bits) >> (32u - nb);
+      else {
+        grp = 0;
+        for (uint32_t q = t; q; --q) { grp = (grp << R) | (bits & rmask); bits >>= R; }
+      }
+      val = (val << nb) | grp;
+      rem -= t;
+      if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
+    } while (rem);
   }
-  return ans_unfold_general(sym, folds, R, tab.recip(cp), d, stream, err);
+  return val;
 }
 
 template <class Tab>
