@@ -2,19 +2,26 @@
 """bench.py -- full-graph ANS decode throughput (Garcs/s) on B200, with roofline and CPU baseline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+                    [--scaling strong|weak] [--random-nodes Q]
 
-A "step" is one full decode of the rank's graph: every node of an ANS-compressed BvGraph
-(.ans + .pointers + .states, resident in HBM) into CSR successor lists in HBM.  Default workload at
-N=1: a synthetic eu-2015-host-shaped web graph (11,264,052 nodes, ~387 M arcs; BASELINE.json configs[2],
-the configuration the 1/2/4/8-GPU metric is quoted on).  With N ranks every rank decodes its own graph of
-that shape (weak scaling, no data-path collective); the model tables are built once from histograms
-all-reduced over NCCL, as in the north star.
+A "step" is one full decode of the graph: every node of an ANS-compressed BvGraph (.ans + .pointers + .states,
+resident in HBM) into CSR successor lists in HBM.  Default workload: a synthetic eu-2015-host-shaped web graph
+(11,264,052 nodes, ~388 M arcs; BASELINE.json configs[2], the configuration the 1/2/4/8-GPU metric is quoted on).
 
-Inputs are produced on the box by the product's own host front end (synthetic generator -> BvComp ->
-GPU model build -> serial ANS encode) and cached under /tmp; none of that is timed.
-The oracle (oracle/) is used only by the cpu_baseline leg, the post-run verification and --impl reference.
+N ranks (torchrun, one per GPU), default --scaling strong: ONE graph, sharded by contiguous node ranges balanced
+by compressed stream words.  Every rank opens only its shard (wga_open_shard), finds the few
+predecessor nodes its range references (k_halo) and decodes independently: no data-path collective.  The graph is
+built cooperatively: every rank runs the BvComp front end on its node range, the symbol histograms are all-reduced
+over NCCL, every rank derives the identical model, rank 0 runs the (serial) ANS encode.  --scaling weak: every rank
+decodes its own graph of the named shape (what a gsh-2015-shaped graph needs: workload gsh-2015-shard x 8).
+
+Inputs are produced on the box by the product's own host front end (synthetic generator -> BvComp -> GPU model
+build -> serial ANS encode) and cached under /tmp; none of that is timed.
+The oracle (oracle/) is used only by the cpu_baseline leg, the post-run verification and --impl reference, which
+never loads the product library.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -37,12 +44,6 @@ WORKLOADS = {
     "web-1m": ("web", 1_000_000, 34.3, 0x5EED0010),
     "tiny": ("web", 100_000, 34.3, 0x5EED0011),
 }
-# measured DRAM traffic of one decode step (sum over the kernels of the chain), see profiles/r01_*_ncu_*.txt
-NCU_DRAM_BYTES_PER_STEP = {
-    # profiles/r01_v3_ncu_full_eu-host.txt: k_outdegree 0.46 + k_entropy 2.09 + k_levels 0.15 + k_resolve levels
-    # 0..3 0.60+1.12+1.27+1.76 GB (the cub scan/sort launches, ~2 % of the step, were not captured)
-    "eu-2015-host-shaped": 7.45e9,
-}
 BVCOMP = dict(compression_window=7, max_ref_count=3, min_interval_length=4)  # CLI defaults
 CHUNK_NODES = 65536
 
@@ -61,6 +62,22 @@ def measured_peak_gbs():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def captured_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the launch chain of one decode step, captured with
+    `ncu --set full` for THIS build and committed under profiles/ (not measured in the run that prints it)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(workload)
+        return (float(t["bytes"]), t["source"]) if t else (None, None)
+    except Exception:
+        return None, None
+
+
+def config_of(name, nodes, arcs):
+    """The same object in both arms (the driver compares them)."""
+    return {"workload": name, "nodes": int(nodes), "arcs": int(arcs), "bvcomp": BVCOMP}
 
 
 class ClockSampler:
@@ -111,94 +128,205 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def prepare_workload(W, name, rank, world, dist=None):
-    """Generates + compresses this rank's graph with the product's host front end and GPU model builder.
-    Returns (basename, meta).  Cached under /tmp (rank-specific)."""
-    kind, n, deg, seed = WORKLOADS[name]
-    seed = seed + 1000 * rank
-    cache = os.environ.get("WGA_BENCH_CACHE", "/tmp/wga_bench")
-    os.makedirs(cache, exist_ok=True)
-    base = os.path.join(cache, f"{name}-w{world}-r{rank}")
-    meta_path = base + ".json"
-    have = all(os.path.exists(base + e) for e in (".ans", ".pointers", ".states", ".json"))
-    if dist is not None and world > 1:  # every rank must take the same path (collectives inside)
-        import torch
-        flag = torch.tensor([1 if have else 0], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        have = bool(flag.item())
-    if have:
-        return base, json.load(open(meta_path))
-    thr = host_threads(world)
+def bind_to_gpu_numa_node(local_rank):
+    """Runs this rank on the host cores next to its GPU, so that the pinned result buffers it allocates afterwards
+    (first touch) and the staging copies are NUMA-local.  Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1 and 64 * w + b < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": f"{cpus[0]}-{cpus[-1]}", "count": len(cpus)}
+    except Exception as e:  # not fatal: the numbers are then measured without placement control
+        return {"error": str(e)[:80]}
+    return None
+
+
+# ---------------------------------------------------------------------------------------------- inputs
+def node_split(n, world):
+    """Contiguous node ranges for the cooperative build, aligned to the BvComp chunks."""
+    per = (n + world - 1) // world
+    per = (per + CHUNK_NODES - 1) // CHUNK_NODES * CHUNK_NODES
+    return [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+
+
+def build_graph(W, name, seed, base, rank, world, dist, thr, keep_symbols=False):
+    """Generates + compresses ONE graph with the product's host front end and GPU model builder; with world > 1 the
+    ranks share the work (node ranges) and the histograms are all-reduced.  Rank 0 writes the files."""
+    kind, n, deg, _ = WORKLOADS[name]
+    a, b = node_split(n, world)[rank]
     t0 = time.time()
-    off, succ = W.synth_graph(kind, n, deg, seed=seed, threads=thr)
+    off, succ = W.synth_graph(kind, n, deg, seed=seed, first=a, last=b, threads=thr)
     t_gen = time.time() - t0
-    log(f"rank {rank}: generated {name}: {n} nodes, {succ.size} arcs in {t_gen:.1f}s ({thr} threads)")
+    log(f"rank {rank}: generated nodes [{a},{b}) of {name}: {succ.size} arcs in {t_gen:.1f}s ({thr} threads)")
     tables = None
     t_model = 0.0
+    comps = syms = None
     for p in (1, 2):  # pass 1: Log2Estimator ; pass 2: EntropyEstimator(model1)   (random_access.rs:105-163)
         t1 = time.time()
-        comps, syms = W.bvcomp_symbols(off, succ, estimator_tables=tables, chunk_nodes=CHUNK_NODES, threads=thr, **BVCOMP)
+        comps, syms = W.bvcomp_symbols(off, succ, estimator_tables=tables, chunk_nodes=CHUNK_NODES, threads=thr,
+                                       first_node=a, **BVCOMP)
         t2 = time.time()
         mb = W.ANSModel4EncoderBuilder()
         mb.push_symbols(comps, syms)
-        if dist is not None and world > 1:
+        if world > 1:
             mb.all_reduce()  # NCCL all-reduce of the histogram bins + all-gather of the sparse tail
         tables, _, _ = mb.build()
         del mb
         t_model += time.time() - t2
         log(f"rank {rank}: pass {p}: {syms.size} symbols, bvcomp {t2 - t1:.1f}s, model build {time.time() - t2:.1f}s")
-    t3 = time.time()
-    stream, state, states, pointers = W.ans_encode(tables, comps, syms)
-    t_enc = time.time() - t3
-    W.write_files(base, tables, stream, state, n, BVCOMP["compression_window"], BVCOMP["min_interval_length"],
-                  int(succ.size), states, pointers)
-    meta = dict(workload=name, nodes=int(n), arcs=int(succ.size), symbols=int(syms.size), stream_words=int(stream.size),
-                bits_per_link=float(stream.size * 16 / max(1, succ.size)), seed=int(seed), gen_s=t_gen,
-                model_build_s=t_model, encode_s=t_enc,
-                models=[[t["frame_size"], t["fidelity"], t["radix"], int(t["entries"].size)] for t in tables])
-    json.dump(meta, open(meta_path, "w"))
-    log(f"rank {rank}: encoded in {t_enc:.1f}s: {meta['bits_per_link']:.3f} bit/link, {stream.size * 2 / 1e6:.1f} MB stream")
-    return base, meta
+    arcs_local = int(succ.size)
+    del off, succ
+    if world > 1:  # the serial encode needs every symbol on rank 0: through the cache directory (same box)
+        import torch
+        np.save(base + f".sym{rank}.c.npy", comps)
+        np.save(base + f".sym{rank}.v.npy", syms)
+        tot = torch.tensor([arcs_local, int(syms.size)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        dist.barrier()
+        arcs_all, nsym_all = int(tot[0].item()), int(tot[1].item())
+        if rank == 0:
+            comps = np.concatenate([np.load(base + f".sym{r}.c.npy") for r in range(world)])
+            syms = np.concatenate([np.load(base + f".sym{r}.v.npy") for r in range(world)])
+            for r in range(world):
+                os.remove(base + f".sym{r}.c.npy")
+                os.remove(base + f".sym{r}.v.npy")
+    else:
+        arcs_all, nsym_all = arcs_local, int(syms.size)
+    if rank == 0:
+        t3 = time.time()
+        stream, state, states, pointers = W.ans_encode(tables, comps, syms)
+        t_enc = time.time() - t3
+        W.write_files(base, tables, stream, state, n, BVCOMP["compression_window"], BVCOMP["min_interval_length"],
+                      arcs_all, states, pointers)
+        meta = dict(workload=name, nodes=int(n), arcs=arcs_all, symbols=nsym_all, stream_words=int(stream.size),
+                    bits_per_link=float(stream.size * 16 / max(1, arcs_all)), seed=int(seed), gen_s=t_gen,
+                    model_build_s=t_model, encode_s=t_enc, build_ranks=world,
+                    models=[[t["frame_size"], t["fidelity"], t["radix"], int(t["entries"].size)] for t in tables])
+        if keep_symbols:
+            np.save(base + ".symbols.c.npy", comps)
+            np.save(base + ".symbols.v.npy", syms)
+        json.dump(meta, open(base + ".json", "w"))
+        log(f"encoded in {t_enc:.1f}s: {meta['bits_per_link']:.3f} bit/link, {stream.size * 2 / 1e6:.1f} MB stream")
+    if world > 1:
+        dist.barrier()
 
 
+def prepare_workload(W, name, rank, world, dist=None, scaling="strong", keep_symbols=False):
+    """-> (basename, meta).  strong (or one rank): one graph for all ranks.  weak: one graph per rank."""
+    _, _, _, seed = WORKLOADS[name]
+    cache = os.environ.get("WGA_BENCH_CACHE", "/tmp/wga_bench")
+    os.makedirs(cache, exist_ok=True)
+    shared = world == 1 or scaling == "strong"
+    base = os.path.join(cache, f"{name}-one" if shared else f"{name}-w{world}-r{rank}")
+    need = [".ans", ".pointers", ".states", ".json"] + ([".symbols.c.npy", ".symbols.v.npy"] if keep_symbols else [])
+    have = all(os.path.exists(base + e) for e in need)
+    if dist is not None and world > 1:  # every rank must take the same path (collectives inside)
+        import torch
+        flag = torch.tensor([1 if have else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        have = bool(flag.item())
+    if not have:
+        if shared:
+            build_graph(W, name, seed, base, rank, world, dist, host_threads(world), keep_symbols)
+        else:
+            build_graph(W, name, seed + 1000 * rank, base, 0, 1, None, host_threads(world), keep_symbols)
+    return base, json.load(open(base + ".json"))
+
+
+def nrank_model_parity(W, O, rank, world, dist):
+    """Parity of the N-rank model build on hardware: every rank histograms the symbols of its node range of a small
+    graph, the bins are all-reduced (NCCL) and the sparse tails merged; rank 0 compares all table fields of every
+    component with the oracle's build() on the union of the symbols."""
+    import torch
+    kind, n, deg, seed = WORKLOADS["tiny"]
+    n = 8 * CHUNK_NODES
+    a, b = node_split(n, world)[rank]
+    off, succ = W.synth_graph(kind, n, deg, seed=seed, first=a, last=b, threads=host_threads(world))
+    comps, syms = W.bvcomp_symbols(off, succ, chunk_nodes=CHUNK_NODES, threads=host_threads(world), first_node=a, **BVCOMP)
+    mb = W.ANSModel4EncoderBuilder()
+    mb.push_symbols(comps, syms)
+    mb.all_reduce()
+    tables, _, _ = mb.build()
+    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([syms.size], dtype=torch.int64, device="cuda"))
+    mx = int(max(s.item() for s in sizes))
+    pad_c = torch.zeros(mx, dtype=torch.uint8, device="cuda")
+    pad_v = torch.zeros(mx, dtype=torch.int64, device="cuda")
+    pad_c[:syms.size] = torch.from_numpy(comps).cuda()
+    pad_v[:syms.size] = torch.from_numpy(syms.view(np.int64)).cuda()
+    all_c = [torch.zeros_like(pad_c) for _ in range(world)]
+    all_v = [torch.zeros_like(pad_v) for _ in range(world)]
+    dist.all_gather(all_c, pad_c)
+    dist.all_gather(all_v, pad_v)
+    ok = None
+    if rank == 0:
+        cc = np.concatenate([all_c[r][:int(sizes[r].item())].cpu().numpy() for r in range(world)])
+        vv = np.concatenate([all_v[r][:int(sizes[r].item())].cpu().numpy().view(np.uint64) for r in range(world)])
+        og = O.OracleGraph()
+        og.build_model(cc, vv)
+        ok = True
+        for c in range(9):
+            ref, ours = og.table(c), tables[c]
+            for f in ("frame_size", "radix", "fidelity"):
+                ok = ok and int(ref[f]) == int(ours[f])
+            re, oe = ref["entries"], ours["entries"]
+            ok = ok and re.size == oe.size and all(bool((re[f] == oe[f]).all()) for f in ("freq", "cumul_freq", "upperbound"))
+        log(f"{world}-rank model build vs oracle on the union of {cc.size} symbols: {'bit-exact' if ok else 'MISMATCH'}")
+    return ok
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
-    """--impl reference: the reference's CPU decode of the same path.  The reference is Rust and cannot be
-    built in this image (no rustc/cargo), so this times the oracle PORT (oracle/) on all host threads:
-    node-range-parallel decode from the per-node phases, each step a bounded node range of the workload."""
+    """--impl reference: the reference's CPU decode of the same path.  The reference is Rust and cannot be built in
+    this image (no rustc/cargo), so this times the oracle PORT (oracle/) on all host threads: node-range-parallel
+    decode from the per-node phases, each step a bounded node range of the workload.  Nothing of the product is
+    loaded: the sample graph is generated and compressed by the oracle itself."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
-    import wga_pkg
-    W = wga_pkg.load()
-    world = 1
-    import torch
-    if torch.cuda.is_available():
-        torch.cuda.set_device(0)
-    base, meta = prepare_workload(W, args.workload, 0, world)
-    og = O.OracleGraph.load(base)
-    n = meta["nodes"]
+    kind, n, deg, seed = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    # size the sample so that steps+warmup take ~2 minutes
-    arcs, secs = og.decode_parallel(0, min(n, 200_000), cores)
+    sample_nodes = int(min(n, 1_500_000))
+    t0 = time.time()
+    # arcs of the whole workload (degrees only: offsets without successors), then a prefix of the same graph as sample
+    arcs_total = None
+    if n <= 50_000_000:
+        arcs_total = int(O.synth_degrees(kind, n, deg, seed, cores))
+    off, succ = O.synth_graph(kind, n, deg, seed, 0, sample_nodes, cores)
+    og = O.OracleGraph.store_csr(off, succ, BVCOMP["compression_window"], BVCOMP["max_ref_count"],
+                                 BVCOMP["min_interval_length"])
+    log(f"reference arm: sample graph (nodes [0,{sample_nodes}) of {args.workload}, {succ.size} arcs) stored by the "
+        f"oracle in {time.time() - t0:.1f}s")
+    if arcs_total is None:
+        arcs_total = int(succ.size / sample_nodes * n)
+    # size a step so that steps+warmup take ~2 minutes
+    arcs, secs = og.decode_parallel(0, min(sample_nodes, 200_000), cores)
     rate = arcs / max(secs, 1e-9)
     budget = 120.0 / max(1, args.steps + args.warmup)
-    sample_nodes = int(min(n, max(200_000, rate * budget / (meta["arcs"] / n))))
+    step_nodes = int(min(sample_nodes, max(200_000, rate * budget / (succ.size / sample_nodes))))
     for _ in range(args.warmup):
-        og.decode_parallel(0, sample_nodes, cores)
+        og.decode_parallel(0, step_nodes, cores)
     tot_arcs, tot_secs = 0, 0.0
     for _ in range(args.steps):
-        a, s = og.decode_parallel(0, sample_nodes, cores)
+        a, s = og.decode_parallel(0, step_nodes, cores)
         tot_arcs += a
         tot_secs += s
     value = tot_arcs / tot_secs / 1e9
-    sample = f"nodes [0,{sample_nodes}) of {args.workload} ({tot_arcs // max(1, args.steps)} arcs) per step, node-range parallel"
+    sample = (f"nodes [0,{step_nodes}) of {args.workload} ({tot_arcs // max(1, args.steps)} arcs) per step, node-range "
+              f"parallel on {cores} threads; inputs built by the oracle (no product code loaded)")
     line = {"impl": "reference", "metric": "full-graph decode throughput", "value": value, "unit": "Garcs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": tot_secs / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": tot_secs / max(1, args.steps) * 1e3, "higher_is_better": True,
+            "scaling": args.scaling if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": args.workload, "nodes": n, "arcs": meta["arcs"], "bvcomp": BVCOMP},
+            "config": config_of(args.workload, n, arcs_total),
             "cpu_baseline": {"value": value, "unit": "Garcs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Garcs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -224,6 +352,22 @@ def emit(line):
     out.flush()
 
 
+def checksum64(off_np, succ_np):
+    """Order-dependent 64-bit checksum of a CSR piece (offsets relative to its first node); wraps mod 2^64."""
+    i = np.arange(1, succ_np.size + 1, dtype=np.uint64)
+    s = (succ_np.astype(np.uint64) * i).sum(dtype=np.uint64)
+    j = np.arange(1, off_np.size + 1, dtype=np.uint64)
+    return (int(s) ^ int((off_np.astype(np.uint64) * j).sum(dtype=np.uint64))) & 0xFFFFFFFFFFFFFFFF
+
+
+def checksum64_cuda(torch, off, succ):
+    i = torch.arange(1, succ.numel() + 1, dtype=torch.int64, device=succ.device)
+    s = ((succ.to(torch.int64) & 0xFFFFFFFF) * i).sum()
+    j = torch.arange(1, off.numel() + 1, dtype=torch.int64, device=off.device)
+    o = (off.to(torch.int64) * j).sum()
+    return ((int(s.item()) & 0xFFFFFFFFFFFFFFFF) ^ (int(o.item()) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -231,11 +375,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="eu-2015-host-shaped", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N>1: strong = one graph sharded by node ranges; weak = one graph of the shape per rank")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--random-nodes", type=int, default=1_000_000,
                     help="queries of the random-access leg (reference: 10M on twitter-2010)")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-model-leg", action="store_true")
     args = ap.parse_args()
     quiet_stdout()
     if args.warmup < 3 and args.impl == "ours":
@@ -256,30 +403,59 @@ def main():
     if not (torch.cuda.is_available() and W.cuda_available()):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the decode path")
     torch.cuda.set_device(local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    strong = world > 1 and args.scaling == "strong"
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    base, meta = prepare_workload(W, args.workload, rank, world, dist if world > 1 else None)
-    g = W.ANSBvGraph.load(base)
-    n, arcs = g.num_nodes(), g.num_arcs_hint()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    model_parity = None
+    if world > 1:
+        import oracle_py as O0
+        model_parity = nrank_model_parity(W, O0, rank, world, dist)
+
+    want_model_leg = world == 1 and not args.no_model_leg and WORKLOADS[args.workload][1] <= 20_000_000
+    base, meta = prepare_workload(W, args.workload, rank, world, dist if world > 1 else None, args.scaling,
+                                  keep_symbols=want_model_leg)
+    N_total, arcs_total = meta["nodes"], meta["arcs"]
+    # ---- this rank's node range
+    halo_nodes = 0
+    if strong:
+        ptrs = W.ANSBvGraph.load(base, host_only=True).prelude()["pointers"]
+        first, last = W.shard_ranges(ptrs, world)[rank]
+        res_first, _ = W.shard_resident_range(first, last, BVCOMP["compression_window"])
+        del ptrs
+        g = W.ANSBvGraph.load(base, shard=(res_first, last))
+    else:
+        g = W.ANSBvGraph.load(base)
+        first, last = 0, g.num_nodes()
+        res_first = 0
+    n = last - first
     off = torch.empty(n + 1, dtype=torch.int64, device="cuda")
-    succ = torch.empty(arcs + 1024, dtype=torch.int32, device="cuda")
-    ws = torch.empty(g.workspace_size(0, n), dtype=torch.uint8, device="cuda")
-    compressed = g.compressed_bytes()
-    b_alg = compressed + 4 * arcs  # SURVEY.md 8d: compressed bytes read + 4-byte arcs written
+    ws = torch.empty(g.workspace_size(first, last), dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
+    # arcs of the range: one outdegree pass (not timed)
+    rc = W.lib().wga_outdegrees(g._h, C.c_uint64(first), C.c_uint64(last), C.c_void_p(off.data_ptr()),
+                                C.c_void_p(ws.data_ptr()), C.c_uint64(ws.numel()), C.c_void_p(stream))
+    assert rc == 0, W.lib().wga_last_error()
+    arcs = int(off[-1].item())
+    succ = torch.empty(arcs + 1024, dtype=torch.int32, device="cuda")
+    compressed = int(g.compressed_bytes() * n / max(1, last - res_first))  # this range's share of the resident inputs
+    b_alg = compressed + 4 * arcs  # SURVEY.md 8d: compressed bytes read + 4-byte arcs written
 
     def step():
-        g.decode_range_into(0, n, off, succ, ws, stream=stream)
+        g.decode_range_into(first, last, off, succ, ws, stream=stream)
 
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
+    if strong:
+        halo_nodes = int(W.lib().wga_last_halo_nodes(g._h))
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -294,23 +470,25 @@ def main():
     barrier()
     launches = W.kernel_launches() - k0
     ms = e0.elapsed_time(e1) / args.steps
-    t = torch.tensor([ms, float(arcs), float(b_alg)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, float(arcs), float(b_alg), float(halo_nodes)], dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
-        mx = t.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = t.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms_max, arcs_all, bytes_all = mx[0].item(), sm[1].item(), sm[2].item()
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        ms_all = [x[0].item() for x in allt]
+        ms_max, arcs_all, bytes_all = max(ms_all), sum(x[1].item() for x in allt), sum(x[2].item() for x in allt)
+        per_rank = {"ms": ms_all, "arcs": [int(x[1].item()) for x in allt], "halo_nodes": [int(x[3].item()) for x in allt],
+                    "imbalance_max_over_mean": ms_max / (sum(ms_all) / world)}
     else:
         ms_max, arcs_all, bytes_all = ms, float(arcs), float(b_alg)
     value = arcs_all / (ms_max * 1e-3) / 1e9
 
     # ---- per-stage device times of one decode (CUDA events inside the library, same stream)
     W.lib().wga_set_profiling(g._h, 1)
-    import ctypes as C
     stages = np.zeros(8, np.float32)
     acc = np.zeros(8)
     reps = 5
+    nev = 0
     for _ in range(reps):
         step()
         torch.cuda.synchronize()
@@ -318,56 +496,109 @@ def main():
         acc += stages
     W.lib().wga_set_profiling(g._h, 0)
     acc /= reps
-    stage_names = ["heads+scan(k_heads,cub)", "entropy_decode(k_entropy)", "tiles(k_tile)",
-                   "global_pass(k_hard_*)"]
+    stage_names = ["heads+scans(k_heads,cub)", "entropy_decode(k_entropy)", "levels+sort(k_levels,cub)",
+                   "resolve(k_resolve x levels)"]
     kernels = {stage_names[i]: float(acc[i]) for i in range(min(4, max(0, nev - 1)))}
     peak, peak_src = measured_peak_gbs()
     step_kernel_ms = float(sum(kernels.values())) or ms
     achieved = b_alg / (step_kernel_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of the whole launch chain from the committed ncu --set full
-    # capture (profiles/, one step of this workload); None for workloads that were not captured
-    traffic = NCU_DRAM_BYTES_PER_STEP.get(args.workload)
+    traffic, traffic_src = captured_traffic(args.workload) if world == 1 else (None, None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "kernel": "decode step = k_outdegree + scan + k_entropy + k_levels + sort + k_resolve per level; one launch chain per step",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": "decode step = k_heads + 2 scans + k_entropy + k_levels + sort + k_resolve per level; one launch chain per step",
                 "algorithmic_bytes_per_step": int(b_alg), "bytes_per_arc": b_alg / max(1, arcs),
                 "stage_ms": kernels, "step_ms_events": step_kernel_ms}
 
     # ---- random access (examples/bench_random_access.rs:15,30-38): uniformly random nodes, seed 0,
     #      ns/arc = device time of wga_successors_batch / sum of outdegrees
-    ra_gpu = None
-    try:
-        nq = int(min(args.random_nodes, max(1000, n)))
-        rng = np.random.default_rng(0)
-        q_t = torch.from_numpy(rng.integers(0, n, nq).astype(np.int64)).cuda()
-        q_off = torch.empty(nq + 1, dtype=torch.int64, device="cuda")
-        sz_ws = torch.empty(g.successors_workspace_size(nq, 0), dtype=torch.uint8, device="cuda")
-        got_arcs = C.c_uint64(0)
-        rc = W.lib().wga_successors_batch(g._h, C.c_void_p(q_t.data_ptr()), C.c_uint64(nq), C.c_void_p(q_off.data_ptr()),
-                                          None, C.c_uint64(0), C.c_void_p(sz_ws.data_ptr()), C.c_uint64(sz_ws.numel()),
-                                          C.byref(got_arcs), C.c_void_p(stream))
-        assert rc == 0, W.lib().wga_last_error()
-        q_arcs = got_arcs.value
-        del sz_ws
-        q_succ = torch.empty(q_arcs + 1024, dtype=torch.int32, device="cuda")
-        q_ws = torch.empty(g.successors_workspace_size(nq, q_arcs), dtype=torch.uint8, device="cuda")
-        for _ in range(2):
-            g.successors_batch_into(q_t, q_off, q_succ, q_ws, stream=stream)
-        torch.cuda.synchronize()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        for _ in range(3):
-            g.successors_batch_into(q_t, q_off, q_succ, q_ws, stream=stream)
-        r1.record()
-        torch.cuda.synchronize()
-        ra_ms = r0.elapsed_time(r1) / 3
-        ra_gpu = {"queries": nq, "arcs": int(q_arcs), "ms": ra_ms, "ns_per_arc": ra_ms * 1e6 / max(1, q_arcs),
-              "Garcs_per_s": q_arcs / (ra_ms * 1e-3) / 1e9}
-        ra_check = (q_t.cpu().numpy(), q_off.cpu().numpy().astype(np.uint64), q_succ[:q_arcs].cpu().numpy().view(np.uint32))
-        del q_succ, q_ws
-    except Exception as e:  # reported, not fatal: the headline metric is the full decode
-        log("random access leg failed:", e)
-        ra_check = None
+    ra_gpu, ra_check = None, None
+    if world == 1 and args.random_nodes > 0:
+        try:
+            nq = int(args.random_nodes)
+            rng = np.random.default_rng(0)
+            q_np = rng.integers(0, n, nq).astype(np.int64)
+            q_t = torch.from_numpy(q_np).cuda()
+            q_off = torch.empty(nq + 1, dtype=torch.int64, device="cuda")
+            sz_ws = torch.empty(g.successors_workspace_size(nq, 0), dtype=torch.uint8, device="cuda")
+            got_arcs = C.c_uint64(0)
+            rc = W.lib().wga_successors_batch(g._h, C.c_void_p(q_t.data_ptr()), C.c_uint64(nq), C.c_void_p(q_off.data_ptr()),
+                                              None, C.c_uint64(0), C.c_void_p(sz_ws.data_ptr()), C.c_uint64(sz_ws.numel()),
+                                              C.byref(got_arcs), C.c_void_p(stream))
+            assert rc == 0, W.lib().wga_last_error()
+            q_arcs = got_arcs.value
+            del sz_ws
+            q_succ = torch.empty(q_arcs + 1024, dtype=torch.int32, device="cuda")
+            q_ws = torch.empty(g.successors_workspace_size(nq, q_arcs), dtype=torch.uint8, device="cuda")
+            for _ in range(2):
+                g.successors_batch_into(q_t, q_off, q_succ, q_ws, stream=stream)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(3):
+                g.successors_batch_into(q_t, q_off, q_succ, q_ws, stream=stream)
+            r1.record()
+            torch.cuda.synchronize()
+            ra_ms = r0.elapsed_time(r1) / 3
+            # algorithmic bytes of the batch: the records of the queried nodes (stream words, 4-byte state, their share
+            # of the pointer payload), the 8-byte query ids and offsets, the 4-byte arcs written.  The records of the
+            # referenced nodes on the chains, which the reference re-decodes per query as well, are not counted.
+            ptrs = g.prelude()["pointers"]
+            Nn = ptrs.size
+            hi = ptrs[Nn - 1 - q_np]
+            lo = np.where(q_np + 1 < Nn, ptrs[np.maximum(Nn - 2 - q_np, 0)], 0)
+            ptr_payload = max(0, int(g.compressed_bytes()) - 2 * int(ptrs[-1]) - 4 * Nn)
+            ra_alg = int(2 * (hi - lo).sum()) + 4 * nq + ptr_payload * nq // max(1, Nn) + 16 * nq + 4 * q_arcs
+            ra_gpu = {"queries": nq, "arcs": int(q_arcs), "ms": ra_ms, "ns_per_arc": ra_ms * 1e6 / max(1, q_arcs),
+                      "Garcs_per_s": q_arcs / (ra_ms * 1e-3) / 1e9,
+                      "roofline": {"bound": "hbm", "algorithmic_bytes": int(ra_alg), "achieved": ra_alg / (ra_ms * 1e-3) / 1e9,
+                                   "peak": peak, "unit": "GB/s", "frac": ra_alg / (ra_ms * 1e-3) / 1e9 / peak}}
+            ra_check = (q_np, q_off.cpu().numpy().astype(np.uint64), q_succ[:q_arcs].cpu().numpy().view(np.uint32))
+            del q_succ, q_ws, ptrs
+        except Exception as e:  # reported, not fatal: the headline metric is the full decode
+            log("random access leg failed:", e)
+
+    # ---- model build as a path (configs[1]: "full decode + model build"): the symbols of the graph, resident in HBM,
+    #      through wga_model_accumulate + wga_model_build (model4encoder_builder.rs:67-271)
+    model_leg = None
+    if want_model_leg and os.path.exists(base + ".symbols.v.npy"):
+        try:
+            comps = np.load(base + ".symbols.c.npy")
+            syms = np.load(base + ".symbols.v.npy")
+            d_c = torch.from_numpy(comps).cuda()
+            d_s = torch.from_numpy(syms.view(np.int64)).cuda()
+            times, hist_ms = [], []
+            for it in range(4):
+                mb = W.ANSModel4EncoderBuilder()
+                torch.cuda.synchronize()
+                m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                m0.record()
+                mb.push_symbols(d_c, d_s)
+                m1.record()
+                mb.build()
+                torch.cuda.synchronize()
+                if it:
+                    times.append(time.perf_counter() - t0)
+                    hist_ms.append(m0.elapsed_time(m1))
+                del mb
+            mt, hm = float(np.median(times)), float(np.median(hist_ms))
+            model_leg = {"symbols": int(syms.size), "ms": mt * 1e3, "Gsymbols_per_s": syms.size / mt / 1e9,
+                         "histogram_ms": hm, "normalise_select_ms": mt * 1e3 - hm,
+                         "roofline": {"bound": "hbm", "kernel": "k_histogram", "algorithmic_bytes": int(9 * syms.size),
+                                      "achieved": 9 * syms.size / (hm * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": 9 * syms.size / (hm * 1e-3) / 1e9 / peak}}
+            if not args.no_cpu_baseline:
+                import oracle_py as Om
+                k = int(min(syms.size, 20_000_000))
+                ogm = Om.OracleGraph()
+                t0 = time.perf_counter()
+                ogm.build_model(comps[:k], syms[:k])
+                ct = time.perf_counter() - t0
+                model_leg["cpu_port"] = {"Gsymbols_per_s": k / ct / 1e9, "cores": 1,
+                                         "sample": f"oracle build() on the first {k} symbols, {ct:.1f}s"}
+            del d_c, d_s, comps, syms
+        except Exception as e:
+            log("model build leg failed:", e)
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D inputs + decode + D2H result
     h_off = torch.empty(n + 1, dtype=torch.int64).pin_memory()
@@ -379,7 +610,7 @@ def main():
     def e2e_step():
         rc = W.lib().wga_upload(g._h, C.c_void_p(0))
         assert rc == 0, W.lib().wga_last_error()
-        rc = W.lib().wga_decode_range_host(g._h, C.c_uint64(0), C.c_uint64(n), C.c_void_p(h_off.data_ptr()),
+        rc = W.lib().wga_decode_range_host(g._h, C.c_uint64(first), C.c_uint64(last), C.c_void_p(h_off.data_ptr()),
                                            C.c_void_p(h_succ.data_ptr()), C.c_uint64(h_succ.numel()), C.byref(got))
         assert rc == 0, W.lib().wga_last_error()
 
@@ -392,41 +623,80 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    # the box's copy floor for these bytes: the same D2H and H2D volumes as plain pinned copies on two streams, all
+    # ranks at the same time
+    barrier()
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    h_in = torch.empty(max(1, h2d), dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(max(1, h2d), dtype=torch.uint8, device="cuda")
+    h_tmp = torch.empty(arcs + 1024, dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+    floor = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_up):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_tmp[:arcs].copy_(succ[:arcs], non_blocking=True)
+        torch.cuda.synchronize()
+        floor.append(time.perf_counter() - t0)
+    floor_s = min(floor[1:])
+    del h_in, d_in, h_tmp
+    te = torch.tensor([e2e_s, floor_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = arcs_all / te.item() / 1e9
+    e2e_value = arcs_all / te[0].item() / 1e9
     e2e = {"value": e2e_value, "unit": "Garcs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": te.item() * 1e3}
+           "ms_per_step": te[0].item() * 1e3, "pcie_floor_ms": te[1].item() * 1e3, "cpu_affinity": affinity}
     clocks = sampler.stop()  # sampled over the timed decode steps, the stage timing and the end-to-end steps
 
-    # ---- verification against the oracle (bit-exact CSR) and CPU baseline, rank 0 only
-    cpu_baseline = None
+    # ---- verification against the oracle (bit-exact CSR).  One rank: element by element.  Sharded: rank 0 decodes the
+    #      whole graph with the oracle and compares every shard by an order-dependent 64-bit checksum, its own shard
+    #      (device result and end-to-end host result) element by element as well.
     verified = None
+    sums = None
+    if strong and not args.no_verify:
+        my_sum = checksum64_cuda(torch, off, succ[:arcs])
+        st = torch.tensor([my_sum & 0x7FFFFFFFFFFFFFFF, my_sum >> 63, first, last], dtype=torch.int64, device="cuda")
+        allst = [torch.zeros_like(st) for _ in range(world)]
+        dist.all_gather(allst, st)
+        sums = [((int(x[1].item()) << 63) | int(x[0].item()), int(x[2].item()), int(x[3].item())) for x in allst]
+    cpu_baseline = None
     if rank == 0:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_py as O
         og = O.OracleGraph.load(base)
         cores = os.cpu_count() or 1
         if not args.no_verify:
             t0 = time.time()
-            d_off = off.cpu().numpy().astype(np.uint64)
-            ref_succ = np.zeros(arcs, np.uint32)
-            og.decode_parallel_into(0, n, cores, d_off, ref_succ)  # raises on any outdegree mismatch
-            ok = bool((h_succ.numpy()[:arcs].view(np.uint32) == ref_succ).all())  # e2e result (host)
-            ok = ok and bool(torch.equal(succ[:arcs].cpu(), torch.from_numpy(ref_succ.view(np.int32))))  # device result
-            ok = ok and bool((h_off.numpy().astype(np.uint64) == d_off).all()) and int(d_off[-1]) == arcs
-            if ok and ra_check is not None:  # random access result == the same lists of the sequential decode
-                qn, qo, qs = ra_check
-                exp_deg = (d_off[qn + 1] - d_off[qn]).astype(np.uint64)
-                ok = bool((np.diff(qo) == exp_deg).all())
-                sample = np.random.default_rng(1).integers(0, qn.size, min(qn.size, 20000))
-                for i in sample:
-                    v = int(qn[i])
-                    if not (qs[int(qo[i]):int(qo[i + 1])] == ref_succ[int(d_off[v]):int(d_off[v + 1])]).all():
-                        ok = False
-                        break
-                ra_gpu["verified_bit_exact"] = ok
+            if world == 1 or not strong:  # (weak scaling: rank 0 checks its own graph)
+                d_off = off.cpu().numpy().astype(np.uint64)
+                ref_succ = np.zeros(arcs, np.uint32)
+                og.decode_parallel_into(first, last, cores, d_off, ref_succ)  # raises on any outdegree mismatch
+                ok = bool((h_succ.numpy()[:arcs].view(np.uint32) == ref_succ).all())  # e2e result (host)
+                ok = ok and bool(torch.equal(succ[:arcs].cpu(), torch.from_numpy(ref_succ.view(np.int32))))  # device result
+                ok = ok and bool((h_off.numpy().astype(np.uint64) == d_off).all()) and int(d_off[-1]) == arcs
+                if ok and ra_check is not None:  # random access result == the same lists of the sequential decode
+                    qn, qo, qs = ra_check
+                    exp_deg = (d_off[qn + 1] - d_off[qn]).astype(np.uint64)
+                    ok = bool((np.diff(qo) == exp_deg).all())
+                    sample = np.random.default_rng(1).integers(0, qn.size, min(qn.size, 20000))
+                    for i in sample:
+                        v = int(qn[i])
+                        if not (qs[int(qo[i]):int(qo[i + 1])] == ref_succ[int(d_off[v]):int(d_off[v + 1])]).all():
+                            ok = False
+                            break
+                    ra_gpu["verified_bit_exact"] = ok
+            else:
+                ok = True
+                for r, (sm, a, b) in enumerate(sums):  # the oracle's own sequential decode of every shard's node range
+                    r_off, r_succ, _ = og.decode_seq(a, b)
+                    r_off = np.asarray(r_off, np.uint64)
+                    ok = ok and checksum64(r_off - r_off[0], r_succ) == sm
+                    if r == 0:
+                        ok = ok and bool((succ[:arcs].cpu().numpy().view(np.uint32) == r_succ).all())
+                        ok = ok and bool((h_succ.numpy()[:arcs].view(np.uint32) == r_succ).all())
+                    del r_off, r_succ
             verified = ok
             log(f"verification vs oracle: {'bit-exact' if ok else 'MISMATCH'} ({time.time() - t0:.1f}s)")
             if not ok:
@@ -448,20 +718,24 @@ def main():
             cpu_baseline["random_access_ns_per_arc"] = rs / max(1, ra) * 1e9
 
     if rank == 0:
+        cfg = config_of(args.workload, N_total, arcs_total)
         line = {"metric": "full-graph decode throughput", "value": value, "unit": "Garcs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": {"workload": args.workload, "nodes_per_gpu": n, "arcs_per_gpu": arcs, "bvcomp": BVCOMP,
-                           "bits_per_link": meta["bits_per_link"], "symbols_per_gpu": meta["symbols"],
-                           "l2": "inputs+outputs (%.2f GB per step) exceed the 126 MB L2; no flush needed" % (b_alg / 1e9),
-                           "sharding": "one independent graph of this shape per rank; shared model from NCCL all-reduced histograms"},
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": cfg,
+                "details": {"bits_per_link": meta["bits_per_link"], "symbols": meta["symbols"],
+                            "l2": "inputs+outputs (%.2f GB per step and rank) exceed the 126 MB L2; no flush needed" % (b_alg / 1e9),
+                            "sharding": ("one graph, contiguous node ranges balanced by stream words; no data-path collective"
+                                         if strong else "one independent graph of this shape per rank"),
+                            "model": "built from histograms all-reduced over NCCL" if world > 1 else "built on one GPU",
+                            "per_rank": per_rank, "n_rank_model_parity_vs_oracle": model_parity},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "random_access": ra_gpu,
-                "gpu_launches": int(launches),
+                "model_build": model_leg, "gpu_launches": int(launches),
                 "clocks": clocks, "verified_bit_exact": verified,
                 "aggregate": {"arcs": arcs_all, "algorithmic_bytes": bytes_all,
                               "achieved_gbs_all_gpus": bytes_all / (ms_max * 1e-3) / 1e9,
                               "frac_of_aggregate_peak": bytes_all / (ms_max * 1e-3) / 1e9 / (peak * world)},
-                "prepare": {k: meta.get(k) for k in ("gen_s", "model_build_s", "encode_s")}}
+                "prepare": {k: meta.get(k) for k in ("gen_s", "model_build_s", "encode_s", "build_ranks")}}
         emit(line)
     if world > 1:
         dist.barrier()

@@ -96,7 +96,12 @@ uint64_t wga_kernel_launches(void);
 /* ---------------------------------------------------------------- load -------------------------- */
 #define WGA_OPEN_DEFAULT 0
 #define WGA_OPEN_HOST_ONLY 1 /* parse files, keep host copies, do not touch the GPU (format tests) */
-/* Loads <basename>.ans/.pointers/.states (ANSBvGraph::load) and uploads to the current CUDA device. */
+#define WGA_OPEN_SEQUENTIAL 2 /* ANSBvGraphSeq::load (src/bvgraph/sequential.rs:29-51): the .ans alone is enough. When
+                                 .pointers and .states are both absent, the per-node phases are recovered at load time by
+                                 one walk of the stream from (stream.len(), prelude.state), as
+                                 bvgraphseq_decoder_factory.rs:29-35 starts it */
+/* Loads <basename>.ans/.pointers/.states (ANSBvGraph::load, src/bvgraph/random_access.rs:52-82) and uploads to the
+ * current CUDA device. */
 int wga_open(const char* basename, int flags, wga_graph** out);
 /* Same from host arrays (copied). */
 int wga_open_mem(const wga_prelude_view* view, int flags, wga_graph** out);
@@ -142,6 +147,9 @@ int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t*
  * in node-range chunks on a stream of the handle; the next wga_decode_range_host overlaps with it. */
 int wga_upload(wga_graph* g, void* stream);
 uint64_t wga_upload_bytes(const wga_graph* g);
+/* Predecessor nodes the last wga_decode_range decoded in addition to its range, to resolve the references that leave
+ * it on the left (0 when it started at the first resident node). */
+uint64_t wga_last_halo_nodes(const wga_graph* g);
 /* Per-stage device times of the last wga_decode_range (CUDA events on the caller's stream):
  * [outdegrees+scan, entropy decode (K1), levels+sort, resolve per level (K2)].
  * Returns the number of events. */
@@ -212,6 +220,13 @@ int wga_bvcomp_symbols(const uint64_t* h_offsets, const uint32_t* h_succ, uint64
                        uint64_t compression_window, uint64_t max_ref_count, uint64_t min_interval_length,
                        const wga_component_model* estimator_tables, uint64_t chunk_nodes, int threads,
                        wga_symbols** out);
+/* Same for nodes [first_node, first_node + n_nodes) only: the CSR arrays hold just these nodes (successor ids stay
+ * global).  With chunk_nodes > 0 the chunks are those of the whole-graph call, so a rank of a sharded model build
+ * gets exactly the whole graph's symbols of its node range (first_node a multiple of chunk_nodes). */
+int wga_bvcomp_symbols_range(const uint64_t* h_offsets, const uint32_t* h_succ, uint64_t first_node, uint64_t n_nodes,
+                             uint64_t compression_window, uint64_t max_ref_count, uint64_t min_interval_length,
+                             const wga_component_model* estimator_tables, uint64_t chunk_nodes, int threads,
+                             wga_symbols** out);
 uint64_t wga_symbols_len(const wga_symbols* s);
 const uint8_t* wga_symbols_components(const wga_symbols* s);
 const uint64_t* wga_symbols_values(const wga_symbols* s);

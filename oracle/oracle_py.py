@@ -79,6 +79,31 @@ def read_bvgraph(basename):
     return off, succ, bits
 
 
+def synth_graph(kind, n_nodes, mean_degree, seed, first=0, last=None, threads=None):
+    """Synthetic benchmark graph (tools/synth/synth_graph.hpp) -> (offsets u64, successors u32) of nodes [first,last)."""
+    last = n_nodes if last is None else last
+    threads = threads or (os.cpu_count() or 1)
+    k = {"web": 0, "social": 1}.get(kind, kind)
+    arcs = C.c_uint64(0)
+    off = np.zeros(last - first + 1, np.uint64)
+    _chk(lib().wgo_synth_graph(k, C.c_uint64(n_nodes), C.c_double(mean_degree), C.c_uint64(seed), C.c_uint64(first),
+                               C.c_uint64(last), C.c_int(threads), _p(off), None, C.byref(arcs)))
+    succ = np.zeros(max(arcs.value, 1), np.uint32)
+    _chk(lib().wgo_synth_graph(k, C.c_uint64(n_nodes), C.c_double(mean_degree), C.c_uint64(seed), C.c_uint64(first),
+                               C.c_uint64(last), C.c_int(threads), _p(off), _p(succ), C.byref(arcs)))
+    return off, succ[:arcs.value]
+
+
+def synth_degrees(kind, n_nodes, mean_degree, seed, threads=None):
+    """Number of arcs of a synthetic benchmark graph (degrees only)."""
+    threads = threads or (os.cpu_count() or 1)
+    k = {"web": 0, "social": 1}.get(kind, kind)
+    arcs = C.c_uint64(0)
+    _chk(lib().wgo_synth_graph(k, C.c_uint64(n_nodes), C.c_double(mean_degree), C.c_uint64(seed), C.c_uint64(0),
+                               C.c_uint64(n_nodes), C.c_int(threads), None, None, C.byref(arcs)))
+    return arcs.value
+
+
 class OracleGraph:
     """An ANS graph (Prelude + phases) held by the oracle."""
 

@@ -9,6 +9,7 @@
 #include <thread>
 #include <unordered_map>
 
+#include "../tools/synth/synth_graph.hpp"
 #include "wgo_io.hpp"
 
 using namespace wgo;
@@ -392,6 +393,20 @@ int64_t wgo_ef_read(const char* path, uint64_t* out, uint64_t cap) {
     n = (int64_t)v.size();
   });
   return n;
+}
+
+// Synthetic benchmark graphs (tools/synth/synth_graph.hpp: workload infrastructure, shared with the product's test
+// API) so that bench.py --impl reference builds its inputs without loading the product library.
+int wgo_synth_graph(int kind, uint64_t n_nodes, double mean_degree, uint64_t seed, uint64_t first, uint64_t last,
+                    int threads, uint64_t* offsets, uint32_t* succ, uint64_t* n_arcs) {
+  try {
+    uint64_t a = wgsynth::synth_graph(kind, n_nodes, mean_degree, seed, first, last, threads, offsets, succ);
+    if (n_arcs) *n_arcs = a;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
 }
 
 }  // extern "C"

@@ -32,6 +32,15 @@ def test_golden_head_full_decode(W, O, gpu, head):
     assert (off2 == head["offsets"]).all() and (succ2 == head["succ"]).all()
 
 
+def test_sequential_load_from_ans_alone_decodes_bit_exact(W, O, gpu, head, tmp_path):
+    """ANSBvGraphSeq::load + iterate with only the .ans present (sequential.rs:29-51)."""
+    import shutil
+    shutil.copy(head["base"] + ".ans", tmp_path / "only.ans")
+    g = W.ANSBvGraphSeq.load(str(tmp_path / "only"))
+    off, succ = gpu_csr(g)
+    assert (off == head["offsets"]).all() and (succ == head["succ"]).all()
+
+
 def test_host_entry_point_pipelined_in_chunks(W, O, gpu, head):
     """wga_upload(NULL) + wga_decode_range_host with small chunks: upload / decode / download overlap on three
     streams with double-buffered chunk outputs; result identical to the one-shot decode."""
@@ -278,6 +287,53 @@ def test_synthetic_shapes_roundtrip(W, O, gpu, kind, n, deg):
     assert (d_off == off).all() and (d_succ == succ).all()
     o_off, o_succ, end = og.decode_seq()
     assert (o_succ == d_succ).all() and end == (0, 65536)
+
+
+def test_output_buffer_too_small_is_reported_and_nothing_is_written_behind_it(W, O, gpu):
+    """A d_succ (or a sub-range halo) smaller than the decoded arcs: WGA_E_WORKSPACE, and no kernel writes past the
+    capacity it was given (guard words behind it stay intact)."""
+    import ctypes as C
+    import torch
+    off, succ = make_case(20000, 12, 91)
+    og = O.OracleGraph.store_csr(off, succ, 7, 3, 4)
+    g = open_oracle_graph(W, og)
+    arcs = succ.size
+    for first, last, cap in ((0, 20000, arcs // 2), (0, 20000, 7), (5000, 15000, 100), (0, 20000, arcs - 1)):
+        d_off = torch.zeros(last - first + 1, dtype=torch.int64, device="cuda")
+        d_succ = torch.full((arcs + 4096,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+        ws = torch.zeros(g.workspace_size(first, last), dtype=torch.uint8, device="cuda")
+        rc = W.lib().wga_decode_range(g._h, C.c_uint64(first), C.c_uint64(last), C.c_void_p(d_off.data_ptr()),
+                                      C.c_void_p(d_succ.data_ptr()), C.c_uint64(cap), C.c_void_p(ws.data_ptr()),
+                                      C.c_uint64(ws.numel()), None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert rc == -6, (first, last, cap, rc)
+        assert b"need" in W.lib().wga_last_error()
+        assert bool((d_succ[cap:] == 0x5A5A5A5A).all()), (first, last, cap)
+    # the handle is still usable
+    d_off, d_succ = gpu_csr(g)
+    assert (d_succ == succ).all()
+
+
+def test_host_entry_point_survives_a_chunk_much_denser_than_the_average(W, O, gpu):
+    """wga_decode_range_host sizes its chunk buffers from the average degree; a chunk with many more arcs is
+    retried with larger buffers instead of failing."""
+    rng = np.random.default_rng(17)
+    n_sparse, n_dense, deg = 150_000, 9_000, 520
+    lists = [np.array([(v * 7 + 1) % (n_sparse + n_dense)], np.uint32) for v in range(n_sparse)]
+    n = n_sparse + n_dense
+    for v in range(n_dense):
+        lists.append(np.unique(rng.integers(0, n, deg)).astype(np.uint32))
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum([x.size for x in lists])
+    succ = np.concatenate(lists)
+    og = O.OracleGraph.store_csr(off, succ, 7, 3, 4)
+    g = open_oracle_graph(W, og)
+    try:
+        W.set_tuning(e2e_chunk=10_000)
+        h_off, h_succ = g.decode_range_host()
+    finally:
+        W.set_tuning(reset=1)
+    assert (h_off == off).all() and (h_succ == succ).all()
 
 
 def test_corrupt_stream_is_reported_not_faulted(W, O, gpu):

@@ -78,6 +78,19 @@ def test_packed_tables_equal_reference_decoder_tables_on_host(W, O, head):
             assert (ours[f] == ref[f]).all(), (c, f)
 
 
+def test_sequential_load_needs_only_the_ans_file(W, head, tmp_path):
+    """ANSBvGraphSeq::load (sequential.rs:29-51): with .pointers and .states deleted, the phases recovered by the
+    load-time walk of the stream equal the stored ones."""
+    import shutil
+    shutil.copy(head["base"] + ".ans", tmp_path / "only.ans")
+    g = W.ANSBvGraphSeq.load(str(tmp_path / "only"), host_only=True)
+    ref = W.ANSBvGraph.load(head["base"], host_only=True).prelude()
+    p = g.prelude()
+    assert (p["states"] == ref["states"]).all() and (p["pointers"] == ref["pointers"]).all()
+    with pytest.raises(W.WgaError):  # the random-access loader still needs all three files (random_access.rs:52-82)
+        W.ANSBvGraph.load(str(tmp_path / "only"), host_only=True)
+
+
 def test_files_roundtrip_through_oracle_reader(W, O, tmp_path):
     """What the product writes, the oracle's independent epserde/Elias-Fano reader reads back."""
     rng = np.random.default_rng(3)

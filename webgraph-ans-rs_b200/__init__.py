@@ -57,7 +57,8 @@ def lib():
         L.wga_last_error.restype = C.c_char_p
         for name in ("wga_num_nodes", "wga_num_arcs", "wga_window", "wga_min_interval_length", "wga_stream_len",
                      "wga_compressed_bytes", "wga_decode_workspace_size", "wga_successors_workspace_size",
-                     "wga_kernel_launches", "wga_symbols_len", "wga_model_sparse_count", "wga_upload_bytes"):
+                     "wga_kernel_launches", "wga_symbols_len", "wga_model_sparse_count", "wga_upload_bytes",
+                     "wga_last_halo_nodes"):
             getattr(L, name).restype = C.c_uint64
         L.wga_model_bins.restype = C.c_void_p
         L.wga_symbols_components.restype = C.c_void_p
@@ -393,12 +394,13 @@ class ANSBvGraph:
 
 
 class ANSBvGraphSeq:
-    """src/bvgraph/sequential.rs:21.  The GPU decoder starts every node from its phase, so it needs
-    the .pointers/.states files next to the .ans as well."""
+    """src/bvgraph/sequential.rs:21.  Only the .ans is required, as in the reference: when .pointers / .states
+    are absent the per-node phases the GPU decoder starts from are recovered at load time by one walk of the
+    stream (WGA_OPEN_SEQUENTIAL)."""
 
     @staticmethod
-    def load(basename):
-        return _open(basename)
+    def load(basename, host_only=False):
+        return _open(basename, 2 | (1 if host_only else 0))
 
 
 class ANSModel4EncoderBuilder:
@@ -477,17 +479,19 @@ class ANSModel4EncoderBuilder:
 
 # ---- host front end pieces (bvcomp) ---------------------------------------------------------------
 def bvcomp_symbols(offsets, succ, compression_window=7, max_ref_count=3, min_interval_length=4,
-                   estimator_tables=None, chunk_nodes=0, threads=1):
+                   estimator_tables=None, chunk_nodes=0, threads=1, first_node=0):
     """(components u8, symbols u64) that BvComp writes for a CSR graph, choosing references with the
-    Log2Estimator (estimator_tables=None) or the EntropyEstimator built from the given tables."""
+    Log2Estimator (estimator_tables=None) or the EntropyEstimator built from the given tables.
+    first_node > 0: the CSR holds nodes [first_node, first_node + n) of a larger graph (one rank's share)."""
     offsets = np.ascontiguousarray(offsets, np.uint64)
     succ = np.ascontiguousarray(succ, np.uint32)
     keep = []
     est = _tables_to_view(estimator_tables, keep) if estimator_tables is not None else None
     h = C.c_void_p()
-    _chk(lib().wga_bvcomp_symbols(_np(offsets), _np(succ), C.c_uint64(offsets.size - 1), C.c_uint64(compression_window),
-                                  C.c_uint64(max_ref_count), C.c_uint64(min_interval_length), est,
-                                  C.c_uint64(chunk_nodes), C.c_int(threads), C.byref(h)))
+    _chk(lib().wga_bvcomp_symbols_range(_np(offsets), _np(succ), C.c_uint64(first_node), C.c_uint64(offsets.size - 1),
+                                        C.c_uint64(compression_window), C.c_uint64(max_ref_count),
+                                        C.c_uint64(min_interval_length), est, C.c_uint64(chunk_nodes), C.c_int(threads),
+                                        C.byref(h)))
     n = int(lib().wga_symbols_len(h))
     comps = np.zeros(n, np.uint8)
     vals = np.zeros(n, np.uint64)

@@ -178,8 +178,16 @@ uint64_t bvcomp_range(const NodeSource& src, uint64_t first, uint64_t last, cons
 
 uint64_t bvcomp_graph(const NodeSource& src, uint64_t n_nodes, const BvCompParams& p, const Estimator& est,
                       uint64_t chunk_nodes, int threads, SymbolStream& out) {
-  if (chunk_nodes == 0 || chunk_nodes >= n_nodes) return bvcomp_range(src, 0, n_nodes, p, est, out);
-  const uint64_t n_chunks = (n_nodes + chunk_nodes - 1) / chunk_nodes;
+  return bvcomp_nodes(src, 0, n_nodes, p, est, chunk_nodes, threads, out);
+}
+
+uint64_t bvcomp_nodes(const NodeSource& src, uint64_t first, uint64_t last, const BvCompParams& p, const Estimator& est,
+                      uint64_t chunk_nodes, int threads, SymbolStream& out) {
+  if (chunk_nodes == 0) return bvcomp_range(src, first, last, p, est, out);
+  // chunks are aligned to multiples of chunk_nodes of the WHOLE graph, so that a node range compressed by one
+  // rank gives the symbols the whole-graph run gives for those nodes
+  const uint64_t c0 = first / chunk_nodes, c1 = (last + chunk_nodes - 1) / chunk_nodes;
+  const uint64_t n_chunks = c1 > c0 ? c1 - c0 : 0;
   if (threads < 1) threads = 1;
   std::vector<SymbolStream> parts(n_chunks);
   std::vector<uint64_t> arcs(n_chunks, 0);
@@ -190,7 +198,7 @@ uint64_t bvcomp_graph(const NodeSource& src, uint64_t n_nodes, const BvCompParam
     pool.emplace_back([&, t] {
       try {
         for (uint64_t c = next.fetch_add(1); c < n_chunks; c = next.fetch_add(1)) {
-          uint64_t a = c * chunk_nodes, b = std::min(n_nodes, a + chunk_nodes);
+          uint64_t a = std::max(first, (c0 + c) * chunk_nodes), b = std::min(last, (c0 + c + 1) * chunk_nodes);
           arcs[c] = bvcomp_range(src, a, b, p, est, parts[c]);
         }
       } catch (const std::exception& e) {

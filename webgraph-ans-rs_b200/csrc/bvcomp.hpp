@@ -62,6 +62,10 @@ uint64_t bvcomp_range(const NodeSource& src, uint64_t first, uint64_t last, cons
 // independent chunks on `threads` host threads, concatenated in node order.
 uint64_t bvcomp_graph(const NodeSource& src, uint64_t n_nodes, const BvCompParams& p, const Estimator& est,
                       uint64_t chunk_nodes, int threads, SymbolStream& out);
+// Nodes [first,last) of the graph only (one rank's share of a sharded model build): with chunk_nodes > 0 the
+// chunks are those of the whole-graph run, so the symbols equal its symbols for these nodes.
+uint64_t bvcomp_nodes(const NodeSource& src, uint64_t first, uint64_t last, const BvCompParams& p, const Estimator& est,
+                      uint64_t chunk_nodes, int threads, SymbolStream& out);
 
 struct EncodeResult {
   std::vector<uint16_t> stream;

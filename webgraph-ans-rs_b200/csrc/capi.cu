@@ -47,6 +47,11 @@ static wga_graph* finish_open(std::unique_ptr<wga_graph> g, uint64_t first, uint
 }
 
 static std::string with_ext(const char* basename, const char* ext) { return std::string(basename) + "." + ext; }
+static bool file_exists(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (f) fclose(f);
+  return f != nullptr;
+}
 
 // ANSBvGraph::store on a node source (random_access.rs:91-222): pass 1 Log2Estimator -> model1,
 // pass 2 EntropyEstimator(model1) -> model2, pass 3 encodes the pass-2 symbols (same estimator, :166-168)
@@ -113,10 +118,19 @@ int wga_open(const char* basename, int flags, wga_graph** out) {
     if (!basename || !out) throw Error(WGA_E_ARG, "null argument");
     std::unique_ptr<wga_graph> g(new wga_graph());
     load_prelude(with_ext(basename, "ans"), g->prelude);  // random_access.rs:58-59
-    EliasFano ef = EliasFano::deserialize(read_whole_file(with_ext(basename, "pointers")));  // :62-63
-    ef.expand(g->phases.pointers);
-    g->pointers_payload_bytes = ef.payload_bytes();
-    load_states(with_ext(basename, "states"), g->phases.states);  // :66-67
+    if ((flags & WGA_OPEN_SEQUENTIAL) && !file_exists(with_ext(basename, "pointers")) &&
+        !file_exists(with_ext(basename, "states"))) {
+      // ANSBvGraphSeq::load (sequential.rs:29-51): only the .ans exists; the phases come from one walk of the stream
+      bootstrap_phases(g->prelude, pack_tables(g->prelude.tables), g->phases);
+      const uint64_t n = g->prelude.number_of_nodes, u = n ? g->phases.pointers.back() + 1 : 1;
+      const uint64_t l = (n && u >= n) ? (uint64_t)(63 - __builtin_clzll(u / n)) : 0;
+      g->pointers_payload_bytes = (n * l + 7) / 8 + (n + (u >> l) + 1 + 7) / 8;
+    } else {
+      EliasFano ef = EliasFano::deserialize(read_whole_file(with_ext(basename, "pointers")));  // :62-63
+      ef.expand(g->phases.pointers);
+      g->pointers_payload_bytes = ef.payload_bytes();
+      load_states(with_ext(basename, "states"), g->phases.states);  // :66-67
+    }
     uint64_t n = g->prelude.number_of_nodes;
     *out = finish_open(std::move(g), 0, n, flags);
   });
@@ -229,55 +243,80 @@ static void decode_range_host_pipelined(wga_graph* g, uint64_t first, uint64_t l
   const uint64_t CH = g->e2e_chunk_nodes;
   const uint64_t N = g->prelude.number_of_nodes;
   const double avg = N ? (double)g->prelude.number_of_arcs / (double)N : 0.0;
-  const uint64_t chunk_cap = (uint64_t)(avg * (double)CH * 1.5) + (4u << 20);
-  const uint64_t ws_bytes = decode_workspace_size(g, 0, CH) + 8 * chunk_cap;  // arena sized for the chunk buffer
-  if (g->e2e_ws_bytes < ws_bytes) {
-    if (g->e2e_ws) cudaFree(g->e2e_ws);
-    g->e2e_ws = nullptr; g->e2e_ws_bytes = 0;
-    WGA_CUDA(cudaMalloc(&g->e2e_ws, ws_bytes));
-    g->e2e_ws_bytes = ws_bytes;
-  }
-  if (g->pipe_off_n < CH + 1 || g->pipe_succ_n < chunk_cap) {
-    for (int i = 0; i < 2; ++i) {
-      if (g->pipe_off[i]) cudaFree(g->pipe_off[i]);
-      if (g->pipe_succ[i]) cudaFree(g->pipe_succ[i]);
-      g->pipe_off[i] = nullptr; g->pipe_succ[i] = nullptr;
+  // first guess of a chunk's arcs; a denser chunk makes its decode fail with "need N" and is retried with larger buffers
+  uint64_t chunk_cap = std::max<uint64_t>(g->pipe_succ_n, (uint64_t)(avg * (double)CH * 1.5) + (4u << 20));
+  auto ensure_buffers = [&](uint64_t cap) {
+    const uint64_t ws_bytes = decode_workspace_size(g, 0, CH) + 8 * cap;  // record buffer sized for the chunk buffer
+    if (g->e2e_ws_bytes < ws_bytes) {
+      if (g->e2e_ws) cudaFree(g->e2e_ws);
+      g->e2e_ws = nullptr; g->e2e_ws_bytes = 0;
+      WGA_CUDA(cudaMalloc(&g->e2e_ws, ws_bytes));
+      g->e2e_ws_bytes = ws_bytes;
     }
-    g->pipe_off_n = g->pipe_succ_n = 0;
-    for (int i = 0; i < 2; ++i) {
-      WGA_CUDA(cudaMalloc((void**)&g->pipe_off[i], (CH + 1) * 8));
-      WGA_CUDA(cudaMalloc((void**)&g->pipe_succ[i], chunk_cap * 4));
+    if (g->pipe_off_n < CH + 1 || g->pipe_succ_n < cap) {
+      for (int i = 0; i < 2; ++i) {
+        if (g->pipe_off[i]) cudaFree(g->pipe_off[i]);
+        if (g->pipe_succ[i]) cudaFree(g->pipe_succ[i]);
+        g->pipe_off[i] = nullptr; g->pipe_succ[i] = nullptr;
+      }
+      g->pipe_off_n = g->pipe_succ_n = 0;
+      for (int i = 0; i < 2; ++i) {
+        WGA_CUDA(cudaMalloc((void**)&g->pipe_off[i], (CH + 1) * 8));
+        WGA_CUDA(cudaMalloc((void**)&g->pipe_succ[i], cap * 4));
+      }
+      g->pipe_off_n = CH + 1; g->pipe_succ_n = cap;
     }
-    g->pipe_off_n = CH + 1; g->pipe_succ_n = chunk_cap;
-  }
-  uint64_t base = 0;
-  int i = 0;
-  for (uint64_t a = first; a < last; a += CH, ++i) {
-    const uint64_t b = std::min(last, a + CH);
-    const int j = i & 1;
-    if (g->up_pending) {  // inputs of this chunk (and of the halo just before it) must have arrived
-      const uint64_t c1 = (b - 1 - g->res_first) / CH, c0 = a > g->res_first ? (a - 1 - g->res_first) / CH : 0;
-      for (uint64_t c = c0; c <= c1 && c < g->up_ev.size(); ++c) WGA_CUDA(cudaStreamWaitEvent(g->s_dec, g->up_ev[c], 0));
+  };
+  ensure_buffers(chunk_cap);
+  auto drain = [&]() {  // nothing of this call may still be in flight when it returns, also on errors
+    cudaStreamSynchronize(g->s_dec);
+    cudaStreamSynchronize(g->s_down);
+    g->up_pending = false;
+  };
+  try {
+    uint64_t base = 0;
+    int i = 0;
+    for (uint64_t a = first; a < last; a += CH, ++i) {
+      const uint64_t b = std::min(last, a + CH);
+      const int j = i & 1;
+      if (g->up_pending) {  // inputs of this chunk (and of the halo just before it) must have arrived
+        const uint64_t c1 = (b - 1 - g->res_first) / CH, c0 = a > g->res_first ? (a - 1 - g->res_first) / CH : 0;
+        for (uint64_t c = c0; c <= c1 && c < g->up_ev.size(); ++c) WGA_CUDA(cudaStreamWaitEvent(g->s_dec, g->up_ev[c], 0));
+      }
+      if (i >= 2) WGA_CUDA(cudaStreamWaitEvent(g->s_dec, g->down_done[j], 0));  // buffer j is free again
+      uint64_t arcs = 0;
+      for (int attempt = 0;; ++attempt) {
+        try {
+          decode_range(g, a, b, g->pipe_off[j], g->pipe_succ[j], g->pipe_succ_n, g->e2e_ws, g->e2e_ws_bytes, &arcs, g->s_dec);
+          break;
+        } catch (const Error& e) {
+          if (e.code != WGA_E_WORKSPACE || attempt >= 2) throw;
+          // a chunk denser than the guess: both chunk buffers must be idle before they are replaced
+          WGA_CUDA(cudaStreamSynchronize(g->s_dec));
+          WGA_CUDA(cudaStreamSynchronize(g->s_down));
+          ensure_buffers(std::max<uint64_t>(2 * g->pipe_succ_n, g->last_need_succ + (1u << 20)));
+        }
+      }
+      if (base + arcs > succ_capacity && h_succ)
+        throw Error(WGA_E_WORKSPACE, "h_succ too small: need more than " + std::to_string(base + arcs) + " elements");
+      launch_offsets_add(g->pipe_off[j], b - a + 1, base, g->s_dec);
+      WGA_CUDA(cudaEventRecord(g->dec_done[j], g->s_dec));
+      WGA_CUDA(cudaStreamWaitEvent(g->s_down, g->dec_done[j], 0));
+      // offsets: the last entry of a chunk equals the first of the next one
+      WGA_CUDA(cudaMemcpyAsync(h_offsets + (a - first), g->pipe_off[j], (b - a + (b == last ? 1 : 0)) * 8,
+                               cudaMemcpyDeviceToHost, g->s_down));
+      if (arcs && h_succ)
+        WGA_CUDA(cudaMemcpyAsync(h_succ + base, g->pipe_succ[j], arcs * 4, cudaMemcpyDeviceToHost, g->s_down));
+      WGA_CUDA(cudaEventRecord(g->down_done[j], g->s_down));
+      base += arcs;
     }
-    if (i >= 2) WGA_CUDA(cudaStreamWaitEvent(g->s_dec, g->down_done[j], 0));  // buffer j is free again
-    uint64_t arcs = 0;
-    decode_range(g, a, b, g->pipe_off[j], g->pipe_succ[j], g->pipe_succ_n, g->e2e_ws, g->e2e_ws_bytes, &arcs, g->s_dec);
-    if (base + arcs > succ_capacity && h_succ)
-      throw Error(WGA_E_WORKSPACE, "h_succ too small: need more than " + std::to_string(base + arcs) + " elements");
-    launch_offsets_add(g->pipe_off[j], b - a + 1, base, g->s_dec);
-    WGA_CUDA(cudaEventRecord(g->dec_done[j], g->s_dec));
-    WGA_CUDA(cudaStreamWaitEvent(g->s_down, g->dec_done[j], 0));
-    // offsets: the last entry of a chunk equals the first of the next one
-    WGA_CUDA(cudaMemcpyAsync(h_offsets + (a - first), g->pipe_off[j], (b - a + (b == last ? 1 : 0)) * 8,
-                             cudaMemcpyDeviceToHost, g->s_down));
-    if (arcs && h_succ)
-      WGA_CUDA(cudaMemcpyAsync(h_succ + base, g->pipe_succ[j], arcs * 4, cudaMemcpyDeviceToHost, g->s_down));
-    WGA_CUDA(cudaEventRecord(g->down_done[j], g->s_down));
-    base += arcs;
+    WGA_CUDA(cudaStreamSynchronize(g->s_down));
+    g->up_pending = false;
+    if (h_arcs) *h_arcs = base;
+  } catch (...) {
+    drain();
+    throw;
   }
-  WGA_CUDA(cudaStreamSynchronize(g->s_down));
-  g->up_pending = false;
-  if (h_arcs) *h_arcs = base;
 }
 
 int wga_decode_range_host(wga_graph* g, uint64_t first, uint64_t last, uint64_t* h_offsets, uint32_t* h_succ,
@@ -342,6 +381,8 @@ uint64_t wga_upload_bytes(const wga_graph* g) {
   uint64_t n = g->res_last - g->res_first;
   return 2 * g->stream_words + 4 * n + 8 * n;
 }
+
+uint64_t wga_last_halo_nodes(const wga_graph* g) { return g ? g->last_halo_nodes : 0; }
 
 int wga_set_profiling(wga_graph* g, int on) {
   if (!g) return WGA_E_ARG;
@@ -435,27 +476,35 @@ int wga_model_build(wga_model* m, wga_component_model out_tables[WGA_COMPONENTS]
 }
 
 // ---------------------------------------------------------------------------------------- bvcomp
-int wga_bvcomp_symbols(const uint64_t* h_offsets, const uint32_t* h_succ, uint64_t n_nodes,
-                       uint64_t compression_window, uint64_t max_ref_count, uint64_t min_interval_length,
-                       const wga_component_model* estimator_tables, uint64_t chunk_nodes, int threads,
-                       wga_symbols** out) {
+int wga_bvcomp_symbols_range(const uint64_t* h_offsets, const uint32_t* h_succ, uint64_t first_node, uint64_t n_nodes,
+                             uint64_t compression_window, uint64_t max_ref_count, uint64_t min_interval_length,
+                             const wga_component_model* estimator_tables, uint64_t chunk_nodes, int threads,
+                             wga_symbols** out) {
   return guarded([&] {
     if (!h_offsets || !out) throw Error(WGA_E_ARG, "null argument");
     BvCompParams p{compression_window, max_ref_count, min_interval_length};
     std::unique_ptr<wga_symbols> s(new wga_symbols());
+    // the CSR arrays hold nodes [first_node, first_node + n_nodes) only; successor ids are global
     NodeSource src = [&](uint64_t v, std::vector<uint64_t>& o) {
-      o.assign(h_succ + h_offsets[v], h_succ + h_offsets[v + 1]);
+      o.assign(h_succ + h_offsets[v - first_node], h_succ + h_offsets[v - first_node + 1]);
     };
     if (estimator_tables) {
       ComponentModel m[WGA_COMPONENTS];
       view_to_models(estimator_tables, m);
       Estimator est(m);
-      bvcomp_graph(src, n_nodes, p, est, chunk_nodes, threads, s->s);
+      bvcomp_nodes(src, first_node, first_node + n_nodes, p, est, chunk_nodes, threads, s->s);
     } else {
-      bvcomp_graph(src, n_nodes, p, Estimator(), chunk_nodes, threads, s->s);
+      bvcomp_nodes(src, first_node, first_node + n_nodes, p, Estimator(), chunk_nodes, threads, s->s);
     }
     *out = s.release();
   });
+}
+int wga_bvcomp_symbols(const uint64_t* h_offsets, const uint32_t* h_succ, uint64_t n_nodes,
+                       uint64_t compression_window, uint64_t max_ref_count, uint64_t min_interval_length,
+                       const wga_component_model* estimator_tables, uint64_t chunk_nodes, int threads,
+                       wga_symbols** out) {
+  return wga_bvcomp_symbols_range(h_offsets, h_succ, 0, n_nodes, compression_window, max_ref_count, min_interval_length,
+                                  estimator_tables, chunk_nodes, threads, out);
 }
 uint64_t wga_symbols_len(const wga_symbols* s) { return s->s.size(); }
 const uint8_t* wga_symbols_components(const wga_symbols* s) { return s->s.comps.data(); }

@@ -593,13 +593,13 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
           // heads of the three runs
           p = 0;
           rj = 0;
-          rval = nres ? res[0] : INF;
+          rval = (nres && d != 0) ? res[0] : INF;
           ival = INF;
           if (ni) { ival = hp[ip]; ilim = ival + hp[ip + 1]; ip += 2; }
           cval = INF;
           ci = cend = 0;
           kb = 0;
-          if (rt) {
+          if (rt && d != 0) {  // (d == 0: nothing to do, or the node / its reference does not fit the output buffer)
             cend = b ? min(hp[0], dref) : dref;
             if (ci < cend) cval = ref[0]; else next_copy_block();  // (only the first block can be empty)
           }
@@ -1003,6 +1003,7 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
     throw Error(WGA_E_WORKSPACE, "halo successors exceed the workspace");
   }
   if (tot[1] - tot[0] > rv.succ_cap) {
+    g->last_need_succ = tot[1] - tot[0];
     if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
     throw Error(WGA_E_WORKSPACE, "d_succ too small: need " + std::to_string(tot[1] - tot[0]) + " elements");
   }
@@ -1077,6 +1078,7 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     lo = g->h_pub[0];
     if (lo < g->res_first) throw Error(WGA_E_ARG, "reference chain leaves the resident shard");
   }
+  g->last_halo_nodes = first - lo;
   const uint64_t n = last - lo;
   const uint32_t unit = effective_unit(tn);
   WorkspacePlan p = plan_workspace(n);

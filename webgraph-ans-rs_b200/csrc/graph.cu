@@ -75,6 +75,102 @@ PackedTablesData pack_tables(const ComponentModel tables[WGA_COMPONENTS]) {
   return p;
 }
 
+// ---- sequential bootstrap: phases from the .ans alone -----------------------------------------------------
+// ANSBvGraphSeq::load needs only the .ans (src/bvgraph/sequential.rs:29-51): its decoder starts at
+// (stream.len(), prelude.state) (bvgraphseq_decoder_factory.rs:29-35) and walks the one ANS state chain node by
+// node.  The GPU decode starts every node from its own phase, so when .pointers / .states are missing the phases
+// are recovered here, at load time, by the same walk: every symbol of every record is decoded once in record order
+// (host, serial by construction of the format) and the decoder (state, pointer) is noted before each node.
+namespace {
+struct HostDecoder {
+  const PackedTablesData& p;
+  const uint16_t* stream;
+  uint64_t ptr;
+  uint32_t state;
+  bool ok = true;
+  void extend() {  // decoder.rs:89-93
+    if (ptr == 0) { ok = false; return; }
+    --ptr;
+    state = (state << 16) | stream[ptr];
+  }
+  uint64_t decode(int c) {  // decoder.rs:58-87 on the packed tables (same lookup as the device code)
+    const uint32_t L = p.L[c], R = p.R[c];
+    const uint32_t slot = state & ((1u << L) - 1u);
+    const Bkt& bk = p.bkt[p.bkt_off[c] + (slot >> 5)];
+    const uint32_t j = bk.j0 + (uint32_t)__builtin_popcount(bk.mask & ((2u << (slot & 31u)) - 1u));
+    const Ent& e = p.ent[p.ent_off[c] + j];
+    const uint32_t folds = e.bf >> 16;
+    if (folds == 0xFFFFu) { ok = false; return 0; }
+    state = (state >> L) * (e.cf >> 16) + slot - (e.cf & 0xFFFFu);
+    if (state < WGA_LOWER_BOUND) extend();
+    uint64_t fold = 0;
+    for (uint32_t f = 0; f < folds && ok; ++f) {  // decoder.rs:74-85, one trip per fold
+      if (state < WGA_LOWER_BOUND) extend();
+      fold = (fold << R) | (state & ((1u << R) - 1u));
+      state >>= R;
+      if (state < WGA_LOWER_BOUND) extend();
+    }
+    return ((uint64_t)(e.bf & 0xFFFFu) << (folds * R)) | fold;
+  }
+};
+}  // namespace
+
+void bootstrap_phases(const Prelude& pre, const PackedTablesData& pk, Phases& out) {
+  const uint64_t N = pre.number_of_nodes;
+  const uint64_t window = pre.compression_window, minint = pre.min_interval_length;
+  out.states.assign(N, 0);
+  out.pointers.assign(N, 0);
+  std::vector<uint64_t> outdeg(N, 0);
+  HostDecoder dec{pk, pre.stream.data(), pre.stream.size(), pre.state};
+  auto fail = [&](uint64_t v) { throw Error(WGA_E_CORRUPT, "sequential bootstrap: inconsistent stream at node " + std::to_string(v)); };
+  for (uint64_t v = 0; v < N; ++v) {
+    // file order: entry i belongs to node N-1-i (random_access.rs:202, 225-231)
+    out.states[N - 1 - v] = dec.state;
+    out.pointers[N - 1 - v] = dec.ptr;
+    const uint64_t d = dec.decode(Outdegree);
+    if (!dec.ok) fail(v);
+    outdeg[v] = d;
+    if (d == 0) continue;
+    uint64_t extras = d;
+    if (window != 0) {
+      const uint64_t r = dec.decode(ReferenceOffset);
+      if (!dec.ok || r > window || r > v) fail(v);
+      if (r != 0) {
+        const uint64_t dref = outdeg[v - r];
+        const uint64_t b = dec.decode(BlockCount);
+        if (!dec.ok || b > dref + 1) fail(v);
+        uint64_t pos = 0, copied = 0;
+        for (uint64_t k = 0; k < b; ++k) {
+          const uint64_t len = dec.decode(Blocks) + (k ? 1 : 0);
+          if (!dec.ok || len > dref - pos) fail(v);
+          if ((k & 1) == 0) copied += len;
+          pos += len;
+        }
+        if ((b & 1) == 0) copied += dref - pos;
+        if (copied > d) fail(v);
+        extras = d - copied;
+      }
+    }
+    if (extras && minint != 0) {
+      const uint64_t ni = dec.decode(IntervalCount);
+      if (!dec.ok || ni > extras) fail(v);
+      for (uint64_t k = 0; k < ni; ++k) {
+        dec.decode(IntervalStart);
+        const uint64_t len = dec.decode(IntervalLen) + minint;
+        if (!dec.ok || len > extras) fail(v);
+        extras -= len;
+      }
+    }
+    if (extras) {
+      dec.decode(FirstResidual);
+      for (uint64_t k = 1; k < extras; ++k) dec.decode(Residual);
+      if (!dec.ok) fail(v);
+    }
+  }
+  // a full sequential decode ends where the encoder started (encoder.rs:22-28)
+  if (dec.ptr != 0 || dec.state != WGA_LOWER_BOUND) throw Error(WGA_E_CORRUPT, "sequential bootstrap: the stream does not end at the initial encoder state");
+}
+
 }  // namespace wga
 
 using namespace wga;

@@ -17,6 +17,9 @@ namespace wga {
       throw ::wga::Error(WGA_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));            \
   } while (0)
 
+// phases of every node from the .ans alone (ANSBvGraphSeq::load, sequential.rs:29-51): see graph.cu
+void bootstrap_phases(const Prelude& pre, const PackedTablesData& pk, Phases& out);
+
 extern std::atomic<uint64_t> g_kernel_launches;
 inline void count_launch(int n = 1) { g_kernel_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
@@ -63,6 +66,8 @@ struct wga_graph {
   cudaEvent_t dec_done[2] = {}, down_done[2] = {};
   uint64_t* pipe_off[2] = {}; uint64_t pipe_off_n = 0;
   uint32_t* pipe_succ[2] = {}; uint64_t pipe_succ_n = 0;
+  uint64_t last_halo_nodes = 0;     // halo of the last decode_range
+  uint64_t last_need_succ = 0;      // elements the last "d_succ too small" failure asked for
   uint64_t max_record_words = UINT64_MAX;  // largest record of the resident range in stream words (lazy)
   uint64_t longest_record();
   void ensure_pipeline();

@@ -390,6 +390,7 @@ struct ModelBuilder::Impl {
   DevBuf sp_keys, sp_counts;
   uint64_t sp_n = 0;
   bool constants_set = false;
+  DevBuf k_in, c_in, k_out, c_out, tmp, d_num, big_keys, big_count;  // scratch of accumulate / merge_sparse
 
   void init() {
     if (d_bins) return;
@@ -410,7 +411,7 @@ struct ModelBuilder::Impl {
                     cudaStream_t st) {
     if (n == 0) return;
     const uint64_t tot = sp_n + n;
-    DevBuf k_in, c_in, k_out, c_out, tmp, d_num;
+    // (grow-only scratch kept in the builder: allocating gigabyte buffers per call costs more than the kernels)
     k_in.ensure(tot * 8); c_in.ensure(tot * 8); k_out.ensure(tot * 8); c_out.ensure(tot * 8);
     d_num.ensure(8);
     if (sp_n) {
@@ -472,7 +473,8 @@ uint64_t* ModelBuilder::device_bins() {
 void ModelBuilder::accumulate_device(const uint8_t* d_comps, const uint64_t* d_syms, uint64_t n, cudaStream_t st) {
   impl_->init();
   if (n == 0) return;
-  DevBuf big_keys, big_count;
+  DevBuf& big_keys = impl_->big_keys;
+  DevBuf& big_count = impl_->big_count;
   big_keys.ensure(n * 8);
   big_count.ensure(8);
   WGA_CUDA(cudaMemsetAsync(big_count.p, 0, 8, st));
