@@ -1,1 +1,2 @@
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+timeout 900 python -m pytest tests/test_gpu_decode.py -m gpu -x -q 2>&1 | tail -4
+python tools/prof_decode.py eu-2015-host-shaped 3 2>&1 | tail -1

@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
   const uint32_t c_extras = minint ? (uint32_t)IntervalCount : (uint32_t)FirstResidual;
   const uint32_t lo32 = (uint32_t)rv.lo;
   const uint16_t* __restrict__ const stream = g.stream;
+  const uint64_t offs_h = rv.offs[rv.h];  // first arc of the caller's range
 
   // warp-uniform
   uint32_t nx = 0, ne = 0;      // nodes [nx, ne) of the current unit are not yet handed out
@@ -412,7 +413,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
       if (isres0 && !err) {
         // The residuals go to the tail of the node's own slot (they are merged in place by K2: the write position
         // never overtakes the unread ones); without reference and intervals they are the final list.
-        uint32_t* slot = node_slot(rv, t);
+        // (node_slot, with the range start kept in a register)
+        const uint64_t so = rv.offs[t];
+        uint32_t* slot = t < rv.h ? (so + d <= rv.halo_cap ? rv.halo_succ + so : nullptr)
+                                  : (so + d - offs_h <= rv.succ_cap ? rv.succ + (so - offs_h) : nullptr);
         if (!slot) err |= ERR_WORKSPACE;
         else {
           wp = slot + (d - extras - 1u);
