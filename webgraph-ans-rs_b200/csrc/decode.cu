@@ -88,6 +88,8 @@ struct RangeView {
   uint32_t h;         // halo nodes: first - lo
   uint32_t* outdeg;   // n+1
   uint4* nrec;        // n : from K0: decoder (state, stream index) after the record's head, outdegree, head word
+  uint4* nrec2;       // n : from K0: prefetched stream word, phase (state, stream index) the record must end at
+                      //     (state 0: not checked); from k_plan: .w = aux (see k_plan)
   uint64_t* offs;     // n+1, relative to lo
   uint32_t* meta;     // n : record word of K1
   uint64_t* roff;     // n+1 : record regions
@@ -136,12 +138,30 @@ __device__ __forceinline__ void load_phase(const DevGraph& g, uint64_t v, Dec& d
   dec_prime(d, g.stream);
 }
 
+// A record ends where the next one begins: after the last symbol of node v the decoder must stand at the phase of
+// node v+1 (the encoder runs through the whole graph with one state, encoder.rs / bvgraph_decoder_factory.rs:46-58),
+// which any corruption of the record breaks.  Returns that phase as (state, stream index); state 0 = not checked:
+// the last node of a shard (the next phase is not resident) and the last node of a contiguous range (the
+// pipelined host entry point decodes a chunk while the phases of the next one are still on their way to the
+// device).  The last node of the graph ends at the initial encoder state.
+__device__ __forceinline__ uint2 expected_end(const DevGraph& g, bool last_of_range, uint64_t v) {
+  if (v + 1 > g.top) return (g.top + 1 == g.N && g.stream_base == 0) ? make_uint2(WGA_LOWER_BOUND, 0u) : make_uint2(0u, 0u);
+  if (last_of_range) return make_uint2(0u, 0u);
+  uint64_t p = g.ptrs[g.top - (v + 1)] - g.stream_base;
+  if (p > g.stream_words) return make_uint2(1u, 0u);  // (never matches)
+  uint32_t s = g.states[g.top - (v + 1)];
+  // The encoder's upper bound wraps in 32 bits for frames below 2^16 (component_model4encoder.rs:28-34), which can
+  // leave a recorded state below 2^16; the decoder arriving there has already extended it (decoder.rs:67-69).
+  if (s < WGA_LOWER_BOUND && p != 0) { --p; s = (s << 16) | (uint32_t)g.stream[p]; }
+  return make_uint2(s, (uint32_t)p);
+}
+
 // -------------------------------------------------------------------------------------------- K0
 // One lane per node, every lane at the same symbol: the fixed-shape head of a record -- outdegree, reference
 // offset, block count -- and the decoder state after it.  The block count is validated by K1, which knows the
 // outdegree of the referenced node.
 __global__ void __launch_bounds__(TPB) k_heads(DevGraph g, uint64_t lo, const uint32_t* nodes, uint32_t n,
-                                               uint32_t* outdeg, uint4* nrec, uint32_t* err_out) {
+                                               uint32_t* outdeg, uint4* nrec, uint4* nrec2, uint32_t* err_out) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n) return;
   if (t == n) { outdeg[n] = 0; return; }
@@ -171,6 +191,8 @@ __global__ void __launch_bounds__(TPB) k_heads(DevGraph g, uint64_t lo, const ui
     }
     if (err) { rt = 0; b = 0; }
     nrec[t] = make_uint4(dc.state, dc.sp, (uint32_t)d, rt | (b << RT_BITS));
+    const uint2 ee = expected_end(g, !nodes && t + 1 == n, v);
+    nrec2[t] = make_uint4(dc.w, ee.x, ee.y, 0u);
   }
   if (err) atomicOr(err_out, err);
 }
@@ -178,9 +200,15 @@ __global__ void __launch_bounds__(TPB) k_heads(DevGraph g, uint64_t lo, const ui
 struct U32ToU64 {
   __host__ __device__ uint64_t operator()(uint32_t x) const { return (uint64_t)x; }
 };
-// words of a node's record region: block count + interval count word + at most one word per successor
+// words of a node's record region: the copy blocks, the interval count, two words per interval, the residual count.
+// An interval covers at least min_interval_length successors: two words per interval are at most one per successor
+// (two when the minimum length is one).
+__host__ __device__ inline uint64_t rec_words(uint32_t b, uint32_t d, uint32_t minint) {
+  return (uint64_t)b + 2u + (minint == 1u ? 2ull * d : (uint64_t)d);
+}
 struct RecWords {
-  __host__ __device__ uint64_t operator()(const uint4& r) const { return (uint64_t)(r.w >> RT_BITS) + 2u + r.z; }
+  uint32_t minint;
+  __host__ __device__ uint64_t operator()(const uint4& r) const { return rec_words(r.w >> RT_BITS, r.z, minint); }
 };
 
 // -------------------------------------------------------------------------------------------- halo
@@ -252,33 +280,84 @@ struct SmemTables {
   __device__ __forceinline__ uint32_t recip(const uint4& cp) const { return recip_tab[(cp.x >> 21) & 31u]; }
 };
 
-// per-lane machine states: the component being decoded (3..8 = BVGraphComponent, mod.rs:46-61) or one of
-enum : uint32_t { C_FETCH = 9, C_IDLE = 10 };
+// Per-lane machine states of the entropy kernel: where in the record the lane is (the first interval start and the
+// first residual are nat-coded differences to the node id, so they get states of their own).
+enum : uint32_t { S_BLK = 0, S_ICNT, S_IST0, S_IST, S_ILEN, S_RES0, S_RES, S_FREE, S_COUNT = S_FREE };
+__device__ __constant__ uint8_t c_state_comp[S_COUNT] = {Blocks, IntervalCount, IntervalStart, IntervalStart,
+                                                         IntervalLen, FirstResidual, Residual};
 
-// node + nat2int(x) in 32-bit arithmetic (ids are < 2^32, so a valid x is < 2^33); false on leaving [0, 2^32-2]
-__device__ __forceinline__ bool add_nat(uint32_t v, uint64_t x, uint32_t& out) {
-  const uint32_t half = (uint32_t)(x >> 1);
-  const bool neg = (x & 1) != 0;
-  out = neg ? v - half - 1u : v + half;
-  return (x >> 33) == 0 && (neg ? half < v : (out >= v && out != 0xFFFFFFFFu));
+// What K1 needs to start the record of node t, prepared by k_plan (which sees the scans and the outdegree of the
+// referenced node) so that K1's set-up is three independent loads and no dependent one.
+struct NodePlan {
+  uint32_t* slot_end;  // one past the node's CSR slot
+  uint32_t* rec;       // the node's region of the record buffer; nullptr: nothing to decode in K1 (meta is final)
+};
+
+// One thread per node, after the scans.  Decides which nodes have symbols left for K1 and validates the head:
+//   no successors, or a pure copy of the referenced list (no blocks, same outdegree)  -> meta = 0, nothing for K1
+//   block count > outdegree of the referenced node + 1, pure copy longer than the list -> corrupt
+//   slot or record region beyond the buffers                                         -> workspace error
+// aux (nrec2[t].w) = outdegree of the referenced node (records with copy blocks) or the number of successors that
+// are not copied (records without).  Records without K1 work must already stand at the phase of the next node.
+__global__ void __launch_bounds__(256) k_plan(DevGraph g, RangeView rv, NodePlan* plan) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rv.n) return;
+  const uint4 p = rv.nrec[t];
+  const uint32_t d = p.z, rt = p.w & RT_MASK, b = p.w >> RT_BITS;
+  NodePlan pl{nullptr, nullptr};
+  uint32_t a = 0, err = 0, m = 0;
+  bool work = false;
+  if (d != 0) {
+    uint32_t* slot = node_slot(rv, t);
+    const uint64_t ro = rv.roff[t];
+    if (!slot || ro + rec_words(b, d, g.min_interval) > rv.recs_cap) err = ERR_WORKSPACE;
+    else if (rt == 0) { a = d; work = true; }
+    else {
+      const uint32_t dref = rv.outdeg[t - rt];
+      if (b > dref && b - dref > 1u) err = ERR_CORRUPT;  // at most dref + 1 blocks
+      else if (b != 0) { a = dref; work = true; }
+      else if (dref > d) err = ERR_CORRUPT;
+      else { a = d - dref; work = a != 0; }
+    }
+    if (work) pl = NodePlan{slot + d, rv.recs + ro};
+  }
+  if (!work && !err) {
+    const uint4 q = rv.nrec2[t];
+    if (q.y != 0 && (q.y != p.x || q.z != p.y)) err = ERR_CORRUPT;
+  }
+  if (err) { atomicOr(rv.err, err); m = MF_ERR << 29; pl = NodePlan{nullptr, nullptr}; }
+  if (!pl.rec) rv.meta[t] = m;
+  plan[t] = pl;
+  rv.nrec2[t].w = a;
 }
 
 // LIST: node t is rv.nodes[t] (random access) instead of rv.lo + t.  ALLHOT: every table entry is in shared memory.
+// Every busy lane decodes one symbol per iteration.  What follows the table lookup is the same instruction sequence
+// for every state -- the value is one of
+//   gap  prev + 1 + x     copy-block ends (cumulative: prev starts at -1), later interval starts, residuals
+//   nat  v + nat2int(x)   first interval start, first residual
+//   len  x (+ min_interval_length)   interval count, interval length
+// and the counters and the next state follow from a few selects and one packed transition table.
+// Values are not range-checked one by one: what is checked is what memory safety needs (interval count and lengths
+// and copied elements within the outdegree) and, at the end of every record, that the decoder stands exactly at
+// the phase of the next node -- which any corruption of the record breaks.
 template <bool LIST, bool ALLHOT>
-__global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView rv, K1Tables kt, uint32_t refill_min) {
+__global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView rv, K1Tables kt, const NodePlan* plan,
+                                                           uint32_t refill_min) {
   extern __shared__ __align__(16) unsigned char k1_smem[];
-  uint4* s_cp = reinterpret_cast<uint4*>(k1_smem);                        // 9 x 16 B
+  uint4* s_cp = reinterpret_cast<uint4*>(k1_smem);                        // one per machine state (8 x 16 B, + 1 spare)
   uint32_t* s_goff = reinterpret_cast<uint32_t*>(k1_smem + 9 * 16);       // 9 (+ pad to 12)
   uint32_t* s_recip = s_goff + 12;                                         // 32
   uint2* s_bkt = reinterpret_cast<uint2*>(s_recip + 32);
   uint2* s_ent = s_bkt + kt.bkt_words;
   {
-    if (threadIdx.x < WGA_COMPONENTS) {
-      uint4 c = kt.cp[threadIdx.x];
-      c.x |= threadIdx.x << 26;  // component index for the cold-entry path
+    if (threadIdx.x < S_COUNT) {
+      const uint32_t comp = c_state_comp[threadIdx.x];
+      uint4 c = kt.cp[comp];
+      c.x |= comp << 26;  // component index for the cold-entry path
       s_cp[threadIdx.x] = c;
-      s_goff[threadIdx.x] = kt.gent_off[threadIdx.x];
     }
+    if (threadIdx.x < WGA_COMPONENTS) s_goff[threadIdx.x] = kt.gent_off[threadIdx.x];
     if (threadIdx.x < 32) s_recip[threadIdx.x] = 65536u / (threadIdx.x ? threadIdx.x : 1u) + 1u;
     // buckets and hot entries of components 3..8, laid out as kt.cp says
     for (int c = Blocks; c <= Residual; ++c) {
@@ -293,161 +372,137 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t minint = g.min_interval;
-  const uint32_t c_extras = minint ? (uint32_t)IntervalCount : (uint32_t)FirstResidual;
+  const uint32_t s_extras = minint ? (uint32_t)S_ICNT : (uint32_t)S_RES0;  // what follows the copy blocks
   const uint32_t lo32 = (uint32_t)rv.lo;
   const uint16_t* __restrict__ const stream = g.stream;
-  const uint64_t offs_h = rv.offs[rv.h];  // first arc of the caller's range
+  // transition table, 4 bits per (state, run counter k != 0): next state | 8 when the record may end here
+  //   BLK: k ? BLK : extras-state*   ICNT: k ? IST0 : RES0*   IST0, IST: ILEN   ILEN: k ? IST : RES0*   RES0, RES: RES*
+  uint64_t trans = 0;
+  {
+    const uint32_t e[14] = {s_extras | 8u, S_BLK, S_RES0 | 8u, S_IST0, S_ILEN, S_ILEN, S_ILEN, S_ILEN,
+                            S_RES0 | 8u, S_IST, S_RES | 8u, S_RES | 8u, S_RES | 8u, S_RES | 8u};
+#pragma unroll
+    for (int i = 0; i < 14; ++i) trans |= (uint64_t)e[i] << (4 * i);
+  }
 
   // warp-uniform
   uint32_t nx = 0, ne = 0;      // nodes [nx, ne) of the current unit are not yet handed out
   bool exhausted = false;
   // per-lane record state
-  uint32_t c = C_FETCH, t = 0, v = 0, prev = 0, d = 0, dref = 0, k = 0, b = 0, copied = 0, sgn = 1, ub = 0xFFFFFFFEu, extras = 0,
-           ni = 0, ns = 0, flags = 0;
-  uint32_t* wp = nullptr;    // residuals parked in the node's own slot (MF_INSLOT)
-  uint32_t* recw = nullptr;  // the node's region of the record buffer
+  uint32_t c = S_FREE, t = 0, prev = 0, d = 0, k = 0, bb = 0, copied = 0, sgn = 1, extras = 0, ni = 0, ns = 0;
+  uint32_t vl = 0;               // LIST: the node id
+  uint32_t end_state = 0, end_sp = 0;  // where the decoder must stand after the record (end_state 0: not checked)
+  uint32_t* slot_end = nullptr;  // the residuals are parked at the tail of the node's own slot (MF_INSLOT)
+  uint32_t* recw = nullptr;      // the node's region of the record buffer
   Dec dc{0, 0, 0};
 
   for (;;) {
-    uint32_t err = 0;
-    bool finish = false;
     // ---------------------------------------------------------------- hand out nodes
-    const uint32_t nf = __ballot_sync(FULL, c == C_FETCH);
-    if (nf) {
-      const uint32_t busy = __ballot_sync(FULL, c < C_FETCH);
-      const uint32_t cnt = (uint32_t)__popc(nf);
-      if (busy == 0 || cnt >= refill_min) {
-        const uint32_t r = (uint32_t)__popc(nf & lt_mask);  // rank among the fetching lanes
+    const uint32_t busy = __ballot_sync(FULL, c != S_FREE);
+    if (!exhausted) {
+      const uint32_t cnt = 32u - (uint32_t)__popc(busy);
+      if (cnt >= refill_min) {
+        const uint32_t r = (uint32_t)__popc(~busy & lt_mask);  // rank among the free lanes
         uint32_t my = NOT_FOUND;
         uint32_t taken = 0;
-        while (taken < cnt) {  // (uniform) the fetchers may straddle a unit boundary
+        while (taken < cnt) {  // (uniform) the free lanes may straddle a unit boundary
           if (nx >= ne) {
-            if (exhausted) break;
             uint32_t u = 0;
             if (lane == 0) u = atomicAdd(rv.unit_ctr, 1u);
             u = __shfl_sync(FULL, u, 0);
             if (u >= rv.n_units) { exhausted = true; break; }
             nx = u * rv.unit;
             ne = min(nx + rv.unit, rv.n);
+            // the set-up data of the unit's nodes will be needed within the next few hundred iterations
+            for (uint32_t i = nx + 8 * lane; i < ne; i += 256) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rv.nrec + i));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rv.nrec2 + i));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(plan + i));
+            }
           }
           const uint32_t take = min(ne - nx, cnt - taken);
           if (r >= taken && r < taken + take) my = nx + (r - taken);
           nx += take;
           taken += take;
         }
-        if (c == C_FETCH) {
-          if (my == NOT_FOUND) { if (exhausted) c = C_IDLE; }
-          else {
+        if (c == S_FREE && my != NOT_FOUND) {
+          const NodePlan pl = plan[my];
+          if (pl.rec != nullptr) {
+            const uint4 p = rv.nrec[my];
+            const uint4 q = rv.nrec2[my];
+            const uint32_t a = q.w;
             t = my;
-            const uint4 p = rv.nrec[t];
+            if (LIST) vl = rv.nodes[my];
             d = p.z;
-            v = LIST ? rv.nodes[t] : lo32 + t;
             dc.state = p.x;
             dc.sp = p.y;
+            dc.w = q.x;
+            end_state = q.y;
+            end_sp = q.z;
+            recw = pl.rec;
+            slot_end = pl.slot_end;
             ns = 0;
-            flags = 0;
             ni = 0;
-            ub = 0xFFFFFFFEu;
-            wp = nullptr;
-            if (d == 0) finish = true;
-            else {
-              dec_prime(dc, stream);
-              const uint32_t rt = p.w & RT_MASK;
-              b = p.w >> RT_BITS;
-              const uint64_t ro = rv.roff[t];
-              recw = rv.recs + ro;
-              if (ro + b + 2 + d > rv.recs_cap) err |= ERR_WORKSPACE;
-              if (rt == 0) { extras = d; c = c_extras; }
-              else {
-                flags = 8u;  // (internal) the node has a reference
-                dref = rv.outdeg[t - rt];
-                if (b > dref && b - dref > 1u) err |= ERR_CORRUPT;  // at most dref + 1 blocks
-                else if (b == 0) {
-                  if (dref > d) err |= ERR_CORRUPT;
-                  else { extras = d - dref; if (extras) c = c_extras; else finish = true; }
-                } else { k = b; prev = 0xFFFFFFFFu; copied = 0; sgn = 1u; ub = dref; c = Blocks; }
-              }
-            }
+            extras = a;  // (records with copy blocks: the outdegree of the referenced node, until the blocks end)
+            const uint32_t b = p.w >> RT_BITS;
+            bb = b | ((p.w & RT_MASK) ? 0x80000000u : 0u);
+            k = b;
+            prev = 0xFFFFFFFFu;
+            copied = 0;
+            sgn = 1u;
+            c = b ? (uint32_t)S_BLK : s_extras;
           }
         }
       }
-      if (__all_sync(FULL, c == C_IDLE)) break;
-    }
+    } else if (busy == 0) break;
     // ---------------------------------------------------------------- one symbol per busy lane
-    // The step after the table lookup is the same instruction sequence for every component: the value is one of
-    //   gap  prev + 1 + x     copy-block ends (cumulative: prev starts at -1), later interval starts, residuals
-    //   nat  v + nat2int(x)   first interval start, first residual
-    //   len  x (+ min_interval_length)   interval count, interval length
-    // and counters / next component follow from a few selects, so the lanes of a warp do not diverge here.
-    const bool decoding = c < C_FETCH && !err && !finish;
-    uint32_t val = 0;
-    if (decoding) {
+    if (c != S_FREE) {
+      uint32_t err = 0;
       const uint64_t x = ans_decode_cp(s_cp[c], tab, dc, stream, err);
       const uint32_t xl = (uint32_t)x;
-      const bool wide = (x >> 32) != 0;  // only nat2int arguments (first residual / interval start) may need 33 bits
-      const bool isblk = c == Blocks, isicnt = c == IntervalCount, isist = c == IntervalStart, isilen = c == IntervalLen,
-                 isres0 = c == FirstResidual;
-      const bool nat = isres0 || (isist && k == ni);  // k = intervals still to come
-      const bool gap = !nat && (isblk || isist || c == Residual);
-      uint32_t natv;
-      const bool natok = add_nat(v, x, natv);
-      const uint32_t gapv = prev + 1u + xl;
+      const uint32_t v = LIST ? vl : lo32 + t;
+      const bool isblk = c == S_BLK, isicnt = c == S_ICNT, isilen = c == S_ILEN, isres = c >= S_RES0;
+      const bool nat = c == S_IST0 || c == S_RES0;
+      const uint32_t half = (uint32_t)(x >> 1);
+      const uint32_t natv = (xl & 1u) ? v - half - 1u : v + half;  // v + nat2int(x)
       const uint32_t lenv = xl + (isilen ? minint : 0u);
-      val = nat ? natv : gap ? gapv : lenv;
-      const bool gapok = !wide && gapv >= prev + 1u && gapv <= ub;  // (block ends: ub = outdegree of the referenced node)
-      const bool lenok = !wide && lenv >= xl && lenv <= extras && (!isilen || (lenv != 0 && prev + lenv >= prev)) &&
-                         (!isicnt || (uint64_t)xl * minint <= extras);
-      if (!(nat ? natok : gap ? gapok : lenok)) err |= (nat || (gap && !isblk)) ? ERR_SYMBOL_WIDTH : ERR_CORRUPT;
-      if (nat || gap) prev = val;
-      else if (isilen) prev += lenv;  // one past the end of this interval
+      const uint32_t val = nat ? natv : (isicnt || isilen) ? lenv : prev + 1u + xl;
+      prev = isilen ? prev + lenv : val;  // (interval length: one past the end of the interval)
+      bool bad = err != 0;
       if (isblk) { copied += sgn * val; sgn = 0u - sgn; }  // alternating sum of the cumulative ends = copied elements
-      extras -= c >= FirstResidual ? 1u : (isilen ? lenv : 0u);
-      if (isicnt) { ni = xl; k = xl; }
+      if (isicnt) { ni = xl; k = xl; bad = bad || (uint64_t)xl * minint > extras || (x >> 32) != 0; }
       else if (isblk || isilen) --k;
+      if (isilen) bad = bad || lenv > extras || lenv < xl || (x >> 32) != 0;
       if (isblk && k == 0) {  // end of the block run: what is left for intervals and residuals
-        if ((b & 1u) == 0) copied += dref;  // even count: the tail of the referenced list is copied too
-        if (copied > d) err |= ERR_CORRUPT;
+        if ((bb & 1u) == 0) copied += extras;  // even count: the tail of the referenced list is copied too
+        bad = bad || copied > d;
         extras = d - copied;
-        ub = 0xFFFFFFFEu;
+      } else extras -= isres ? 1u : (isilen ? lenv : 0u);
+      // ---------------------------------------------------------------- one word of the record
+      if (!bad) {
+        if (c == S_RES0) recw[ns++] = extras + 1u;  // the record ends with the number of parked residuals
+        // residuals: the last words of the node's slot (they are merged in place by K2: the write position never
+        // overtakes the unread ones); without reference and intervals they are the final list
+        uint32_t* const base = isres ? slot_end : recw;
+        const int32_t idx = isres ? -(int32_t)(extras + 1u) : (int32_t)ns;
+        base[idx] = val;
+        ns += isres ? 0u : 1u;
       }
-      if (isres0 && !err) {
-        // The residuals go to the tail of the node's own slot (they are merged in place by K2: the write position
-        // never overtakes the unread ones); without reference and intervals they are the final list.
-        // (node_slot, with the range start kept in a register)
-        const uint64_t so = rv.offs[t];
-        uint32_t* slot = t < rv.h ? (so + d <= rv.halo_cap ? rv.halo_succ + so : nullptr)
-                                  : (so + d - offs_h <= rv.succ_cap ? rv.succ + (so - offs_h) : nullptr);
-        if (!slot) err |= ERR_WORKSPACE;
-        else {
-          wp = slot + (d - extras - 1u);
-          flags |= (!(flags & 8u) && ni == 0) ? (MF_INSLOT | MF_FINAL) : MF_INSLOT;
-          recw[ns++] = extras + 1u;  // the record ends with the number of parked residuals
+      // ---------------------------------------------------------------- next state / end of the record
+      const uint32_t tr = (uint32_t)(trans >> (8u * c + (k != 0 ? 4u : 0u))) & 15u;
+      const bool finish = (tr & 8u) != 0 && extras == 0;
+      if (bad || finish) {
+        uint32_t m;
+        if (bad || ns > NSYM_MAX || (end_state != 0 && (dc.state != end_state || dc.sp != end_sp))) {
+          atomicOr(rv.err, (!bad && ns > NSYM_MAX) ? ERR_LIMIT : ERR_CORRUPT);
+          m = MF_ERR << 29;
+        } else {
+          const uint32_t fl = !isres ? 0u : ((bb >> 31) == 0 && ni == 0) ? (MF_INSLOT | MF_FINAL) : MF_INSLOT;
+          m = ns | (fl << 29);
         }
-      }
-      // next component
-      const bool run_more = (isblk || isicnt || isilen) && k != 0;
-      const bool more = extras != 0;
-      uint32_t nc = isist ? (uint32_t)IntervalLen
-                   : run_more ? (isblk ? (uint32_t)Blocks : (uint32_t)IntervalStart)
-                   : c >= FirstResidual ? (uint32_t)Residual
-                   : isblk ? c_extras : (uint32_t)FirstResidual;
-      finish = !isist && !run_more && !more;
-      c = nc;
-    }
-    // ---------------------------------------------------------------- one word of the record
-    if (decoding && !err) {
-      if (wp != nullptr) *wp++ = val;
-      else recw[ns++] = val;
-    }
-    // ---------------------------------------------------------------- end of a record
-    if (err) {
-      atomicOr(rv.err, err);
-      rv.meta[t] = MF_ERR << 29;
-      c = C_FETCH;
-    } else if (finish) {
-      if (ns > NSYM_MAX) { atomicOr(rv.err, ERR_LIMIT); flags |= MF_ERR; }
-      rv.meta[t] = (ns & NSYM_MAX) | ((flags & 7u) << 29);
-      c = C_FETCH;
+        rv.meta[t] = m;
+        c = S_FREE;
+      } else c = tr & 7u;
     }
   }
 }
@@ -614,19 +669,48 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
 #pragma unroll
     for (int step = 0; step < STEPS_PER_VOTE; ++step) {
       if (st == S_MERGE) {
+        // The smallest head goes out, and with it up to three more elements of the SAME run that are still below
+        // the heads of the other two runs: their loads are independent, so a lane inside a long copy block (or a
+        // run of residuals) moves four elements per memory round trip instead of one.
         const uint32_t mn = min(cval, min(ival, rval));
-        out[p] = mn;
-        if (mn == cval) {
-          if (++ci == cend) next_copy_block(); else cval = ref[ci];  // (loading one element ahead was measured: no gain)
-        } else if (mn == rval) {
-          // (in-slot residuals: res[rj + 1] is still unread input: written <= copied + intervals + residuals consumed)
-          rval = ++rj < nres ? res[rj] : INF;
+        const bool is_c = mn == cval, is_r = !is_c && mn == rval;
+        const uint32_t other = is_c ? min(ival, rval) : is_r ? min(cval, ival) : min(cval, rval);
+        uint32_t e1 = INF, e2 = INF, e3 = INF, e4 = INF;  // the elements after the head (INF: the run ends before)
+        if (is_c || is_r) {
+          const uint32_t* src = is_c ? ref + ci : res + rj;  // (in-slot residuals: unread input, see above)
+          const uint32_t avail = is_c ? cend - ci : nres - rj;
+          if (avail > 1) e1 = src[1];
+          if (avail > 2) e2 = src[2];
+          if (avail > 3) e3 = src[3];
+          if (avail > 4) e4 = src[4];
         } else {
-          if (++ival == ilim) {
+          const uint32_t avail = ilim - ival;
+          if (avail > 1) e1 = ival + 1;
+          if (avail > 2) e2 = ival + 2;
+          if (avail > 3) e3 = ival + 3;
+          if (avail > 4) e4 = ival + 4;
+        }
+        const bool t1 = e1 < other, t2 = t1 && e2 < other, t3 = t2 && e3 < other;
+        const uint32_t m = min(1u + (uint32_t)t1 + (uint32_t)t2 + (uint32_t)t3, d - p);
+        out[p] = mn;
+        if (m > 1) out[p + 1] = e1;
+        if (m > 2) out[p + 2] = e2;
+        if (m > 3) out[p + 3] = e3;
+        const uint32_t nh = m == 1 ? e1 : m == 2 ? e2 : m == 3 ? e3 : e4;  // the run's next head
+        p += m;
+        if (is_c) {
+          ci += m;
+          if (ci == cend) next_copy_block(); else cval = nh;
+        } else if (is_r) {
+          rj += m;
+          rval = nh;
+        } else {
+          ival += m;
+          if (ival == ilim) {
             if (ip < iend) { ival = hp[ip]; ilim = ival + hp[ip + 1]; ip += 2; } else ival = INF;
           }
         }
-        if (++p == d) st = S_FETCH;
+        if (p == d) st = S_FETCH;
       }
     }
   }
@@ -738,7 +822,7 @@ __global__ void k_decode_symbols(DevGraph g, const uint8_t* comps, uint64_t n, u
   uint32_t err = 0;
   Dec dc{state, (uint32_t)ptr, 0};
   dec_prime(dc, g.stream);
-  for (uint64_t i = 0; i < n; ++i) out[i] = ans_decode(g.tb, tab, comps[i], dc, g.stream, err);
+  for (uint64_t i = 0; i < n; ++i) out[i] = ans_decode<true>(g.tb, tab, comps[i], dc, g.stream, err);
   end[0] = (uint64_t)dc.sp;
   end[1] = dc.state;
   end[2] = err;
@@ -778,7 +862,7 @@ struct Scalars {
 static_assert(sizeof(Scalars) <= 256, "Scalars must fit the cleared line");
 
 struct WorkspacePlan {
-  uint64_t off_outdeg, off_nrec, off_offs, off_roff, off_meta, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_recs;
+  uint64_t off_outdeg, off_nrec, off_nrec2, off_offs, off_roff, off_meta, off_plan, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_recs;
   uint64_t cub_bytes, halo_cap, fixed_bytes;
 };
 
@@ -788,9 +872,11 @@ WorkspacePlan plan_workspace(uint64_t n) {
   o += 256;  // Scalars
   p.off_outdeg = o; o = align_up(o + 4 * (n + 1), 256);
   p.off_nrec = o; o = align_up(o + 16 * n, 256);
+  p.off_nrec2 = o; o = align_up(o + 16 * n, 256);
   p.off_offs = o; o = align_up(o + 8 * (n + 1), 256);
   p.off_roff = o; o = align_up(o + 8 * (n + 1), 256);
   p.off_meta = o; o = align_up(o + 4 * n, 256);
+  p.off_plan = o; o = align_up(o + sizeof(NodePlan) * n, 256);
   p.off_lev = o; o = align_up(o + 4 * n, 256);
   for (int i = 0; i < 2; ++i) { p.off_keys[i] = o; o = align_up(o + n, 256); }
   for (int i = 0; i < 2; ++i) { p.off_vals[i] = o; o = align_up(o + 4 * n, 256); }
@@ -820,6 +906,7 @@ uint64_t decode_workspace_size(const wga_graph* g, uint64_t first, uint64_t last
   uint64_t arcs_est = (uint64_t)((double)g->prelude.number_of_arcs * frac) + (1u << 20);
   // record buffer: (block count + 1 + outdegree) words per node; the block counts sum to about three per node on web
   // graphs and are bounded by (outdegree of the referenced node + 1)
+  if (g->prelude.min_interval_length == 1) arcs_est *= 2;  // (two record words per successor in the worst case)
   uint64_t rows_bytes = 4 * (arcs_est + arcs_est / 4 + 8 * n) + (16ull << 20);
   return p.fixed_bytes + rows_bytes;
 }
@@ -851,7 +938,7 @@ void outdegrees(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets
   if (ws_bytes < p.off_nrec) throw Error(WGA_E_WORKSPACE, "workspace too small");
   uint8_t* w = (uint8_t*)ws;
   uint32_t* outdeg = (uint32_t*)(w + p.off_outdeg);
-  k_heads<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, first, nullptr, (uint32_t)n, outdeg, nullptr, g->d_err);
+  k_heads<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, first, nullptr, (uint32_t)n, outdeg, nullptr, nullptr, g->d_err);
   count_launch();
   // the scan's temporary storage lives behind the outdegrees (the other arrays of the plan are not used here)
   size_t cb = p.cub_bytes;
@@ -932,18 +1019,21 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
   const uint64_t n = rv.n;
   const DeviceInfo& di = device_info(g->device);
   // ---- K0 + scan
-  k_heads<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, rv.lo, rv.nodes, (uint32_t)n, rv.outdeg, rv.nrec, g->d_err);
+  k_heads<<<(unsigned)((n + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, rv.lo, rv.nodes, (uint32_t)n, rv.outdeg, rv.nrec, rv.nrec2, g->d_err);
   count_launch();
   {
     size_t cb = p.cub_bytes;
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(rv.outdeg, U32ToU64());
     WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_cub, cb, it, rv.offs, (int64_t)(n + 1), st));
     cb = p.cub_bytes;
-    cub::TransformInputIterator<uint64_t, RecWords, const uint4*> itr(rv.nrec, RecWords());
+    cub::TransformInputIterator<uint64_t, RecWords, const uint4*> itr(rv.nrec, RecWords{g->dev.min_interval});
     WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + p.off_cub, cb, itr, rv.roff, (int64_t)n, st));
     count_launch(4);
   }
-  mark(g, st);  // 1: heads + scans done
+  NodePlan* const nplan = (NodePlan*)(w + p.off_plan);
+  k_plan<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g->dev, rv, nplan);
+  count_launch();
+  mark(g, st);  // 1: heads + scans + plan done
   // ---- K1: entropy decode into rows
   {
     K1Tables kt{};
@@ -956,7 +1046,7 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
     const uint32_t refill = std::max<uint32_t>(1u, std::min<uint32_t>(32u, tn.refill));
     auto launch = [&](auto kern) {
       WGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin - 1024));
-      kern<<<blocks, K1_THREADS, smem, st>>>(g->dev, rv, kt, refill);
+      kern<<<blocks, K1_THREADS, smem, st>>>(g->dev, rv, kt, nplan, refill);
     };
     if (rv.nodes) { if (allhot) launch(k_entropy<true, true>); else launch(k_entropy<true, false>); }
     else { if (allhot) launch(k_entropy<false, true>); else launch(k_entropy<false, false>); }
@@ -1043,6 +1133,7 @@ static void apply_env_tuning() {
 static void bind_views(RangeView& rv, uint8_t* w, const WorkspacePlan& p, Scalars* sc, uint64_t ws_bytes, uint32_t unit) {
   rv.outdeg = (uint32_t*)(w + p.off_outdeg);
   rv.nrec = (uint4*)(w + p.off_nrec);
+  rv.nrec2 = (uint4*)(w + p.off_nrec2);
   rv.meta = (uint32_t*)(w + p.off_meta);
   rv.maxlevel = &sc->maxlevel;
   rv.roff = (uint64_t*)(w + p.off_roff);
@@ -1178,7 +1269,7 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   count_launch();
   if (!d_succ) {  // sizing call: only the outdegrees of the queries (first symbol of each record)
     uint32_t* deg = all;
-    k_heads<<<(unsigned)((nq + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, 0, qid, (uint32_t)nq, deg, nullptr, g->d_err);
+    k_heads<<<(unsigned)((nq + 1 + TPB - 1) / TPB), TPB, 0, st>>>(g->dev, 0, qid, (uint32_t)nq, deg, nullptr, nullptr, g->d_err);
     size_t cbs = b.cub_bytes;
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(deg, U32ToU64());
     WGA_CUDA(cub::DeviceScan::ExclusiveSum(w + b.off_cub, cbs, it, d_offsets, (int64_t)(nq + 1), st));

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "common.hpp"
 
@@ -64,14 +65,15 @@ struct GlobalTables {
 // The decoder of one record: (state, index of the next word below, prefetched next word).
 // The next word is loaded right after the previous extend consumed one, so that the 16-bit renormalisation
 // (decoder.rs:89-93) never waits for memory: the load overlaps the table lookups of the following symbol.
+// The resident span is preceded by 16 readable padding bytes, so the prefetch needs no bounds test (stream[-1]).
 struct Dec {
   uint32_t state;
   uint32_t sp;  // words of the resident span below the record's read position
-  uint32_t w;   // stream[sp-1] (0 when sp == 0)
+  uint32_t w;   // stream[sp-1]
 };
 
 __device__ __forceinline__ void dec_prime(Dec& d, const uint16_t* __restrict__ stream) {
-  d.w = d.sp ? (uint32_t)__ldg(stream + d.sp - 1) : 0u;
+  d.w = (uint32_t)__ldg(stream + (int64_t)d.sp - 1);
 }
 
 // One 16-bit extend (decoder.rs:89-93).  false = the stream is exhausted.
@@ -79,8 +81,23 @@ __device__ __forceinline__ bool ans_extend(Dec& d, const uint16_t* __restrict__ 
   if (d.sp == 0) return false;
   d.state = (d.state << 16) | d.w;
   --d.sp;
-  d.w = d.sp ? (uint32_t)__ldg(stream + d.sp - 1) : 0u;
+  d.w = (uint32_t)__ldg(stream + (int64_t)d.sp - 1);
   return true;
+}
+
+// Order of the R-bit groups of x reversed (n groups, n*R <= 32, or <= 64 for the wide decoder).
+__device__ __forceinline__ uint32_t reverse_groups(uint32_t x, uint32_t n, uint32_t R) {
+  if (R == 1) return __brev(x) >> (32u - n);
+  const uint32_t rmask = (1u << R) - 1u;
+  uint32_t out = 0;
+  for (; n; --n) { out = (out << R) | (x & rmask); x >>= R; }
+  return out;
+}
+__device__ __forceinline__ uint64_t reverse_groups(uint64_t x, uint32_t n, uint32_t R) {
+  const uint64_t rmask = (1ull << R) - 1ull;
+  uint64_t out = 0;
+  for (; n; --n) { out = (out << R) | (x & rmask); x >>= R; }
+  return out;
 }
 
 // One ANS symbol.  Restates ANSDecoder::decode (src/ans/decoder.rs:58-87) on the packed tables:
@@ -92,10 +109,14 @@ __device__ __forceinline__ bool ans_extend(Dec& d, const uint16_t* __restrict__ 
 //   result = (base << folds*R) | fold                         decoder.rs:86 with quasi_fold (model4decoder.rs:56-68)
 // The fold loop of the reference takes R bits per trip (up to 38 trips).  Between two extends the trips only shift
 // the state, so they are done in one step per extend: with n = bit length of the state, the next
-// t = ceil((n-16)/R) trips need no extend (the state stays >= 2^16 until the t-th shift), they consume the low t*R
-// bits, and the chunks enter `fold` first-taken-highest, i.e. in reversed group order (radix 1: a bit reversal).
-// One loop for every folded symbol (usually one or two passes), so that the folded lanes of a warp stay together.
-template <class Tab>
+// t = ceil((n-16)/R) trips need no extend (the state stays >= 2^16 until the t-th shift) and consume the low t*R
+// bits.  The bits are collected in the order they leave the state; the reference puts the first chunk highest, so
+// the R-bit groups are reversed once at the end (nothing to do for the common single-chunk symbol).
+// One loop serves the extend after the state update and the extends between chunk runs, so that the lanes of a warp
+// meet at the same instructions whatever their fold counts are.
+// The graph kernels collect at most 32 folded bits (every value of a graph with 32-bit node ids has at most 33 bits,
+// i.e. folds*R <= 32; more is reported as corrupt); WIDE collects 64 (ANSDecoder::decode on arbitrary symbols).
+template <bool WIDE = false, class Tab>
 __device__ __forceinline__ uint64_t ans_decode_cp(const uint4 cp, const Tab& tab, Dec& d,
                                                   const uint16_t* __restrict__ stream, uint32_t& err) {
   const uint32_t slot = d.state & (cp.x & 0xFFFFu);
@@ -103,43 +124,34 @@ __device__ __forceinline__ uint64_t ans_decode_cp(const uint4 cp, const Tab& tab
   const uint2 bk = tab.bucket(cp.y + (slot >> 5));
   const uint32_t j = bk.y + (uint32_t)__popc(bk.x & ((2u << (slot & 31u)) - 1u));
   const uint2 e = tab.entry(cp, cp.z, j);
-  uint32_t rem = e.y >> 16;  // folds
-  if (rem == 0xFFFFu) {  // sentinel: slot beyond the sum of frequencies
-    err |= ERR_CORRUPT;
-    return 0;
-  }
+  const uint32_t folds = e.y >> 16;
+  const uint32_t R = (cp.x >> 21) & 31u;
+  // sentinel (slot beyond the sum of frequencies: folds = 0xFFFF) and symbols wider than the collector
+  if (folds * R > (WIDE ? 48u : 32u)) { err |= ERR_CORRUPT; return 0; }
   d.state = (d.state >> L) * (e.x >> 16) + slot - (e.x & 0xFFFFu);
-  if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
-  uint64_t val = e.y & 0xFFFFu;
-  if (rem) {
-    const uint32_t R = (cp.x >> 21) & 31u;
-    const uint32_t recip = tab.recip(cp);  // floor(65536/R)+1
-    const uint32_t rmask = (1u << R) - 1u;
-    do {
-      const uint32_t room = 16u - (uint32_t)__clz((int)d.state);  // bit length - 16 (>= 1 while state >= 2^16)
-      uint32_t t = ((room + R - 1u) * recip) >> 16;                // ceil(room/R): trips until state < 2^16
-      t = max(min(t, rem), 1u);  // >= 1 also on corrupt input (state < 2^16 after a failed extend)
-      const uint32_t nb = t * R;                                   // <= 31 bits
-      uint32_t bits = d.state & ((1u << nb) - 1u);
-      d.state >>= nb;
-      uint32_t grp;
-      if (R == 1) grp = __brev(bits) >> (32u - nb);
-      else {
-        grp = 0;
-        for (uint32_t q = t; q; --q) { grp = (grp << R) | (bits & rmask); bits >>= R; }
-      }
-      val = (val << nb) | grp;
-      rem -= t;
-      if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
-    } while (rem);
+  using Acc = typename std::conditional<WIDE, uint64_t, uint32_t>::type;
+  uint32_t rem = folds, pos = 0;
+  Acc acc = 0;
+  const uint32_t recip = tab.recip(cp);  // floor(65536/R)+1
+  for (;;) {
+    if (d.state < WGA_LOWER_BOUND && !ans_extend(d, stream)) { err |= ERR_CORRUPT; return 0; }
+    if (rem == 0) break;
+    const uint32_t room = 16u - (uint32_t)__clz((int)d.state);  // bit length - 16 (>= 1: state >= 2^16 here)
+    const uint32_t t = min(((room + R - 1u) * recip) >> 16, rem);  // ceil(room/R) trips until state < 2^16
+    const uint32_t nb = t * R;                                    // <= 16 + R - 1 bits
+    acc |= (Acc)(d.state & ((1u << nb) - 1u)) << pos;
+    pos += nb;
+    d.state >>= nb;
+    rem -= t;
   }
-  return val;
+  if (folds > 1u) acc = reverse_groups(acc, folds, R);
+  return ((uint64_t)(e.y & 0xFFFFu) << pos) | acc;
 }
 
-template <class Tab>
+template <bool WIDE = false, class Tab>
 __device__ __forceinline__ uint64_t ans_decode(const DevTables& tb, const Tab& tab, int c, Dec& d,
                                                const uint16_t* __restrict__ stream, uint32_t& err) {
-  return ans_decode_cp(comp_params(tb, c), tab, d, stream, err);
+  return ans_decode_cp<WIDE>(comp_params(tb, c), tab, d, stream, err);
 }
 
 __device__ __forceinline__ int64_t nat2int(uint64_t x) {

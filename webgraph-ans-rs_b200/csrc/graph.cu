@@ -177,7 +177,7 @@ using namespace wga;
 
 wga_graph::~wga_graph() {
   if (on_device) {
-    cudaFree(d_stream);
+    cudaFree(d_stream_alloc);
     cudaFree(d_states);
     cudaFree(d_ptrs);
     cudaFree(d_bkt);
@@ -311,8 +311,10 @@ void wga_graph::upload() {
   stream_base = lo;
   stream_words = hi - lo;
   if (stream_words >= 0xFFFFFFFFull) throw Error(WGA_E_UNSUPPORTED, "resident stream span of 2^32 words or more: open a smaller shard");
-  WGA_CUDA(cudaMalloc(&d_stream, (stream_words + 8) * 2));
-  WGA_CUDA(cudaMemset(d_stream, 0, (stream_words + 8) * 2));
+  // 8 padding words on both sides: the decoder prefetches the word below its read position without a bounds test
+  WGA_CUDA(cudaMalloc(&d_stream_alloc, (stream_words + 16) * 2));
+  WGA_CUDA(cudaMemset(d_stream_alloc, 0, (stream_words + 16) * 2));
+  d_stream = d_stream_alloc + 8;
   if (stream_words)
     WGA_CUDA(cudaMemcpy(d_stream, prelude.stream.data() + lo, stream_words * 2, cudaMemcpyHostToDevice));
   WGA_CUDA(cudaMalloc(&d_states, (n_res + 1) * 4));

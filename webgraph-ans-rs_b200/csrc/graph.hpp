@@ -34,7 +34,8 @@ struct wga_graph {
   bool on_device = false;
   int device = -1;
   // device buffers
-  uint16_t* d_stream = nullptr;
+  uint16_t* d_stream = nullptr;        // word 0 of the resident span (inside d_stream_alloc, 16 bytes of zero padding in front)
+  uint16_t* d_stream_alloc = nullptr;
   uint64_t stream_base = 0, stream_words = 0;
   uint32_t* d_states = nullptr;  // res_last-res_first entries; entry k = node res_last-1-k
   uint64_t* d_ptrs = nullptr;
