@@ -572,8 +572,15 @@ constexpr uint32_t HS = 16;  // header words (copy-block ends, interval count, i
 __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_t* order, const uint32_t* seg, uint32_t lb,
                                                      uint32_t exact_level, const uint32_t* lev, uint32_t minint) {
   __shared__ uint32_t s_hdr[RES_TPB * (HS + 1)];
+  __shared__ __align__(16) uint32_t s_stage[16 * RES_TPB];
   __shared__ uint32_t s_next;
   uint32_t* const hdr = s_hdr + threadIdx.x * (HS + 1);  // odd stride: conflict-free
+  // Output staging: a ring of 16 words per lane (word i at stg[i * RES_TPB]: conflict-free).  The successors go out
+  // as whole 32-byte sectors (two 16-byte stores) instead of one 4-byte store each -- every lane writes to its own
+  // list, so each scalar store is a separate L2 request, and those requests were what bound this kernel
+  // (lts__t_tag_requests 71 %).  Only the partial sectors at the two ends of a list are written word by word.
+  uint32_t* const stg = s_stage + threadIdx.x;
+  uint32_t A = 0;  // word offset of the slot inside its sector: list position p lives at sector position A + p
   const uint32_t beg = seg[lb], end = seg[lb + 1];
   const uint32_t len = end - beg;
   const uint32_t share = (len + gridDim.x - 1) / gridDim.x;
@@ -625,6 +632,7 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
           d = nr.z;
           b = nr.w >> RT_BITS;
           out = node_slot(rv, t);
+          A = (uint32_t)(reinterpret_cast<uintptr_t>(out) >> 2) & 7u;
           ref = nullptr;
           dref = 0;
           if (rt) {
@@ -692,12 +700,29 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
         }
         const bool t1 = e1 < other, t2 = t1 && e2 < other, t3 = t2 && e3 < other;
         const uint32_t m = min(1u + (uint32_t)t1 + (uint32_t)t2 + (uint32_t)t3, d - p);
-        out[p] = mn;
-        if (m > 1) out[p + 1] = e1;
-        if (m > 2) out[p + 2] = e2;
-        if (m > 3) out[p + 3] = e3;
+        const uint32_t q0 = A + p;
+        stg[(q0 & 15u) * RES_TPB] = mn;
+        if (m > 1) stg[((q0 + 1u) & 15u) * RES_TPB] = e1;
+        if (m > 2) stg[((q0 + 2u) & 15u) * RES_TPB] = e2;
+        if (m > 3) stg[((q0 + 3u) & 15u) * RES_TPB] = e3;
         const uint32_t nh = m == 1 ? e1 : m == 2 ? e2 : m == 3 ? e3 : e4;  // the run's next head
         p += m;
+        {
+          const uint32_t q1 = A + p, s0 = q0 & ~7u;
+          const bool crossed = q1 >= s0 + 8u;
+          if (crossed || p == d) {
+            uint32_t qa = s0 < A ? A : s0, qb = q1;  // staged and not yet written: [qa, qb)
+            if (crossed && s0 >= A) {  // a whole sector of this list
+              const uint32_t* r = stg + (s0 & 8u) * RES_TPB;
+              uint4* dst = reinterpret_cast<uint4*>(out + (s0 - A));
+              dst[0] = make_uint4(r[0], r[RES_TPB], r[2 * RES_TPB], r[3 * RES_TPB]);
+              dst[1] = make_uint4(r[4 * RES_TPB], r[5 * RES_TPB], r[6 * RES_TPB], r[7 * RES_TPB]);
+              qa = s0 + 8u;
+            } else if (crossed) qb = (p == d) ? q1 : s0 + 8u;  // (the list starts inside this sector)
+            if (p != d && !(crossed && s0 < A)) qb = qa;        // the open sector stays staged until it is complete
+            for (uint32_t q = qa; q < qb; ++q) out[q - A] = stg[(q & 15u) * RES_TPB];
+          }
+        }
         if (is_c) {
           ci += m;
           if (ci == cend) next_copy_block(); else cval = nh;
