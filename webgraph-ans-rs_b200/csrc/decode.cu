@@ -38,9 +38,9 @@ std::atomic<uint64_t> g_kernel_launches{0};
 
 // run-time tuning (tests change these to exercise tile boundaries, sub-tiling and the hard-node path)
 struct Tuning {
-  uint32_t unit = 128;        // nodes per K1 unit (what a warp pulls from the global counter)
+  uint32_t unit = 64;         // nodes per K1 unit (what a warp pulls from the global counter)
   uint32_t k1_blocks = 0;     // K1 grid; 0 = one block per SM
-  uint32_t refill = 6;        // K1: lanes that must be free before the warp fetches new nodes
+  uint32_t refill = 10;       // K1: lanes that must be free before the warp fetches new nodes (swept: 3..16)
   uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
                               // equal share of the level, so a partial second wave would double the time
   uint32_t e2e_chunk = 1u << 19;  // nodes per chunk of the pipelined host entry point
@@ -648,7 +648,13 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
           H += 2 * ni;
           iend = H;
           if (H <= HS) {
-            for (uint32_t w = 0; w < H; ++w) hdr[w] = recp[w];
+            for (uint32_t w = 0; w < H; w += 4) {  // four independent loads per trip
+              uint32_t x[4];
+#pragma unroll
+              for (uint32_t j = 0; j < 4; ++j) x[j] = w + j < H ? recp[w + j] : 0u;
+#pragma unroll
+              for (uint32_t j = 0; j < 4; ++j) if (w + j < H) hdr[w + j] = x[j];
+            }
             hp = hdr;
           } else hp = recp;
           nres = 0;
@@ -720,7 +726,11 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
               qa = s0 + 8u;
             } else if (crossed) qb = (p == d) ? q1 : s0 + 8u;  // (the list starts inside this sector)
             if (p != d && !(crossed && s0 < A)) qb = qa;        // the open sector stays staged until it is complete
-            for (uint32_t q = qa; q < qb; ++q) out[q - A] = stg[(q & 15u) * RES_TPB];
+            // (seven words at most inside one sector: no loop for them, the lanes of a warp have different counts)
+#pragma unroll
+            for (uint32_t j = 0; j < 7; ++j)
+              if (qa + j < qb) out[qa + j - A] = stg[((qa + j) & 15u) * RES_TPB];
+            for (uint32_t q = qa + 7u; q < qb; ++q) out[q - A] = stg[(q & 15u) * RES_TPB];  // (a short list that starts inside one sector and ends in the next)
           }
         }
         if (is_c) {
