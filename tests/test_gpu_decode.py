@@ -138,9 +138,9 @@ def test_graph_decode_matches_oracle(W, O, gpu, n, deg, params, seed):
 
 STRESS_TUNINGS = [
     dict(unit=37, k1_blocks=1, refill=1, k2_blocks=3),   # many tiny K1 units on one block; a K2 grid with long shares per block
-    dict(unit=5, refill=32, k2_blocks=1),
+    dict(unit=5, refill=32, k2_blocks=1, k2_batch=1),
     dict(unit=100000, k1_blocks=2, k2_blocks=5000),
-    dict(unit=64, refill=12),
+    dict(unit=128, refill=6, k2_batch=32),
 ]
 
 

@@ -43,6 +43,7 @@ struct Tuning {
   uint32_t refill = 10;       // K1: lanes that must be free before the warp fetches new nodes (swept: 3..16)
   uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
                               // equal share of the level, so a partial second wave would double the time
+  uint32_t k2_batch = 14;     // K2: lanes that must be free before the warp sets up new nodes (swept: 4..24)
   uint32_t e2e_chunk = 1u << 19;  // nodes per chunk of the pipelined host entry point
 };
 static Tuning g_tuning;
@@ -53,6 +54,7 @@ int set_tuning(const char* key, uint64_t value) {
   else if (k == "k1_blocks") g_tuning.k1_blocks = (uint32_t)value;
   else if (k == "refill") g_tuning.refill = (uint32_t)value;
   else if (k == "k2_blocks") g_tuning.k2_blocks = (uint32_t)value;
+  else if (k == "k2_batch") g_tuning.k2_batch = (uint32_t)value;
   else if (k == "e2e_chunk") g_tuning.e2e_chunk = (uint32_t)value;
   else if (k == "reset") g_tuning = Tuning();
   else return WGA_E_ARG;
@@ -560,7 +562,7 @@ __global__ void k_segments(const uint32_t* hist, uint32_t* seg) {
 
 // One level of phase two.  Lane-per-node state machine: every lane holds one node and emits ONE successor per
 // step -- the minimum of the three run heads -- so that all lanes of a warp run the same short merge step
-// regardless of how their lists are composed.  Lanes that finish a node wait until SETUP_BATCH lanes are free and
+// regardless of how their lists are composed.  Lanes that finish a node wait until setup_batch lanes are free and
 // then fetch + set up their next nodes together (the set-up is several dependent loads).  Each block owns a
 // contiguous share of the level's segment and hands its nodes out in order.
 //   record of node t (K1), contiguous in the record buffer:
@@ -570,7 +572,8 @@ __global__ void k_segments(const uint32_t* hist, uint32_t* seg) {
 constexpr uint32_t HS = 16;  // header words (copy-block ends, interval count, interval pairs) a lane caches in shared memory
 
 __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_t* order, const uint32_t* seg, uint32_t lb,
-                                                     uint32_t exact_level, const uint32_t* lev, uint32_t minint) {
+                                                     uint32_t exact_level, const uint32_t* lev, uint32_t minint,
+                                                     uint32_t setup_batch) {
   __shared__ uint32_t s_hdr[RES_TPB * (HS + 1)];
   __shared__ __align__(16) uint32_t s_stage[16 * RES_TPB];
   __shared__ uint32_t s_next;
@@ -588,7 +591,6 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
   if (cb >= ce) return;
   if (threadIdx.x == 0) s_next = cb;
   __syncthreads();
-  constexpr uint32_t SETUP_BATCH = 8;
   constexpr int STEPS_PER_VOTE = 2;  // merge steps between two scheduling votes
   enum { S_FETCH, S_MERGE, S_IDLE };
   int st = S_FETCH;
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
     const uint32_t fetchers = __ballot_sync(FULL, st == S_FETCH);
     const uint32_t mergers = __ballot_sync(FULL, st == S_MERGE);
     if ((fetchers | mergers) == 0) break;
-    if (fetchers && (mergers == 0 || __popc(fetchers) >= SETUP_BATCH)) {
+    if (fetchers && (mergers == 0 || __popc(fetchers) >= setup_batch)) {
       if (st == S_FETCH) {
         uint32_t i = atomicAdd(&s_next, 1u);
         uint32_t t = 0;
@@ -1094,6 +1096,7 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
   cub::DoubleBuffer<uint32_t> dvals((uint32_t*)(w + p.off_vals[0]), (uint32_t*)(w + p.off_vals[1]));
   const bool have_refs = g->prelude.compression_window != 0 || g->prelude.min_interval_length != 0;
   uint32_t grid = tn.k2_blocks;
+  const uint32_t k2_batch = std::max<uint32_t>(1u, std::min<uint32_t>(32u, tn.k2_batch));
   if (have_refs) {
     k_levels<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rv, dkeys.Current(), dvals.Current(), lev, sc->hist);
     count_launch();
@@ -1111,7 +1114,7 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
     }
     const uint32_t nlev = g->prelude.compression_window ? LCAP : 1;  // without references everything is level 0
     for (uint32_t l = 0; l < nlev; ++l) {
-      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, l, 0, lev, g->dev.min_interval);
+      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, l, 0, lev, g->dev.min_interval, k2_batch);
       count_launch();
     }
   } else {
@@ -1141,7 +1144,7 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
   //      launch per extra level over the shared deep segment
   if (have_refs && maxlevel >= LCAP) {
     for (uint32_t l = LCAP; l <= maxlevel; ++l) {
-      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, LCAP, l, lev, g->dev.min_interval);
+      k_resolve<<<grid, RES_TPB, 0, st>>>(rv, dvals.Current(), sc->seg, LCAP, l, lev, g->dev.min_interval, k2_batch);
       count_launch();
     }
     check_device_error(g, read_device_error(g, st), st);
