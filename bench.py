@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (generator kind, nodes, mean degree, seed)   shapes: reference README.md:72-79
     "eu-2015-host-shaped": ("web", 11_264_052, 34.3, 0x5EED0003),
-    "dblp-2011-shaped": ("social", 986_324, 6.8, 0x5EED0002),
+    "dblp-2011-shaped": ("coauthor", 986_324, 6.8, 0x5EED0002),
     "twitter-2010-shaped": ("social", 41_652_230, 35.3, 0x5EED0004),
     # one rank's share of the gsh-2015-shaped graph (988.5 M nodes / 33.9 G arcs over 8 GPUs): > 2^32 arcs per GPU
     "gsh-2015-shard": ("web", 123_561_336, 34.3, 0x5EED0005),
@@ -496,7 +496,7 @@ def main():
         acc += stages
     W.lib().wga_set_profiling(g._h, 0)
     acc /= reps
-    stage_names = ["heads+scans(k_heads,cub)", "entropy_decode(k_entropy)", "levels+sort(k_levels,cub)",
+    stage_names = ["heads+scans+plan(k_heads,cub,k_plan)", "entropy_decode(k_entropy)", "levels+sort(k_levels,cub)",
                    "resolve(k_resolve x levels)"]
     kernels = {stage_names[i]: float(acc[i]) for i in range(min(4, max(0, nev - 1)))}
     peak, peak_src = measured_peak_gbs()
@@ -505,7 +505,7 @@ def main():
     traffic, traffic_src = captured_traffic(args.workload) if world == 1 else (None, None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "kernel": "decode step = k_heads + 2 scans + k_entropy + k_levels + sort + k_resolve per level; one launch chain per step",
+                "kernel": "decode step = k_heads + 2 scans + k_plan + k_entropy + k_levels + sort + k_resolve per level; one launch chain per step",
                 "algorithmic_bytes_per_step": int(b_alg), "bytes_per_arc": b_alg / max(1, arcs),
                 "stage_ms": kernels, "step_ms_events": step_kernel_ms}
 

@@ -10,9 +10,8 @@
  *    reference (Rust)                                         this library
  *    -------------------------------------------------------  -------------------------
  *    ANSBvGraph::load      src/bvgraph/random_access.rs:52    wga_open / wga_open_mem
- *    ANSBvGraphSeq::load   src/bvgraph/sequential.rs:29       wga_open (flags WGA_OPEN_SEQ_ONLY
- *                                                              still needs .pointers/.states:
- *                                                              the GPU starts every node from its phase)
+ *    ANSBvGraphSeq::load   src/bvgraph/sequential.rs:29       wga_open (flags WGA_OPEN_SEQUENTIAL: .ans alone
+ *                                                              is enough, the phases are rebuilt at load)
  *    ANSModel4Decoder::new src/ans/models/model4decoder.rs:18 done inside wga_open (packed tables)
  *    graph.iter()          examples/bench_seq_access.rs:24    wga_decode_range (+ _host)
  *    graph.successors(v)   examples/bench_random_access.rs:35 wga_successors_batch (+ _host)
@@ -126,9 +125,14 @@ int wga_prelude(const wga_graph* g, wga_prelude_view* out);
 uint64_t wga_decode_workspace_size(const wga_graph* g, uint64_t first, uint64_t last);
 /* Decodes the successor lists of nodes [first,last) into CSR form:
  *   d_offsets[last-first+1] (u64, d_offsets[0]==0), d_succ[>= arcs of the range] (u32, ascending per node).
- * `succ_capacity` = elements available in d_succ; on return *h_arcs (optional, host) = arcs written
- * (forces a stream sync when non-NULL).  References that leave the range on the left are resolved by
- * re-decoding the needed predecessor nodes (halo) inside the workspace. */
+ * `succ_capacity` = elements available in d_succ; on return *h_arcs (optional, host) = arcs written.
+ * References that leave the range on the left are resolved by re-decoding the needed predecessor nodes (halo)
+ * inside the workspace.
+ * The kernels run on `stream`, but the call is NOT asynchronous: it returns after they have completed, because
+ * the host reads the totals and the error word (one stream synchronisation, two for sub-ranges with a halo and
+ * for reference chains deeper than six levels) to size-check the output and to report WGA_E_* codes.  A too
+ * small d_succ or workspace returns WGA_E_WORKSPACE ("need N elements" in wga_last_error) and writes nothing
+ * behind the given capacities. */
 int wga_decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offsets, uint32_t* d_succ,
                      uint64_t succ_capacity, void* d_workspace, uint64_t workspace_bytes, uint64_t* h_arcs,
                      void* stream);
@@ -171,6 +175,11 @@ uint64_t wga_successors_workspace_size(const wga_graph* g, uint64_t n_queries, u
 int wga_successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t n_queries, uint64_t* d_offsets,
                          uint32_t* d_succ, uint64_t succ_capacity, void* d_workspace, uint64_t workspace_bytes,
                          uint64_t* h_arcs, void* stream);
+/* Same with HOST arrays: copies the queries up, sizes, decodes into buffers owned by the handle (grow-only) and
+ * copies h_offsets[n_queries+1] and the successors back.  h_succ == NULL or a too small succ_capacity: only
+ * h_offsets and *h_arcs are produced and WGA_E_WORKSPACE is returned in the second case. */
+int wga_successors_batch_host(wga_graph* g, const uint64_t* h_nodes, uint64_t n_queries, uint64_t* h_offsets,
+                              uint32_t* h_succ, uint64_t succ_capacity, uint64_t* h_arcs);
 
 /* ---------------------------------------------------------------- debug / parity hooks ---------- */
 /* Expands the packed device tables of component c into the REFERENCE layout
@@ -182,8 +191,9 @@ int wga_debug_expand_table(wga_graph* g, int component, void* h_out, uint64_t n_
 int wga_debug_decode_symbols(wga_graph* g, const uint8_t* h_components, uint64_t n, uint64_t ptr, uint32_t state,
                              uint64_t* h_out, uint64_t* h_end_ptr, uint32_t* h_end_state);
 
-/* Kernel tuning knobs of the decode path (process-wide; the parity tests shrink them so that small graphs
- * cross unit boundaries, refill lanes one by one and stride the grid).  Keys: "unit", "k1_blocks", "refill",
+/* Kernel tuning knobs of the decode path (process-wide, for tests and profiling: every decode call takes one
+ * consistent snapshot of them under a lock; the parity tests shrink them so that small graphs cross unit
+ * boundaries, refill lanes one by one and stride the grid).  Keys: "unit", "k1_blocks", "refill",
  * "k2_blocks", "k2_batch", "e2e_chunk", "reset". */
 int wga_debug_set_tuning(const char* key, uint64_t value);
 

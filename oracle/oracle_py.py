@@ -83,7 +83,7 @@ def synth_graph(kind, n_nodes, mean_degree, seed, first=0, last=None, threads=No
     """Synthetic benchmark graph (tools/synth/synth_graph.hpp) -> (offsets u64, successors u32) of nodes [first,last)."""
     last = n_nodes if last is None else last
     threads = threads or (os.cpu_count() or 1)
-    k = {"web": 0, "social": 1}.get(kind, kind)
+    k = {"web": 0, "social": 1, "coauthor": 2}.get(kind, kind)
     arcs = C.c_uint64(0)
     off = np.zeros(last - first + 1, np.uint64)
     _chk(lib().wgo_synth_graph(k, C.c_uint64(n_nodes), C.c_double(mean_degree), C.c_uint64(seed), C.c_uint64(first),
@@ -97,7 +97,7 @@ def synth_graph(kind, n_nodes, mean_degree, seed, first=0, last=None, threads=No
 def synth_degrees(kind, n_nodes, mean_degree, seed, threads=None):
     """Number of arcs of a synthetic benchmark graph (degrees only)."""
     threads = threads or (os.cpu_count() or 1)
-    k = {"web": 0, "social": 1}.get(kind, kind)
+    k = {"web": 0, "social": 1, "coauthor": 2}.get(kind, kind)
     arcs = C.c_uint64(0)
     _chk(lib().wgo_synth_graph(k, C.c_uint64(n_nodes), C.c_double(mean_degree), C.c_uint64(seed), C.c_uint64(0),
                                C.c_uint64(n_nodes), C.c_int(threads), None, None, C.byref(arcs)))

@@ -275,6 +275,14 @@ def test_random_access_batch_matches_oracle(W, O, gpu, params):
     assert (g.successors(12345) == succ[off[12345]:off[12346]]).all()
     with pytest.raises(W.WgaError):
         g.successors_batch([20000])
+    # the host-buffer entry point (numpy in, numpy out), sizing call included
+    q = rng.integers(0, 20000, 3000)
+    h_off, h_succ = g.successors_batch_host(q)
+    exp = [succ[off[v]:off[v + 1]] for v in q]
+    assert (np.diff(h_off) == np.array([e.size for e in exp], np.uint64)).all() and (h_succ == np.concatenate(exp)).all()
+    with pytest.raises(W.WgaError) as e:
+        g.successors_batch_host(q, succ_capacity=max(1, h_succ.size // 2))
+    assert e.value.code == -6
 
 
 @pytest.mark.parametrize("kind,n,deg", [("web", 300_000, 34.3), ("social", 200_000, 35.3)])

@@ -5,8 +5,9 @@
 //                        it (-> BvComp copy blocks from one of the previous nodes), link runs of consecutive
 //                        ids inside nearby hosts (-> intervals) and a few far pages with power-law gaps
 //                        (-> residuals); LLP-like locality.
-//   kind 1  social-like: power-law out-degree (alpha ~ 2), targets drawn from a skewed popularity
-//                        distribution mixed with uniform ones -> large gaps, almost no copying.
+//   kind 1  social-like: power-law out-degree (alpha ~ 2); communities of 8 consecutive accounts share part of their
+//                        lists, most other targets are near the account, the rest popular or uniformly random.
+//   kind 2  co-authorship: the same with cliques inside the communities and almost only near targets.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -104,9 +105,43 @@ inline void web_list(uint64_t seed, uint64_t v, uint64_t N, double mean_degree, 
   out.erase(std::unique(out.begin(), out.end()), out.end());
 }
 
-inline void social_list(uint64_t seed, uint64_t v, uint64_t N, double mean_degree, std::vector<uint64_t>& out) {
+// Social-like lists.  Accounts of one community (8 consecutive ids, as a locality-preserving ordering such as LLP
+// leaves them) share part of their lists (-> some copying, as in co-authorship and follower graphs), most other
+// targets are near the account in id space (scale independent of the graph size, so that bit/link does not grow
+// with log N), the rest are popular accounts (small ids, very skewed) and uniformly random ones.
+constexpr uint64_t COMMUNITY = 8;
+
+struct SocialShape {
+  double near, popular;  // fractions of the targets near the account / among the popular accounts (rest: uniform)
+  double span;           // scale of the near gaps
+  double shared;         // size of the community's shared list relative to the mean degree
+  double keep;           // probability that a member keeps a shared target
+  bool clique;           // members of a community link to each other (co-authorship)
+  double degree_scale;   // calibration: duplicates removed from the lists
+};
+// kind 1: follower graph (twitter-2010-shaped) ; kind 2: co-authorship (dblp-2011-shaped)
+constexpr SocialShape SOCIAL_SHAPES[2] = {{0.62, 0.28, 65536.0, 0.35, 0.75, false, 1.23},
+                                          {0.85, 0.08, 4096.0, 0.70, 0.85, true, 1.28}};
+
+inline uint64_t social_target(Rng& r, uint64_t v, uint64_t N, const SocialShape& sh) {
+  const double c = r.unit();
+  if (c < sh.near) {  // near v: heavy-tailed gap, absolute scale
+    int64_t g = (int64_t)v + r.powerlaw_gap(sh.span);
+    return (uint64_t)(g < 0 ? -g : g) % N;
+  }
+  if (c < sh.near + sh.popular) {  // popular accounts: skewed towards small ids
+    const double x = r.unit();
+    const double x2 = x * x;
+    return (uint64_t)((double)N * x2 * x2 * x2) % N;
+  }
+  return r.below(N);
+}
+
+inline void social_list(uint64_t seed, uint64_t v, uint64_t N, double mean_degree, std::vector<uint64_t>& out,
+                        std::vector<uint64_t>& T, const SocialShape& sh) {
   out.clear();
   Rng r(seed, v, 3);
+  mean_degree *= sh.degree_scale;
   // Pareto degrees: alpha = 2 -> mean = 2*dmin ; capped so that one record cannot dominate the decode
   // E[min(Pareto(2, xm), cap)] = xm * (2 - xm / cap); 10 % of the accounts follow nobody
   double u = r.unit();
@@ -117,21 +152,22 @@ inline void social_list(uint64_t seed, uint64_t v, uint64_t N, double mean_degre
   if (d > cap) d = cap;
   uint64_t deg = (uint64_t)d;
   if (r.unit() < 0.1) deg = 0;
-  out.reserve(deg);
-  for (uint64_t i = 0; i < deg; ++i) {
-    double c = r.unit();
-    uint64_t t;
-    if (c < 0.55) {  // popular accounts: skewed towards small ids
-      double x = r.unit();
-      t = (uint64_t)((double)N * x * x * x);
-    } else if (c < 0.75) {  // community: near v
-      int64_t g = (int64_t)v + r.powerlaw_gap((double)N * 0.01);
-      t = (uint64_t)(g < 0 ? -g : g);
-    } else {
-      t = r.below(N);
-    }
-    out.push_back(t % N);
+  if (deg == 0) return;
+  // the community's shared targets: about a third of a typical list
+  const uint64_t com = v / COMMUNITY;
+  Rng rc(seed, com, 4);
+  T.clear();
+  const uint64_t shared = 1 + rc.geometric(mean_degree * sh.shared);
+  for (uint64_t i = 0; i < shared; ++i) T.push_back(social_target(rc, com * COMMUNITY, N, sh));
+  if (sh.clique) {
+    const uint64_t members = 2 + rc.below(COMMUNITY - 1);
+    for (uint64_t i = 0; i < members; ++i) T.push_back((com * COMMUNITY + i) % N);
   }
+  out.reserve(deg + 8);
+  uint64_t from_template = 0;
+  for (size_t i = 0; i < T.size() && from_template < deg; ++i)
+    if (T[i] != v && r.unit() < sh.keep) { out.push_back(T[i]); ++from_template; }
+  for (uint64_t i = from_template; i < deg; ++i) out.push_back(social_target(r, v, N, sh));
   std::sort(out.begin(), out.end());
   out.erase(std::unique(out.begin(), out.end()), out.end());
 }
@@ -141,13 +177,13 @@ inline void social_list(uint64_t seed, uint64_t v, uint64_t N, double mean_degre
 inline void synth_list(int kind, uint64_t seed, uint64_t v, uint64_t N, double mean_degree, std::vector<uint64_t>& out,
                 std::vector<uint64_t>& scratch) {
   if (kind == 0) detail::web_list(seed, v, N, mean_degree, out, scratch);
-  else detail::social_list(seed, v, N, mean_degree, out);
+  else detail::social_list(seed, v, N, mean_degree, out, scratch, detail::SOCIAL_SHAPES[kind - 1]);
 }
 
 // Fills CSR for nodes [first,last). h_succ == nullptr: count only (offsets still written when given).
 inline uint64_t synth_graph(int kind, uint64_t N, double mean_degree, uint64_t seed, uint64_t first, uint64_t last,
                      int threads, uint64_t* h_offsets, uint32_t* h_succ) {
-  if (kind != 0 && kind != 1) throw std::invalid_argument("unknown synthetic graph kind");
+  if (kind < 0 || kind > 2) throw std::invalid_argument("unknown synthetic graph kind");
   if (first > last || last > N) throw std::invalid_argument("bad node range");
   if (N >= (1ull << 32)) throw std::invalid_argument("synthetic graphs are limited to 2^32 nodes");
   if (threads < 1) threads = 1;

@@ -275,6 +275,21 @@ class BvGraph:
                                         C.c_uint64(workspace.numel()), C.byref(arcs), st))
         return arcs.value
 
+    def successors_batch_host(self, nodes, succ_capacity=None):
+        """wga_successors_batch_host: numpy in, numpy out -> (offsets u64[q+1], successors u32).  Without a capacity the
+        call is made twice (sizing, then the lists), like a caller that owns its buffers would."""
+        nodes = np.ascontiguousarray(nodes, np.uint64)
+        off = np.zeros(nodes.size + 1, np.uint64)
+        arcs = C.c_uint64(0)
+        if succ_capacity is None:
+            _chk(lib().wga_successors_batch_host(self._h, _np(nodes), C.c_uint64(nodes.size), _np(off), None,
+                                                 C.c_uint64(0), C.byref(arcs)))
+            succ_capacity = arcs.value
+        succ = np.zeros(max(1, succ_capacity), np.uint32)
+        _chk(lib().wga_successors_batch_host(self._h, _np(nodes), C.c_uint64(nodes.size), _np(off), _np(succ),
+                                             C.c_uint64(succ_capacity), C.byref(arcs)))
+        return off, succ[:arcs.value]
+
     def successors_workspace_size(self, n_queries, max_total_arcs):
         return int(lib().wga_successors_workspace_size(self._h, C.c_uint64(n_queries), C.c_uint64(max_total_arcs)))
 
@@ -552,7 +567,7 @@ def synth_graph(kind, n_nodes, mean_degree, seed, first=0, last=None, threads=No
     """Synthetic graph of a benchmark shape -> (offsets u64, successors u32) of nodes [first,last)."""
     last = n_nodes if last is None else last
     threads = threads or (os.cpu_count() or 1)
-    k = {"web": 0, "social": 1}.get(kind, kind)
+    k = {"web": 0, "social": 1, "coauthor": 2}.get(kind, kind)
     arcs = C.c_uint64(0)
     off = np.zeros(last - first + 1, np.uint64)
     _chk(lib().wga_synth_graph(k, C.c_uint64(n_nodes), C.c_double(mean_degree), C.c_uint64(seed), C.c_uint64(first),

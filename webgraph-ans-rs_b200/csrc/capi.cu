@@ -412,6 +412,56 @@ int wga_successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t n_queri
   });
 }
 
+int wga_successors_batch_host(wga_graph* g, const uint64_t* h_nodes, uint64_t n_queries, uint64_t* h_offsets,
+                              uint32_t* h_succ, uint64_t succ_capacity, uint64_t* h_arcs) {
+  return guarded([&] {
+    if (!g || (!h_nodes && n_queries) || !h_offsets) throw Error(WGA_E_ARG, "null argument");
+    if (!g->on_device) throw Error(WGA_E_CUDA, "graph was opened host-only");
+    if (g->up_pending) {
+      WGA_CUDA(cudaStreamSynchronize(g->s_up));
+      g->up_pending = false;
+    }
+    // grow-only device buffers of the handle: queries + offsets share e2e_off, the lists use e2e_succ, e2e_ws
+    const uint64_t n_off = 2 * n_queries + 2;
+    if (g->e2e_off_n < n_off) {
+      if (g->e2e_off) cudaFree(g->e2e_off);
+      g->e2e_off = nullptr; g->e2e_off_n = 0;
+      WGA_CUDA(cudaMalloc((void**)&g->e2e_off, n_off * 8));
+      g->e2e_off_n = n_off;
+    }
+    uint64_t* d_q = g->e2e_off;
+    uint64_t* d_off = g->e2e_off + n_queries + 1;
+    auto need_ws = [&](uint64_t bytes) {
+      if (g->e2e_ws_bytes < bytes) {
+        if (g->e2e_ws) cudaFree(g->e2e_ws);
+        g->e2e_ws = nullptr; g->e2e_ws_bytes = 0;
+        WGA_CUDA(cudaMalloc(&g->e2e_ws, bytes));
+        g->e2e_ws_bytes = bytes;
+      }
+    };
+    if (n_queries) WGA_CUDA(cudaMemcpyAsync(d_q, h_nodes, n_queries * 8, cudaMemcpyHostToDevice, 0));
+    uint64_t arcs = 0;
+    need_ws(successors_workspace_size(g, n_queries, 0));
+    successors_batch(g, d_q, n_queries, d_off, nullptr, 0, g->e2e_ws, g->e2e_ws_bytes, &arcs, 0);  // sizing call
+    if (h_arcs) *h_arcs = arcs;
+    const bool want = h_succ && succ_capacity >= arcs;
+    if (want && arcs) {
+      if (g->e2e_succ_n < arcs + 1024) {
+        if (g->e2e_succ) cudaFree(g->e2e_succ);
+        g->e2e_succ = nullptr; g->e2e_succ_n = 0;
+        WGA_CUDA(cudaMalloc((void**)&g->e2e_succ, (arcs + 1024) * 4));
+        g->e2e_succ_n = arcs + 1024;
+      }
+      need_ws(successors_workspace_size(g, n_queries, arcs));
+      successors_batch(g, d_q, n_queries, d_off, g->e2e_succ, g->e2e_succ_n, g->e2e_ws, g->e2e_ws_bytes, &arcs, 0);
+      WGA_CUDA(cudaMemcpyAsync(h_succ, g->e2e_succ, arcs * 4, cudaMemcpyDeviceToHost, 0));
+    }
+    WGA_CUDA(cudaMemcpyAsync(h_offsets, d_off, (n_queries + 1) * 8, cudaMemcpyDeviceToHost, 0));
+    WGA_CUDA(cudaStreamSynchronize(0));
+    if (h_succ && !want) throw Error(WGA_E_WORKSPACE, "h_succ too small: need " + std::to_string(arcs) + " elements");
+  });
+}
+
 // ----------------------------------------------------------------------------------------- debug
 int wga_debug_expand_table(wga_graph* g, int component, void* h_out, uint64_t n_slots) {
   return guarded([&] {

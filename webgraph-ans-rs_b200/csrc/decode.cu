@@ -47,9 +47,15 @@ struct Tuning {
   uint32_t e2e_chunk = 1u << 19;  // nodes per chunk of the pipelined host entry point
 };
 static Tuning g_tuning;
+static std::mutex g_tuning_mu;  // wga_debug_set_tuning may race with decode calls of other threads
+static Tuning tuning_snapshot() {
+  std::lock_guard<std::mutex> lk(g_tuning_mu);
+  return g_tuning;
+}
 
 int set_tuning(const char* key, uint64_t value) {
   std::string k(key ? key : "");
+  std::lock_guard<std::mutex> lk(g_tuning_mu);
   if (k == "unit") g_tuning.unit = (uint32_t)value;
   else if (k == "k1_blocks") g_tuning.k1_blocks = (uint32_t)value;
   else if (k == "refill") g_tuning.refill = (uint32_t)value;
@@ -60,7 +66,7 @@ int set_tuning(const char* key, uint64_t value) {
   else return WGA_E_ARG;
   return WGA_OK;
 }
-uint64_t tuning_e2e_chunk() { return g_tuning.e2e_chunk; }
+uint64_t tuning_e2e_chunk() { return tuning_snapshot().e2e_chunk; }
 
 namespace {
 
@@ -1195,7 +1201,7 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
     return;
   }
   apply_env_tuning();
-  const Tuning tn = g_tuning;
+  const Tuning tn = tuning_snapshot();
   uint8_t* w = (uint8_t*)ws;
   if (ws_bytes < 256) throw Error(WGA_E_WORKSPACE, "workspace too small");
   WGA_CUDA(cudaMemsetAsync(w, 0, 256, st));
@@ -1274,7 +1280,7 @@ BatchPlan plan_batch(uint64_t nq, uint64_t max_total_arcs, uint32_t unit) {
 }  // namespace
 
 uint64_t successors_workspace_size(const wga_graph* g, uint64_t n_queries, uint64_t max_total_arcs) {
-  return plan_batch(n_queries, max_total_arcs, effective_unit(g_tuning)).total;
+  return plan_batch(n_queries, max_total_arcs, effective_unit(tuning_snapshot())).total;
 }
 
 void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64_t* d_offsets, uint32_t* d_succ,
@@ -1287,7 +1293,7 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
     return;
   }
   apply_env_tuning();
-  const Tuning tn = g_tuning;
+  const Tuning tn = tuning_snapshot();
   const uint32_t unit = effective_unit(tn);
   // the caller sizes the workspace with an upper bound of the arcs it expects; recover it from the size
   BatchPlan b = plan_batch(nq, 0, unit);
