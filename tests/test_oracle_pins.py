@@ -146,3 +146,66 @@ def test_decodes_correctly_sequential_and_random_access_graph(O, params):
     if params == (7, 3, 4):  # SURVEY 8a "chosen models"
         assert [m[:3] for m in anchors["models"]] == [[16, 5, 2], [6, 1, 3], [12, 3, 1], [13, 1, 6], [11, 1, 3],
                                                       [16, 10, 1], [11, 1, 6], [16, 10, 1], [16, 10, 1]]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Two restatements that were written separately must agree: tests/golden/restate_ans.py is a plain-Python
+# restatement of the reference's model builder / encoder / decoder made from the Rust sources, not from the oracle.
+def _tables_sha(tables):
+    parts = []
+    for t in tables:
+        e = t["entries"]
+        a = np.empty((e.size, 3), np.uint32)
+        a[:, 0], a[:, 1], a[:, 2] = e["freq"], e["cumul_freq"], e["upperbound"]
+        parts.append(a.tobytes())
+    return hashlib.sha256(b"".join(parts)).hexdigest()
+
+
+def _restated():
+    return json.load(open(os.path.join(GOLDEN, "cnr2000_restated.json")))
+
+
+def test_python_restatement_and_oracle_agree_on_cnr2000_anchors():
+    """Whole cnr-2000, CLI defaults: models, stream, final state and phases of the oracle's store (cnr2000_full.json,
+    written by make_golden.py) equal what the independent Python restatement produced from the same symbol stream
+    (cnr2000_restated.json, written by restate_ans.py)."""
+    a = json.load(open(os.path.join(GOLDEN, "cnr2000_full.json")))["w7_r3_l4"]
+    b = _restated()["w7_r3_l4"]
+    for k in ("models", "stream_bytes", "final_state", "stream_sha256", "states_sha256", "pointers_sha256", "symbols"):
+        assert a[k] == b[k], k
+
+
+@needs_ref
+def test_oracle_tables_equal_the_python_restatement_on_cnr2000(O):
+    off, succ, _ = O.read_bvgraph(REF_CNR)
+    g = O.OracleGraph.store_csr(off, succ, 7, 3, 4)
+    assert _tables_sha(g.tables()) == _restated()["w7_r3_l4"]["tables_sha256"]
+
+
+@pytest.mark.parametrize("name", ["dummy", "folding", "zipf"])
+def test_oracle_equals_the_python_restatement_on_small_sequences(O, name):
+    """The known-answer style inputs of tests/compressor_tests.rs: tables, stream and final state, oracle (C++) against
+    the committed output of the Python restatement -- and, for the smallest one, against the restatement run live."""
+    rng = np.random.default_rng(7)
+    seqs = {"dummy": [1, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 5] * 3,
+            "folding": [int(x) for x in rng.integers(0, 1 << 20, 400)],
+            "zipf": [int(x) for x in np.minimum(rng.zipf(1.2, 3000), 1 << 30)]}
+    seq = seqs[name]
+    exp = _restated()["seq_" + name]
+    assert hashlib.sha256(np.array(seq, np.uint64).tobytes()).hexdigest() == exp["input_sha256"]
+    comps, syms = np.zeros(len(seq), np.uint8), np.array(seq, np.uint64)
+    g = O.OracleGraph()
+    g.build_model(comps, syms)
+    g.encode_symbols(comps[::-1].copy(), syms[::-1].copy())  # (the store replays the symbols last to first)
+    assert [[t["frame_size"], t["fidelity"], t["radix"], len(t["entries"])] for t in g.tables()] == exp["models"]
+    assert _tables_sha(g.tables()) == exp["tables_sha256"]
+    assert g.info()["state"] == exp["final_state"] and g.info()["stream_len"] * 2 == exp["stream_bytes"]
+    assert hashlib.sha256(g.stream().tobytes()).hexdigest() == exp["stream_sha256"]
+    if name == "dummy":
+        import sys
+        sys.path.insert(0, GOLDEN)
+        import restate_ans as R
+        models, stream, state, _, _ = R.store_symbols([0] * len(seq), seq)
+        assert R.digest(models, stream, state, [], [])["stream_sha256"] == exp["stream_sha256"] and state == exp["final_state"]
+        dec = R.Decoder(models, stream, state)
+        assert [dec.decode(0) for _ in seq] == seq

@@ -1,3 +1,3 @@
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 900 python bench.py > gpurun_out/bench_r02_final.json 2> gpurun_out/bench_r02_final.err; tail -3 gpurun_out/bench_r02_final.err
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 2 --warmup 3 --no-verify --no-cpu-baseline --no-model-leg --random-nodes 0 --e2e-steps 1 > gpurun_out/ncu_launches.log 2>&1; tail -2 gpurun_out/ncu_launches.log
+timeout 1500 python bench.py --workload twitter-2010-shaped --random-nodes 10000000 --steps 5 > gpurun_out/bench_r02_twitter.json 2> gpurun_out/bench_r02_twitter.err; tail -4 gpurun_out/bench_r02_twitter.err
+timeout 600 python bench.py --workload dblp-2011-shaped --steps 20 > gpurun_out/bench_r02_dblp.json 2> gpurun_out/bench_r02_dblp.err; tail -3 gpurun_out/bench_r02_dblp.err
