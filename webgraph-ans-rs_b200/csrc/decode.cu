@@ -1138,7 +1138,9 @@ static void run_pipeline(wga_graph* g, RangeView& rv, uint8_t* w, const Workspac
   const uint32_t herr = (uint32_t)g->h_pub[4];
   if (tot[0] > rv.halo_cap) {
     if (herr) WGA_CUDA(cudaMemsetAsync(g->d_err, 0, 4, st));
-    throw Error(WGA_E_WORKSPACE, "halo successors exceed the workspace");
+    throw Error(WGA_E_WORKSPACE, "the " + std::to_string(rv.h) + " predecessor nodes this range references (halo) have " +
+                                     std::to_string(tot[0]) + " successors, the workspace holds " + std::to_string(rv.halo_cap) +
+                                     ": decode a range that starts " + std::to_string(rv.h) + " nodes earlier");
   }
   if (tot[1] - tot[0] > rv.succ_cap) {
     g->last_need_succ = tot[1] - tot[0];
@@ -1221,7 +1223,10 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
   const uint64_t n = last - lo;
   const uint32_t unit = effective_unit(tn);
   WorkspacePlan p = plan_workspace(n);
-  if (ws_bytes < p.fixed_bytes + 4096) throw Error(WGA_E_WORKSPACE, "workspace too small");
+  if (ws_bytes < p.fixed_bytes + 4096)
+    throw Error(WGA_E_WORKSPACE, "workspace too small: the range needs " + std::to_string(p.fixed_bytes + 4096) +
+                                     " bytes before the record buffer (it references " + std::to_string(first - lo) +
+                                     " predecessor nodes; wga_decode_workspace_size allows for 4096)");
   RangeView rv{};
   rv.lo = lo; rv.n = (uint32_t)n; rv.h = (uint32_t)(first - lo);
   bind_views(rv, w, p, sc, ws_bytes, unit);
