@@ -623,8 +623,8 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    # the box's copy floor for these bytes: the same D2H and H2D volumes as plain pinned copies on two streams, all
-    # ranks at the same time
+    # the box's copy floor for these bytes: the same D2H (successors + offsets) and H2D volumes as plain pinned copies
+    # on two streams, all ranks at the same time
     barrier()
     s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
     h_in = torch.empty(max(1, h2d), dtype=torch.uint8).pin_memory()
@@ -639,6 +639,7 @@ def main():
             d_in.copy_(h_in, non_blocking=True)
         with torch.cuda.stream(s_dn):
             h_tmp[:arcs].copy_(succ[:arcs], non_blocking=True)
+            h_off.copy_(off, non_blocking=True)  # (the offsets are part of the result: d2h_bytes_per_step counts them)
         torch.cuda.synchronize()
         floor.append(time.perf_counter() - t0)
     floor_s = min(floor[1:])
