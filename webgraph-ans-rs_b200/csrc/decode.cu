@@ -8,21 +8,25 @@
 //      -> ANSDecoder::decode(component)              src/ans/decoder.rs:58-100
 //  Pipeline (all launches on the caller's stream):
 //    K0  k_heads       one lane per node, every lane at the same symbol: the fixed-shape head of every record from
-//                      (states[N-1-v], pointers[N-1-v]) -- outdegree, reference offset, block count -- and the
-//                      decoder state after it
-//        cub scans     outdegrees -> CSR offsets ; (block count + 1 + outdegree) -> record regions
+//                      (states[N-1-v], pointers[N-1-v]) -- outdegree, reference offset, block count -- the decoder
+//                      state after it, the prefetched next stream word and the phase the record must end at
+//        cub scans     outdegrees -> CSR offsets ; (block count + 2 + outdegree) -> record regions
+//        k_plan        one thread per node: slot and record pointers, outdegree of the referenced node, head
+//                      validation -- so that K1's per-node set-up is three independent loads
 //    K1  k_entropy     phase one: entropy decode of the rest of every record.  Persistent kernel, one 1024-thread
 //                      block per SM with the decoder tables of the six components in SHARED memory (bucket +
 //                      popcount lookup, no search).  Warps are independent: each pulls units of consecutive nodes
 //                      from a global counter, its lanes take the nodes one by one (ballot-ranked, no atomics) and
 //                      run a per-symbol state machine; every busy lane decodes ONE symbol per iteration and
-//                      appends one word to its node's record (cumulative copy-block ends, interval count, interval
-//                      starts / lengths, prefix-summed residuals).  Reference-free lists without intervals are
-//                      written straight into their CSR slot and are final after K1.
+//                      stores one word: cumulative copy-block ends, interval count, interval starts / lengths into
+//                      the node's record, prefix-summed residuals into the tail of the node's own CSR slot.
+//                      Reference-free lists without intervals are final after K1.  Every record must end exactly
+//                      at the phase of the next node: that is the corruption check.
 //    K2  k_levels      phase two, by reference-chain depth: depth of every node that still needs work
 //        cub sort      stable sort by level -> one segment per level, node order kept inside a level
 //        k_resolve     per level, one node per lane: three-way merge (copied elements of the finished
-//                      referenced list, expanded intervals, residuals) into the node's CSR slot
+//                      referenced list, expanded intervals, residuals) into the node's CSR slot, up to four
+//                      elements of one run per step, output staged per lane and written as whole sectors
 //    Random access (wga_successors_batch) runs the same kernels on the sorted reference closure of the
 //    query nodes (node-list mode) and gathers the query lists.
 // =============================================================================
