@@ -42,6 +42,7 @@ WORKLOADS = {
     # one rank's share of the gsh-2015-shaped graph (988.5 M nodes / 33.9 G arcs over 8 GPUs): > 2^32 arcs per GPU
     "gsh-2015-shard": ("web", 123_561_336, 34.3, 0x5EED0005),
     "web-1m": ("web", 1_000_000, 34.3, 0x5EED0010),
+    "social-4m": ("social", 4_000_000, 35.3, 0x5EED0012),
     "tiny": ("web", 100_000, 34.3, 0x5EED0011),
 }
 BVCOMP = dict(compression_window=7, max_ref_count=3, min_interval_length=4)  # CLI defaults

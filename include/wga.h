@@ -194,7 +194,7 @@ int wga_debug_decode_symbols(wga_graph* g, const uint8_t* h_components, uint64_t
 /* Kernel tuning knobs of the decode path (process-wide, for tests and profiling: every decode call takes one
  * consistent snapshot of them under a lock; the parity tests shrink them so that small graphs cross unit
  * boundaries, refill lanes one by one and stride the grid).  Keys: "unit", "k1_blocks", "refill",
- * "k2_blocks", "k2_batch", "e2e_chunk", "reset". */
+ * "k2_blocks", "k2_batch", "hub_min", "e2e_chunk", "reset". */
 int wga_debug_set_tuning(const char* key, uint64_t value);
 
 /* ---------------------------------------------------------------- model build -------------------- */

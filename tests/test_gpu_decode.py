@@ -141,6 +141,8 @@ STRESS_TUNINGS = [
     dict(unit=5, refill=32, k2_blocks=1, k2_batch=1),
     dict(unit=100000, k1_blocks=2, k2_blocks=5000),
     dict(unit=128, refill=6, k2_batch=32),
+    dict(hub_min=1),                                      # every list that needs K2 is merged by a whole warp
+    dict(hub_min=9, k2_blocks=2),
 ]
 
 

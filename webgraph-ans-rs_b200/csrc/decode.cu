@@ -48,6 +48,7 @@ struct Tuning {
   uint32_t k2_blocks = 0;     // K2 grid; 0 = one full wave (SM count x resident blocks per SM): every block gets an
                               // equal share of the level, so a partial second wave would double the time
   uint32_t k2_batch = 14;     // K2: lanes that must be free before the warp sets up new nodes (swept: 4..24)
+  uint32_t hub_min = 2048;    // K2: lists at least this long are merged by a whole warp (k_resolve, hub pass)
   uint32_t e2e_chunk = 1u << 19;  // nodes per chunk of the pipelined host entry point
 };
 static Tuning g_tuning;
@@ -65,6 +66,7 @@ int set_tuning(const char* key, uint64_t value) {
   else if (k == "refill") g_tuning.refill = (uint32_t)value;
   else if (k == "k2_blocks") g_tuning.k2_blocks = (uint32_t)value;
   else if (k == "k2_batch") g_tuning.k2_batch = (uint32_t)value;
+  else if (k == "hub_min") g_tuning.hub_min = (uint32_t)value;
   else if (k == "e2e_chunk") g_tuning.e2e_chunk = (uint32_t)value;
   else if (k == "reset") g_tuning = Tuning();
   else return WGA_E_ARG;
@@ -108,6 +110,9 @@ struct RangeView {
   uint32_t* recs;     // record buffer
   uint64_t recs_cap;  // words
   uint32_t* maxlevel;   // deepest reference chain seen by k_levels (only tracked from LCAP up)
+  uint2* hubs;          // (node, level) of the long lists that K2 merges with a whole warp each
+  uint32_t* hub_count;
+  uint32_t hub_min;
   uint32_t* unit_ctr;
   uint32_t unit;        // nodes per K1 unit
   uint32_t n_units;
@@ -467,6 +472,33 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
         }
       }
     } else if (busy == 0) break;
+    // ---------------------------------------------------------------- long residual runs
+    // When every busy lane of the warp is deep inside a run of residuals (the hubs of power-law graphs, typically
+    // alone in their warp at the end) and no refill is due, 32 symbols are decoded in a loop that is only the
+    // symbol decode and the running sum: a record is one serial chain, so what counts for it is the latency of
+    // one iteration, and the general step below is four times longer.
+    {
+      const bool inrun = c == S_RES && extras > 32u;
+      if (__all_sync(FULL, c == S_FREE || inrun) && (exhausted || 32u - (uint32_t)__popc(busy) < refill_min)) {
+        if (inrun) {
+          uint32_t err = 0;
+          const uint4 cp = s_cp[S_RES];
+          uint32_t* const wp = slot_end - extras;
+#pragma unroll 1
+          for (int i = 0; i < 32; ++i) {
+            prev += 1u + (uint32_t)ans_decode_cp(cp, tab, dc, stream, err);
+            wp[i] = prev;
+          }
+          extras -= 32u;
+          if (err) {
+            atomicOr(rv.err, ERR_CORRUPT);
+            rv.meta[t] = MF_ERR << 29;
+            c = S_FREE;
+          }
+        }
+        continue;
+      }
+    }
     // ---------------------------------------------------------------- one symbol per busy lane
     if (c != S_FREE) {
       uint32_t err = 0;
@@ -531,6 +563,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_entropy(DevGraph g, RangeView
 constexpr uint32_t LCAP = 6;       // levels 0..LCAP-1 have their own segment; deeper nodes share segment LCAP
 constexpr uint32_t KEY_SKIP = 15;  // level bucket of nodes that are final after K1
 constexpr int RES_TPB = 128;
+constexpr uint32_t HUB_CAP = 1u << 16;  // entries of the hub list (more hubs than that take the per-lane path)
 
 __global__ void __launch_bounds__(256) k_levels(RangeView rv, uint8_t* keys, uint32_t* vals, uint32_t* lev_out, uint32_t* hist) {
   __shared__ uint32_t s_hist[16];
@@ -550,6 +583,10 @@ __global__ void __launch_bounds__(256) k_levels(RangeView rv, uint8_t* keys, uin
       }
       lb = min(lev, LCAP);
       lev_out[t] = lev;
+      if (rv.outdeg[t] >= rv.hub_min) {  // long list: out of the level segments, into the hub list
+        const uint32_t slot = atomicAdd(rv.hub_count, 1u);
+        if (slot < HUB_CAP) { rv.hubs[slot] = make_uint2(t, lev); lb = KEY_SKIP; }
+      }
     }
     keys[t] = (uint8_t)lb;
     vals[t] = t;
@@ -581,6 +618,86 @@ __global__ void k_segments(const uint32_t* hist, uint32_t* seg) {
 //   before the write position reaches them (written <= copied + interval elements + residuals consumed).
 constexpr uint32_t HS = 16;  // header words (copy-block ends, interval count, interval pairs) a lane caches in shared memory
 
+// A long list merged by a whole warp (all lanes call this with the same node).  Same three runs as the per-lane
+// merge; per round the run with the smallest head emits as many of its next 32 elements as are below the heads of the
+// other two runs, with coalesced loads and stores.  A lane-serial merge of a hub of 10^5 successors is 10^5
+// dependent steps on one lane while the rest of the level waits for it; hubs have long runs, so this is ~30x fewer.
+__device__ void resolve_hub(const RangeView& rv, uint32_t t, uint32_t minint) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint4 nr = rv.nrec[t];
+  const uint32_t m = rv.meta[t];
+  const uint32_t* recp = rv.recs + rv.roff[t];
+  const uint32_t rt = nr.w & RT_MASK, ns = m & NSYM_MAX, fl = m >> 29;
+  const uint32_t d = nr.z, b = nr.w >> RT_BITS;
+  uint32_t* const out = node_slot(rv, t);
+  const uint32_t* ref = nullptr;
+  uint32_t dref = 0;
+  if (rt) {
+    ref = node_slot(rv, t - rt);
+    dref = rv.outdeg[t - rt];
+  }
+  if (!out || (rt && !ref)) {
+    if (lane == 0) atomicOr(rv.err, ERR_WORKSPACE);
+    return;
+  }
+  uint32_t ni = 0, H = b;
+  if (ns > b && minint) { ni = recp[b]; H = b + 1; }
+  if (ns < H || 2 * (uint64_t)ni > (uint64_t)(ns - H)) return;  // inconsistent record (K1 reported it)
+  uint32_t ip = H;
+  const uint32_t iend = H + 2 * ni;
+  uint32_t nres = 0;
+  if (fl & MF_INSLOT) {
+    nres = ns > iend ? recp[iend] : 0u;
+    if (nres > d) return;
+  }
+  const uint32_t* const res = out + (d - nres);
+  uint32_t p = 0, rj = 0, kb = 0, ci = 0, cend = 0, ival = INF, ilim = 0;
+  if (ni) { ival = recp[ip]; ilim = ival + recp[ip + 1]; ip += 2; }
+  auto next_copy_block = [&]() {
+    for (;;) {
+      kb += 2;
+      if (kb - 1 >= b) { ci = cend = dref; return; }
+      ci = min(recp[kb - 1], dref);
+      cend = kb < b ? min(recp[kb], dref) : dref;
+      if (ci < cend) return;
+    }
+  };
+  if (rt) {
+    cend = b ? min(recp[0], dref) : dref;
+    if (ci >= cend) next_copy_block();
+  }
+  while (p < d) {
+    const uint32_t cval = ci < cend ? ref[ci] : INF;
+    const uint32_t rval = rj < nres ? res[rj] : INF;
+    const uint32_t mn = min(cval, min(ival, rval));
+    if (mn == INF) {  // (corrupt record: the runs end before the list is full)
+      for (uint32_t q = p + lane; q < d; q += 32) out[q] = INF;
+      return;
+    }
+    const bool is_c = mn == cval, is_r = !is_c && mn == rval;
+    const uint32_t other = is_c ? min(ival, rval) : is_r ? min(cval, ival) : min(cval, rval);
+    uint32_t avail, cand = INF;
+    if (is_c) { avail = cend - ci; if (lane < avail) cand = ref[ci + lane]; }
+    else if (is_r) { avail = nres - rj; if (lane < avail) cand = res[rj + lane]; }
+    else { avail = ilim - ival; if (lane < avail) cand = ival + lane; }
+    const uint32_t okm = __ballot_sync(FULL, lane == 0 || (lane < avail && cand < other));
+    uint32_t n = okm == FULL ? 32u : (uint32_t)__ffs((int)~okm) - 1u;  // leading lanes that go out
+    n = min(n, d - p);
+    if (lane < n) out[p + lane] = cand;
+    p += n;
+    if (is_c) {
+      ci += n;
+      if (ci == cend) next_copy_block();
+    } else if (is_r) rj += n;
+    else {
+      ival += n;
+      if (ival == ilim) {
+        if (ip < iend) { ival = recp[ip]; ilim = ival + recp[ip + 1]; ip += 2; } else ival = INF;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_t* order, const uint32_t* seg, uint32_t lb,
                                                      uint32_t exact_level, const uint32_t* lev, uint32_t minint,
                                                      uint32_t setup_batch) {
@@ -594,6 +711,15 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
   // (lts__t_tag_requests 71 %).  Only the partial sectors at the two ends of a list are written word by word.
   uint32_t* const stg = s_stage + threadIdx.x;
   uint32_t A = 0;  // word offset of the slot inside its sector: list position p lives at sector position A + p
+  {  // the long lists of this level first (they take the longest): one warp each
+    const uint32_t nh = min(*rv.hub_count, HUB_CAP);
+    const uint32_t want = exact_level ? exact_level : lb;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < nh; h += nw) {
+      const uint2 e = rv.hubs[h];
+      if (e.y == want) resolve_hub(rv, e.x, minint);
+    }
+  }
   const uint32_t beg = seg[lb], end = seg[lb + 1];
   const uint32_t len = end - beg;
   const uint32_t share = (len + gridDim.x - 1) / gridDim.x;
@@ -905,11 +1031,12 @@ struct Scalars {
   uint32_t maxlevel;
   uint32_t hist[16];          // nodes per level bucket
   uint32_t seg[17];           // exclusive prefix of hist
+  uint32_t hub_count;
 };
 static_assert(sizeof(Scalars) <= 256, "Scalars must fit the cleared line");
 
 struct WorkspacePlan {
-  uint64_t off_outdeg, off_nrec, off_nrec2, off_offs, off_roff, off_meta, off_plan, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_recs;
+  uint64_t off_outdeg, off_nrec, off_nrec2, off_offs, off_roff, off_meta, off_plan, off_hubs, off_lev, off_keys[2], off_vals[2], off_cub, off_halo, off_recs;
   uint64_t cub_bytes, halo_cap, fixed_bytes;
 };
 
@@ -924,6 +1051,7 @@ WorkspacePlan plan_workspace(uint64_t n) {
   p.off_roff = o; o = align_up(o + 8 * (n + 1), 256);
   p.off_meta = o; o = align_up(o + 4 * n, 256);
   p.off_plan = o; o = align_up(o + sizeof(NodePlan) * n, 256);
+  p.off_hubs = o; o = align_up(o + 8ull * HUB_CAP, 256);
   p.off_lev = o; o = align_up(o + 4 * n, 256);
   for (int i = 0; i < 2; ++i) { p.off_keys[i] = o; o = align_up(o + n, 256); }
   for (int i = 0; i < 2; ++i) { p.off_vals[i] = o; o = align_up(o + 4 * n, 256); }
@@ -1180,12 +1308,16 @@ static void apply_env_tuning() {
   });
 }
 
-static void bind_views(RangeView& rv, uint8_t* w, const WorkspacePlan& p, Scalars* sc, uint64_t ws_bytes, uint32_t unit) {
+static void bind_views(RangeView& rv, uint8_t* w, const WorkspacePlan& p, Scalars* sc, uint64_t ws_bytes, uint32_t unit,
+                       uint32_t hub_min) {
+  rv.hub_min = hub_min ? hub_min : 1u;
   rv.outdeg = (uint32_t*)(w + p.off_outdeg);
   rv.nrec = (uint4*)(w + p.off_nrec);
   rv.nrec2 = (uint4*)(w + p.off_nrec2);
   rv.meta = (uint32_t*)(w + p.off_meta);
   rv.maxlevel = &sc->maxlevel;
+  rv.hubs = (uint2*)(w + p.off_hubs);
+  rv.hub_count = &sc->hub_count;
   rv.roff = (uint64_t*)(w + p.off_roff);
   rv.recs = (uint32_t*)(w + p.off_recs);
   rv.recs_cap = (ws_bytes - p.off_recs) / 4;
@@ -1233,7 +1365,7 @@ void decode_range(wga_graph* g, uint64_t first, uint64_t last, uint64_t* d_offse
                                      " predecessor nodes; wga_decode_workspace_size allows for 4096)");
   RangeView rv{};
   rv.lo = lo; rv.n = (uint32_t)n; rv.h = (uint32_t)(first - lo);
-  bind_views(rv, w, p, sc, ws_bytes, unit);
+  bind_views(rv, w, p, sc, ws_bytes, unit, tn.hub_min);
   rv.offs = rv.h ? (uint64_t*)(w + p.off_offs) : d_offsets;
   rv.succ = d_succ; rv.succ_cap = d_succ ? succ_capacity : 0;
   rv.err = g->d_err;
@@ -1373,7 +1505,7 @@ void successors_batch(wga_graph* g, const uint64_t* d_nodes, uint64_t nq, uint64
   Scalars* sc = (Scalars*)iw;
   RangeView rv{};
   rv.lo = 0; rv.n = nU; rv.h = 0; rv.nodes = U;
-  bind_views(rv, iw, p, sc, b.inner_bytes, unit);
+  bind_views(rv, iw, p, sc, b.inner_bytes, unit, tn.hub_min);
   rv.offs = (uint64_t*)(w + b.off_offsU);
   rv.halo_succ = nullptr; rv.halo_cap = 0;
   rv.succ = (uint32_t*)(w + b.off_succU); rv.succ_cap = b.cap_arcs;
