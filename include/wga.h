@@ -237,6 +237,21 @@ int wga_bvcomp_symbols_range(const uint64_t* h_offsets, const uint32_t* h_succ, 
                              uint64_t compression_window, uint64_t max_ref_count, uint64_t min_interval_length,
                              const wga_component_model* estimator_tables, uint64_t chunk_nodes, int threads,
                              wga_symbols** out);
+/* Same result, with the candidate-reference costing and the reference selection on the GPU (SURVEY.md 8f rank 2;
+ * replaces the per-candidate estimator calls of BvComp, entropy_estimator.rs:81-113 via random_access.rs:108-125): one
+ * device thread per (node, reference offset) pair, integer costs, so the chosen references -- and the symbols -- are
+ * exactly those of wga_bvcomp_symbols_range.  Needs a CUDA device (no fallback); the host threads then compress only
+ * the chosen candidate of every node. */
+int wga_bvcomp_symbols_range_gpu(const uint64_t* h_offsets, const uint32_t* h_succ, uint64_t first_node, uint64_t n_nodes,
+                                 uint64_t compression_window, uint64_t max_ref_count, uint64_t min_interval_length,
+                                 const wga_component_model* estimator_tables, uint64_t chunk_nodes, int threads,
+                                 wga_symbols** out);
+/* Parity hook: the cost of every (node, reference offset) candidate record, h_costs[n_nodes * (window + 1)]
+ * (UINT64_MAX: no such candidate), computed by the GPU kernel (use_gpu != 0) or by the host BvComp. */
+int wga_debug_bvcomp_costs(const uint64_t* h_offsets, const uint32_t* h_succ, uint64_t first_node, uint64_t n_nodes,
+                           uint64_t compression_window, uint64_t min_interval_length,
+                           const wga_component_model* estimator_tables, uint64_t chunk_nodes, int use_gpu,
+                           uint64_t* h_costs);
 uint64_t wga_symbols_len(const wga_symbols* s);
 const uint8_t* wga_symbols_components(const wga_symbols* s);
 const uint64_t* wga_symbols_values(const wga_symbols* s);

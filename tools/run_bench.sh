@@ -1,2 +1,1 @@
-timeout 1500 python bench.py --workload twitter-2010-shaped --random-nodes 10000000 --steps 5 > gpurun_out/bench_r02_twitter.json 2> gpurun_out/bench_r02_twitter.err; tail -3 gpurun_out/bench_r02_twitter.err
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:"k_entropy|k_resolve|k_plan|k_heads" -c 7 -o gpurun_out/prof_r02_final -f python tools/prof_decode.py eu-2015-host-shaped 1 > gpurun_out/ncu_r02_final.log 2>&1; tail -2 gpurun_out/ncu_r02_final.log
+WGA_TIMING=1 timeout 600 python tools/time_bvcomp.py eu-2015-host-shaped 2>&1 | tail -14

@@ -494,16 +494,18 @@ class ANSModel4EncoderBuilder:
 
 # ---- host front end pieces (bvcomp) ---------------------------------------------------------------
 def bvcomp_symbols(offsets, succ, compression_window=7, max_ref_count=3, min_interval_length=4,
-                   estimator_tables=None, chunk_nodes=0, threads=1, first_node=0):
+                   estimator_tables=None, chunk_nodes=0, threads=1, first_node=0, gpu_costing=False):
     """(components u8, symbols u64) that BvComp writes for a CSR graph, choosing references with the
     Log2Estimator (estimator_tables=None) or the EntropyEstimator built from the given tables.
-    first_node > 0: the CSR holds nodes [first_node, first_node + n) of a larger graph (one rank's share)."""
+    first_node > 0: the CSR holds nodes [first_node, first_node + n) of a larger graph (one rank's share).
+    gpu_costing: the candidate costs and the reference selection run on the GPU (same symbols)."""
     offsets = np.ascontiguousarray(offsets, np.uint64)
     succ = np.ascontiguousarray(succ, np.uint32)
     keep = []
     est = _tables_to_view(estimator_tables, keep) if estimator_tables is not None else None
     h = C.c_void_p()
-    _chk(lib().wga_bvcomp_symbols_range(_np(offsets), _np(succ), C.c_uint64(first_node), C.c_uint64(offsets.size - 1),
+    fn = lib().wga_bvcomp_symbols_range_gpu if gpu_costing else lib().wga_bvcomp_symbols_range
+    _chk(fn(_np(offsets), _np(succ), C.c_uint64(first_node), C.c_uint64(offsets.size - 1),
                                         C.c_uint64(compression_window), C.c_uint64(max_ref_count),
                                         C.c_uint64(min_interval_length), est, C.c_uint64(chunk_nodes), C.c_int(threads),
                                         C.byref(h)))
@@ -515,6 +517,21 @@ def bvcomp_symbols(offsets, succ, compression_window=7, max_ref_count=3, min_int
         C.memmove(vals.ctypes.data, lib().wga_symbols_values(h), n * 8)
     lib().wga_symbols_free(h)
     return comps, vals
+
+
+def bvcomp_costs(offsets, succ, compression_window=7, min_interval_length=4, estimator_tables=None, chunk_nodes=0,
+                 first_node=0, use_gpu=True):
+    """Cost of every (node, reference offset) candidate record -> u64[n, window + 1] (UINT64_MAX: no candidate)."""
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    succ = np.ascontiguousarray(succ, np.uint32)
+    keep = []
+    est = _tables_to_view(estimator_tables, keep) if estimator_tables is not None else None
+    n = offsets.size - 1
+    out = np.zeros((n, compression_window + 1), np.uint64)
+    _chk(lib().wga_debug_bvcomp_costs(_np(offsets), _np(succ), C.c_uint64(first_node), C.c_uint64(n),
+                                      C.c_uint64(compression_window), C.c_uint64(min_interval_length), est,
+                                      C.c_uint64(chunk_nodes), C.c_int(1 if use_gpu else 0), _np(out)))
+    return out
 
 
 def ans_encode(tables, components, symbols):

@@ -132,7 +132,7 @@ struct Candidate {
 }  // namespace
 
 uint64_t bvcomp_range(const NodeSource& src, uint64_t first, uint64_t last, const BvCompParams& p,
-                      const Estimator& est, SymbolStream& out) {
+                      const Estimator& est, SymbolStream& out, const uint16_t* choice, uint64_t choice_first) {
   const uint64_t W = p.window, L = p.min_interval_length;
   std::vector<std::vector<uint64_t>> lists(W + 1);
   std::vector<uint64_t> ref_counts(W + 1, 0);
@@ -151,6 +151,13 @@ uint64_t bvcomp_range(const NodeSource& src, uint64_t first, uint64_t last, cons
     cand[0].compress(cur, nullptr, L);
     if (W == 0) {
       cand[0].write(v, -1, L, tap);
+      continue;
+    }
+    if (choice) {  // the reference was chosen on the GPU: only the chosen candidate is compressed
+      const uint64_t best = choice[v - choice_first];
+      if (best > std::min<uint64_t>(W, v - first)) throw Error(WGA_E_ARG, "bad precomputed reference choice");
+      if (best) cand[best].compress(cur, &lists[(v - best) % (W + 1)], L);
+      cand[best].write(v, (int64_t)best, L, tap);
       continue;
     }
     uint64_t best_bits = cand[0].write(v, 0, L, cost);
@@ -181,9 +188,31 @@ uint64_t bvcomp_graph(const NodeSource& src, uint64_t n_nodes, const BvCompParam
   return bvcomp_nodes(src, 0, n_nodes, p, est, chunk_nodes, threads, out);
 }
 
+void bvcomp_costs_host(const NodeSource& src, uint64_t first, uint64_t n, const BvCompParams& p, const Estimator& est,
+                       uint64_t chunk_nodes, std::vector<uint64_t>& costs) {
+  const uint64_t W = p.window, L = p.min_interval_length;
+  costs.assign(n * (W + 1), ~0ull);
+  std::vector<std::vector<uint64_t>> lists(W + 1);
+  Candidate cand;
+  auto cost = [&](int c, uint64_t v) { return est.cost(c, v); };
+  for (uint64_t v = first; v < first + n; ++v) {
+    std::vector<uint64_t>& cur = lists[v % (W + 1)];
+    src(v, cur);
+    const uint64_t a = chunk_nodes ? std::max(first, v / chunk_nodes * chunk_nodes) : first;
+    cand.compress(cur, nullptr, L);
+    costs[(v - first) * (W + 1)] = cand.write(v, 0, L, cost);
+    for (uint64_t delta = 1; delta <= std::min<uint64_t>(W, v - a); ++delta) {
+      const std::vector<uint64_t>& ref = lists[(v - delta) % (W + 1)];
+      if (ref.empty()) continue;
+      cand.compress(cur, &ref, L);
+      costs[(v - first) * (W + 1) + delta] = cand.write(v, (int64_t)delta, L, cost);
+    }
+  }
+}
+
 uint64_t bvcomp_nodes(const NodeSource& src, uint64_t first, uint64_t last, const BvCompParams& p, const Estimator& est,
-                      uint64_t chunk_nodes, int threads, SymbolStream& out) {
-  if (chunk_nodes == 0) return bvcomp_range(src, first, last, p, est, out);
+                      uint64_t chunk_nodes, int threads, SymbolStream& out, const uint16_t* choice) {
+  if (chunk_nodes == 0) return bvcomp_range(src, first, last, p, est, out, choice, first);
   // chunks are aligned to multiples of chunk_nodes of the WHOLE graph, so that a node range compressed by one
   // rank gives the symbols the whole-graph run gives for those nodes
   const uint64_t c0 = first / chunk_nodes, c1 = (last + chunk_nodes - 1) / chunk_nodes;
@@ -199,7 +228,7 @@ uint64_t bvcomp_nodes(const NodeSource& src, uint64_t first, uint64_t last, cons
       try {
         for (uint64_t c = next.fetch_add(1); c < n_chunks; c = next.fetch_add(1)) {
           uint64_t a = std::max(first, (c0 + c) * chunk_nodes), b = std::min(last, (c0 + c + 1) * chunk_nodes);
-          arcs[c] = bvcomp_range(src, a, b, p, est, parts[c]);
+          arcs[c] = bvcomp_range(src, a, b, p, est, parts[c], choice, first);
         }
       } catch (const std::exception& e) {
         errs[t] = e.what();

@@ -1,4 +1,6 @@
 // extern "C" surface of libwgans (include/wga.h).
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <thread>
 
@@ -549,6 +551,62 @@ int wga_bvcomp_symbols_range(const uint64_t* h_offsets, const uint32_t* h_succ, 
     *out = s.release();
   });
 }
+int wga_bvcomp_symbols_range_gpu(const uint64_t* h_offsets, const uint32_t* h_succ, uint64_t first_node, uint64_t n_nodes,
+                                 uint64_t compression_window, uint64_t max_ref_count, uint64_t min_interval_length,
+                                 const wga_component_model* estimator_tables, uint64_t chunk_nodes, int threads,
+                                 wga_symbols** out) {
+  return guarded([&] {
+    if (!h_offsets || !out) throw Error(WGA_E_ARG, "null argument");
+    BvCompParams p{compression_window, max_ref_count, min_interval_length};
+    std::unique_ptr<wga_symbols> s(new wga_symbols());
+    NodeSource src = [&](uint64_t v, std::vector<uint64_t>& o) {
+      o.assign(h_succ + h_offsets[v - first_node], h_succ + h_offsets[v - first_node + 1]);
+    };
+    std::unique_ptr<Estimator> est;
+    if (estimator_tables) {
+      ComponentModel m[WGA_COMPONENTS];
+      view_to_models(estimator_tables, m);
+      est.reset(new Estimator(m));
+    } else est.reset(new Estimator());
+    std::vector<uint16_t> choice;
+    bvcomp_choose_gpu(h_offsets, h_succ, first_node, n_nodes, p, *est, chunk_nodes, choice, nullptr);
+    const auto t0 = std::chrono::steady_clock::now();
+    bvcomp_nodes(src, first_node, first_node + n_nodes, p, *est, chunk_nodes, threads, s->s,
+                 compression_window ? choice.data() : nullptr);
+    if (getenv("WGA_TIMING"))
+      fprintf(stderr, "[wga] host emission of the chosen records: %.3f s\n",
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    *out = s.release();
+  });
+}
+
+int wga_debug_bvcomp_costs(const uint64_t* h_offsets, const uint32_t* h_succ, uint64_t first_node, uint64_t n_nodes,
+                           uint64_t compression_window, uint64_t min_interval_length,
+                           const wga_component_model* estimator_tables, uint64_t chunk_nodes, int use_gpu,
+                           uint64_t* h_costs) {
+  return guarded([&] {
+    if (!h_offsets || !h_costs) throw Error(WGA_E_ARG, "null argument");
+    BvCompParams p{compression_window, 3, min_interval_length};
+    std::unique_ptr<Estimator> est;
+    if (estimator_tables) {
+      ComponentModel m[WGA_COMPONENTS];
+      view_to_models(estimator_tables, m);
+      est.reset(new Estimator(m));
+    } else est.reset(new Estimator());
+    std::vector<uint64_t> costs;
+    if (use_gpu) {
+      std::vector<uint16_t> choice;
+      bvcomp_choose_gpu(h_offsets, h_succ, first_node, n_nodes, p, *est, chunk_nodes, choice, &costs);
+    } else {
+      NodeSource src = [&](uint64_t v, std::vector<uint64_t>& o) {
+        o.assign(h_succ + h_offsets[v - first_node], h_succ + h_offsets[v - first_node + 1]);
+      };
+      bvcomp_costs_host(src, first_node, n_nodes, p, *est, chunk_nodes, costs);
+    }
+    std::memcpy(h_costs, costs.data(), costs.size() * 8);
+  });
+}
+
 int wga_bvcomp_symbols(const uint64_t* h_offsets, const uint32_t* h_succ, uint64_t n_nodes,
                        uint64_t compression_window, uint64_t max_ref_count, uint64_t min_interval_length,
                        const wga_component_model* estimator_tables, uint64_t chunk_nodes, int threads,
