@@ -215,6 +215,16 @@ uint64_t wga_model_sparse_count(wga_model* m);
 int wga_model_sparse_export(wga_model* m, uint8_t* h_components, uint64_t* h_symbols, uint64_t* h_counts);
 int wga_model_sparse_merge(wga_model* m, const uint8_t* h_components, const uint64_t* h_symbols,
                            const uint64_t* h_counts, uint64_t n);
+/* Sums the histograms of all ranks of an NCCL communicator (ncclComm_t passed as void*; `stream` = cudaStream_t):
+ * ncclAllReduce of the dense bins, ncclAllGather + merge of the sparse tail of large raw symbols.  Collective: every
+ * rank calls it once before wga_model_build, which then yields the identical tables on every rank.  NCCL is resolved
+ * at run time from the process (libnccl.so.2); WGA_E_UNSUPPORTED when it is not there. */
+int wga_model_allreduce(wga_model* m, void* nccl_comm, void* stream);
+/* Convenience for callers without NCCL code of their own: ncclGetUniqueId (128 bytes, to be sent to the other ranks by
+ * any means), ncclCommInitRank, ncclCommDestroy. */
+int wga_nccl_get_unique_id(void* out128);
+int wga_nccl_comm_init(int n_ranks, int rank, const void* id128, void** out_comm);
+void wga_nccl_comm_destroy(void* comm);
 /* build() (:80-271) on the GPU. out_tables[c].table points into memory owned by `m`. */
 int wga_model_build(wga_model* m, wga_component_model out_tables[WGA_COMPONENTS], double* h_original_cost9,
                     double* h_final_cost9);

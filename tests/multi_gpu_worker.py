@@ -38,6 +38,27 @@ def main():
     # ---- model build over the ranks: NCCL all-reduce of the histograms, tables against the oracle on the union
     ok = bench.nrank_model_parity(W, O, rank, world, dist)
     assert ok is None or ok is True
+    # ---- the same collective behind the C ABI (wga_model_allreduce on a raw ncclComm_t): identical tables
+    kind, n, deg, seed = bench.WORKLOADS["tiny"]
+    a, b = bench.node_split(4 * bench.CHUNK_NODES, world)[rank]
+    off_r, succ_r = W.synth_graph(kind, 4 * bench.CHUNK_NODES, deg, seed=seed, first=a, last=b, threads=4)
+    comps, syms = W.bvcomp_symbols(off_r, succ_r, chunk_nodes=bench.CHUNK_NODES, threads=4, first_node=a, **bench.BVCOMP)
+    syms = syms.copy()
+    syms[::97] += np.uint64(1) << np.uint64(30 + rank)  # some large raw symbols: they travel in the sparse tail
+    m1, m2 = W.ANSModel4EncoderBuilder(), W.ANSModel4EncoderBuilder()
+    m1.push_symbols(comps, syms)
+    m2.push_symbols(comps, syms)
+    m1.all_reduce()
+    comm = W.nccl_comm_from_torch()
+    m2.all_reduce_nccl(comm)
+    t1, t2 = m1.build()[0], m2.build()[0]
+    for c in range(9):
+        for f in ("frame_size", "radix", "fidelity"):
+            assert t1[c][f] == t2[c][f], (c, f)
+        assert t1[c]["entries"].size == t2[c]["entries"].size
+        for f in ("freq", "cumul_freq", "upperbound"):
+            assert (t1[c]["entries"][f] == t2[c]["entries"][f]).all(), (c, f)
+    W.nccl_comm_destroy(comm)
     dist.barrier()
     dist.destroy_process_group()
     print("rank %d ok: nodes [%d,%d) %d arcs" % (rank, first, last, succ.numel()))

@@ -1,1 +1,2 @@
-WGA_TIMING=1 timeout 600 python tools/time_bvcomp.py eu-2015-host-shaped 2>&1 | tail -14
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python -c "import __graft_entry__ as e; e.smoke()" 2>&1 | tail -1

@@ -483,6 +483,11 @@ class ANSModel4EncoderBuilder:
                 k = np.ascontiguousarray(k, np.uint64)
                 _chk(lib().wga_model_sparse_merge(self._h, _np(c), _np(s), _np(k), C.c_uint64(s.size)))
 
+    def all_reduce_nccl(self, comm, stream=None):
+        """wga_model_allreduce: the same collective behind the C ABI, on a raw ncclComm_t (see nccl_comm_from_torch)."""
+        st = C.c_void_p(stream if stream is not None else _torch().cuda.current_stream().cuda_stream)
+        _chk(lib().wga_model_allreduce(self._h, C.c_void_p(comm), st))
+
     def build(self):
         """-> (tables, original_cost[9], final_cost[9])"""
         arr = (_ComponentModel * COMPONENTS)()
@@ -490,6 +495,26 @@ class ANSModel4EncoderBuilder:
         fc = np.zeros(9)
         _chk(lib().wga_model_build(self._h, arr, _np(oc), _np(fc)))
         return _tables_from_view(arr), oc, fc
+
+
+def nccl_comm_from_torch(group=None):
+    """A raw NCCL communicator over the ranks of a torch.distributed group (the unique id travels through the
+    group): -> ncclComm_t as int, for ANSModel4EncoderBuilder.all_reduce_nccl / wga_model_allreduce.  Free it with
+    nccl_comm_destroy."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    uid = (C.c_char * 128)()
+    if rank == 0:
+        _chk(lib().wga_nccl_get_unique_id(uid))
+    box = [uid.raw]
+    dist.broadcast_object_list(box, src=0, group=group)
+    comm = C.c_void_p()
+    _chk(lib().wga_nccl_comm_init(C.c_int(world), C.c_int(rank), C.c_char_p(box[0]), C.byref(comm)))
+    return comm.value
+
+
+def nccl_comm_destroy(comm):
+    lib().wga_nccl_comm_destroy(C.c_void_p(comm))
 
 
 # ---- host front end pieces (bvcomp) ---------------------------------------------------------------
