@@ -702,15 +702,17 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
                                                      uint32_t exact_level, const uint32_t* lev, uint32_t minint,
                                                      uint32_t setup_batch) {
   __shared__ uint32_t s_hdr[RES_TPB * (HS + 1)];
-  __shared__ __align__(16) uint32_t s_stage[16 * RES_TPB];
+  __shared__ __align__(16) uint32_t s_stage[8 * RES_TPB];
   __shared__ uint32_t s_next;
   uint32_t* const hdr = s_hdr + threadIdx.x * (HS + 1);  // odd stride: conflict-free
-  // Output staging: a ring of 16 words per lane (word i at stg[i * RES_TPB]: conflict-free).  The successors go out
-  // as whole 32-byte sectors (two 16-byte stores) instead of one 4-byte store each -- every lane writes to its own
-  // list, so each scalar store is a separate L2 request, and those requests were what bound this kernel
-  // (lts__t_tag_requests 71 %).  Only the partial sectors at the two ends of a list are written word by word.
+  // Output staging: a ring of 8 words per lane (word i at stg[i * RES_TPB]: conflict-free).  The successors go out
+  // as aligned 16-byte stores instead of one 4-byte store each -- every lane writes to its own list, so each scalar
+  // store is a separate L2 request, and those requests were what bound this kernel (lts__t_tag_requests 71 %).
+  // Only the partial quads at the two ends of a list are written word by word (quads rather than whole 32-byte
+  // sectors: the same number of L2 requests, and the word-by-word code, which runs in nearly every step because
+  // some lane of the warp starts or ends a list, handles three words instead of seven).
   uint32_t* const stg = s_stage + threadIdx.x;
-  uint32_t A = 0;  // word offset of the slot inside its sector: list position p lives at sector position A + p
+  uint32_t A = 0;  // word offset of the slot inside its 16-byte quad: list position p lives at quad position A + p
   {  // the long lists of this level first (they take the longest): one warp each
     const uint32_t nh = min(*rv.hub_count, HUB_CAP);
     const uint32_t want = exact_level ? exact_level : lb;
@@ -770,7 +772,7 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
           d = nr.z;
           b = nr.w >> RT_BITS;
           out = node_slot(rv, t);
-          A = (uint32_t)(reinterpret_cast<uintptr_t>(out) >> 2) & 7u;
+          A = (uint32_t)(reinterpret_cast<uintptr_t>(out) >> 2) & 3u;
           ref = nullptr;
           dref = 0;
           if (rt) {
@@ -845,30 +847,28 @@ __global__ void __launch_bounds__(RES_TPB) k_resolve(RangeView rv, const uint32_
         const bool t1 = e1 < other, t2 = t1 && e2 < other, t3 = t2 && e3 < other;
         const uint32_t m = min(1u + (uint32_t)t1 + (uint32_t)t2 + (uint32_t)t3, d - p);
         const uint32_t q0 = A + p;
-        stg[(q0 & 15u) * RES_TPB] = mn;
-        if (m > 1) stg[((q0 + 1u) & 15u) * RES_TPB] = e1;
-        if (m > 2) stg[((q0 + 2u) & 15u) * RES_TPB] = e2;
-        if (m > 3) stg[((q0 + 3u) & 15u) * RES_TPB] = e3;
+        stg[(q0 & 7u) * RES_TPB] = mn;
+        if (m > 1) stg[((q0 + 1u) & 7u) * RES_TPB] = e1;
+        if (m > 2) stg[((q0 + 2u) & 7u) * RES_TPB] = e2;
+        if (m > 3) stg[((q0 + 3u) & 7u) * RES_TPB] = e3;
         const uint32_t nh = m == 1 ? e1 : m == 2 ? e2 : m == 3 ? e3 : e4;  // the run's next head
         p += m;
         {
-          const uint32_t q1 = A + p, s0 = q0 & ~7u;
-          const bool crossed = q1 >= s0 + 8u;
+          const uint32_t q1 = A + p, s0 = q0 & ~3u;
+          const bool crossed = q1 >= s0 + 4u;
           if (crossed || p == d) {
             uint32_t qa = s0 < A ? A : s0, qb = q1;  // staged and not yet written: [qa, qb)
-            if (crossed && s0 >= A) {  // a whole sector of this list
-              const uint32_t* r = stg + (s0 & 8u) * RES_TPB;
-              uint4* dst = reinterpret_cast<uint4*>(out + (s0 - A));
-              dst[0] = make_uint4(r[0], r[RES_TPB], r[2 * RES_TPB], r[3 * RES_TPB]);
-              dst[1] = make_uint4(r[4 * RES_TPB], r[5 * RES_TPB], r[6 * RES_TPB], r[7 * RES_TPB]);
-              qa = s0 + 8u;
-            } else if (crossed) qb = (p == d) ? q1 : s0 + 8u;  // (the list starts inside this sector)
-            if (p != d && !(crossed && s0 < A)) qb = qa;        // the open sector stays staged until it is complete
-            // (seven words at most inside one sector: no loop for them, the lanes of a warp have different counts)
+            if (crossed && s0 >= A) {  // a whole quad of this list
+              const uint32_t* r = stg + (s0 & 4u) * RES_TPB;
+              *reinterpret_cast<uint4*>(out + (s0 - A)) = make_uint4(r[0], r[RES_TPB], r[2 * RES_TPB], r[3 * RES_TPB]);
+              qa = s0 + 4u;
+            } else if (crossed) qb = (p == d) ? q1 : s0 + 4u;  // (the list starts inside this quad)
+            if (p != d && !(crossed && s0 < A)) qb = qa;        // the open quad stays staged until it is complete
+            // (three words at most inside one quad: no loop for them, the lanes of a warp have different counts)
 #pragma unroll
-            for (uint32_t j = 0; j < 7; ++j)
-              if (qa + j < qb) out[qa + j - A] = stg[((qa + j) & 15u) * RES_TPB];
-            for (uint32_t q = qa + 7u; q < qb; ++q) out[q - A] = stg[(q & 15u) * RES_TPB];  // (a short list that starts inside one sector and ends in the next)
+            for (uint32_t j = 0; j < 3; ++j)
+              if (qa + j < qb) out[qa + j - A] = stg[((qa + j) & 7u) * RES_TPB];
+            for (uint32_t q = qa + 3u; q < qb; ++q) out[q - A] = stg[(q & 7u) * RES_TPB];  // (a short list that starts inside one quad and ends in the next)
           }
         }
         if (is_c) {
