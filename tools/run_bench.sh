@@ -1,1 +1,3 @@
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:"k_entropy|k_resolve|k_plan|k_heads" -c 7 -o gpurun_out/prof_r02_final -f python tools/prof_decode.py eu-2015-host-shaped 1 > gpurun_out/ncu_r02_final.log 2>&1; tail -1 gpurun_out/ncu_r02_final.log
+# what a gpurun call usually runs: GPU tests, then the default bench line
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err
